@@ -1,0 +1,182 @@
+/*
+ * acb200.h -- C ABI of the B200-native Aho-Corasick batch-search path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / Python types.
+ * The reference (WojciechMula/pyahocorasick v2.2.0) has no C plugin ABI of its own --
+ * the path sits behind the CPython type `ahocorasick.Automaton`
+ * (src/Automaton.c:1204-1230 method table, src/pyahocorasick.c:67-137 module init).
+ * Each entry point below names the reference function whose role it takes over; the
+ * Python class pyahocorasick_b200.Automaton (ctypes) keeps the reference's signatures
+ * and exceptions on top of these calls.  INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function that can fail returns an int status: ACB_OK (0) or a negative
+ *     ACB_E* code; acb_last_error() returns a thread-local human-readable message.
+ *   - keys and haystacks are BYTE strings.  Wider letters (the reference's unicode
+ *     flavour, KEY_SEQUENCE) are passed as little-endian fixed-width letters with
+ *     `letter_bytes` in {1,2,4}; matches are only reported at letter boundaries and
+ *     end_index is counted in letters, exactly like the reference's index into
+ *     its TRIE_LETTER_TYPE array (src/common.h:51-67).
+ *   - the library never falls back to a CPU search: acb_scan_* fail with
+ *     ACB_ECUDA when no device / kernel image is available.
+ */
+#ifndef ACB200_H_INCLUDED
+#define ACB200_H_INCLUDED
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACB_ABI_VERSION 1
+
+enum {
+    ACB_OK        =  0,
+    ACB_ENOMEM    = -1,   /* -> MemoryError   (reference: PyErr_NoMemory everywhere)           */
+    ACB_EINVAL    = -2,   /* -> ValueError / TypeError at the Python layer                      */
+    ACB_ESTATE    = -3,   /* automaton not in the AHOCORASICK state (src/Automaton.c:886-891)   */
+    ACB_ECUDA     = -4,   /* CUDA runtime / launch failure, no device, no sm_100a image          */
+    ACB_EOVERFLOW = -5,   /* match buffer too small: *n_found holds the required capacity        */
+    ACB_ERANGE    = -6    /* size beyond what int32 state ids / end_index can hold               */
+};
+
+/* same numeric values as the reference's AutomatonKind (src/Automaton.h:16-20) */
+enum { ACB_EMPTY = 0, ACB_TRIE = 1, ACB_AHOCORASICK = 2 };
+
+/* One reported occurrence.  The Python layer maps key_id -> value so that
+ * (end_index, value) equals what src/AutomatonSearchIter.c:178-190 builds. */
+typedef struct acb_match {
+    int32_t hay_id;      /* index of the haystack inside the batch            */
+    int32_t end_index;   /* index of the LAST letter of the occurrence        */
+    int32_t key_id;      /* caller-chosen id given to acb_trie_add_word       */
+} acb_match;
+
+/* ------------------------------------------------------------------ host --- */
+
+/* Host-side trie + automaton.  Replaces the TrieNode/Pair heap graph
+ * (src/trienode.h:19-42) with an arena of int32 node ids. */
+typedef struct acb_trie acb_trie;
+
+acb_trie *acb_trie_new(int letter_bytes);                 /* automaton_new, src/Automaton.c:96-181 */
+void      acb_trie_free(acb_trie *t);
+int       acb_trie_clear(acb_trie *t);                    /* automaton_clear                       */
+
+/* trie_add_word (src/trie.c:14-63) + value slot of automaton_add_word
+ * (src/Automaton.c:201-300).  key_id >= 0 is stored on the terminal node.
+ * *prev_key_id receives the id previously stored there, or -1 for a new key.
+ * nbytes must be a positive multiple of letter_bytes; nbytes == 0 is a no-op that
+ * sets *prev_key_id = -2 (the reference returns False for an empty key, :257). */
+int acb_trie_add_word(acb_trie *t, const uint8_t *key, int64_t nbytes, int32_t key_id,
+                      int32_t *prev_key_id);
+
+/* trie_remove_word (src/trie.c:66-136): *key_id = removed id or -1 if absent. */
+int acb_trie_remove_word(acb_trie *t, const uint8_t *key, int64_t nbytes, int32_t *key_id);
+
+/* trie_find / automaton_exists / automaton_match (src/trie.c:139-155):
+ * *key_id = id of the key equal to `key` (or -1); *is_prefix = 1 when `key` is a
+ * prefix of at least one live key. */
+int acb_trie_find(const acb_trie *t, const uint8_t *key, int64_t nbytes, int32_t *key_id,
+                  int32_t *is_prefix);
+
+/* trie_longest (src/trie.c:158-174): number of leading LETTERS of `key` that
+ * follow existing edges. */
+int64_t acb_trie_longest_prefix(const acb_trie *t, const uint8_t *key, int64_t nbytes);
+
+/* automaton_make_automaton (src/Automaton.c:560-649): BFS failure links, then --
+ * new in this build -- flatten to the int32 tables the device scans.
+ * Returns ACB_OK; *built = 1 when the state went TRIE -> AHOCORASICK, 0 when there
+ * was nothing to do (the reference returns False, :574-575). */
+int acb_trie_make_automaton(acb_trie *t, int32_t *built);
+
+int     acb_trie_kind(const acb_trie *t);          /* ACB_EMPTY / ACB_TRIE / ACB_AHOCORASICK */
+int64_t acb_trie_count(const acb_trie *t);         /* live keys   (len(A))                   */
+int64_t acb_trie_longest_word(const acb_trie *t);  /* in letters  (Automaton.longest_word)   */
+int64_t acb_trie_nodes(const acb_trie *t);         /* live nodes  (get_stats nodes_count)    */
+int64_t acb_trie_links(const acb_trie *t);         /* live edges  (get_stats links_count)    */
+
+/* Read-only view of the flattened automaton (valid until the trie changes).
+ * State ids are BFS order, root = 0.  Used for upload and for white-box tests. */
+typedef struct acb_flat_view {
+    int32_t        n_states;      /* S                                                        */
+    int32_t        n_classes;     /* K; class 0 = "byte that occurs in no key"                */
+    int32_t        n_keys;        /* 1 + largest key_id                                       */
+    int32_t        letter_bytes;
+    int32_t        min_key_bytes; /* shortest live key                                        */
+    int32_t        max_key_bytes;
+    const uint8_t *byte_class;    /* [256]  byte -> class                                     */
+    const int32_t *goto_cm;       /* [K*S]  column-major: goto_cm[c*S+s] = child or -1        */
+    const int32_t *fail;          /* [S]    failure link, fail[0] = -1 (root has none, A12)   */
+    const int32_t *key_of;        /* [S]    key_id ending exactly at this state, or -1        */
+    const int32_t *out_ptr;       /* [S+1]  CSR over out_idx                                  */
+    const int32_t *out_idx;       /* key ids on the chain s, fail(s), ... (longest first)     */
+    const int32_t *key_len;       /* [n_keys] key length in LETTERS (0 = unused id)           */
+    /* prefilter (see DESIGN.md "gram filter") */
+    int32_t        gram_bytes;    /* g : bytes hashed per probe                               */
+    int32_t        stride;        /* s : probe every s-th byte position                       */
+    int32_t        log2_bits1;    /* stage-1 bitmap (shared memory) has 2^log2_bits1 bits     */
+    int32_t        log2_bits2;    /* stage-2 bitmap (global memory) has 2^log2_bits2 bits     */
+    const uint32_t *bitmap1;
+    const uint32_t *bitmap2;
+} acb_flat_view;
+
+int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out);
+
+/* ---------------------------------------------------------------- device --- */
+
+/* The flattened automaton resident in HBM of one GPU (uploaded once). */
+typedef struct acb_table acb_table;
+
+int  acb_device_count(int32_t *n);
+int  acb_table_upload(const acb_trie *t, int device, acb_table **out);
+void acb_table_free(acb_table *tb);
+int64_t acb_table_device_bytes(const acb_table *tb);
+
+/* which scan kernel to run */
+enum {
+    ACB_ALGO_AUTO   = 0,
+    ACB_ALGO_FILTER = 1,  /* gram-filter + trie walk (start-anchored), the fast path          */
+    ACB_ALGO_DFA    = 2   /* goto/fail automaton walk with CSR outputs, one lane per chunk     */
+};
+
+/* Batch scan, DEVICE buffers, asynchronous on `stream` (a cudaStream_t / CUstream).
+ * Replaces the loop in automaton_search_iter_next (src/AutomatonSearchIter.c:243-300)
+ * and automaton_find_all (src/Automaton.c:693-714) for a whole batch at once.
+ *
+ *   d_hay      : all haystacks back to back, total_bytes bytes
+ *   d_offsets  : n_hay+1 byte offsets (int64, multiples of letter_bytes), or NULL
+ *                when every haystack is `stride_bytes` long (haystack h = [h*stride, (h+1)*stride))
+ *   d_out/cap  : match records; records beyond cap are counted but not stored
+ *   d_count    : device int64; incremented by the number of matches found
+ *                (the caller zeroes it; order of records is unspecified)
+ */
+int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t total_bytes,
+                    const int64_t *d_offsets, int64_t n_hay, int64_t stride_bytes,
+                    acb_match *d_out, int64_t cap, int64_t *d_count,
+                    void *stream, int algo);
+
+/* Batch scan, HOST buffers: H2D copy of haystacks (+offsets), the kernel, and D2H of
+ * the count and the records, all inside the call (this is what `e2e` times).
+ * Returns ACB_EOVERFLOW (and the needed size in *n_found) when cap is too small.
+ * If sort != 0 the records come back in the reference's order:
+ * hay_id, then end_index ascending, then longest key first. */
+int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_bytes,
+                  const int64_t *offsets, int64_t n_hay, int64_t stride_bytes,
+                  acb_match *out, int64_t cap, int64_t *n_found, int algo, int sort);
+
+/* number of kernel launches issued by this library so far (bench.py's gpu_launches) */
+int64_t acb_launch_count(void);
+
+/* timing of the most recent scan kernel on its own stream, in milliseconds, measured
+ * with CUDA events recorded around the launch (0 when timing is disabled). */
+int   acb_set_kernel_timing(int enabled);
+float acb_last_kernel_ms(void);
+
+const char *acb_last_error(void);
+int         acb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACB200_H_INCLUDED */

@@ -1,0 +1,706 @@
+"""`Automaton` -- the reference's Python surface (src/Automaton.c:1204-1256) on top of the
+B200 C ABI (include/acb200.h).
+
+Host side (this file + csrc/acb_host.cpp): keys, values, state machine EMPTY -> TRIE ->
+AHOCORASICK, argument parsing and error behaviour of the reference.
+Device side (csrc/acb_device.cu): every search -- `iter`, `find_all`, and the batch entry
+`find_all_batch` -- runs on the GPU; there is no CPU search path in this package.
+
+Reference semantics are cited as file:line relative to /root/reference.
+"""
+from __future__ import annotations
+
+import ctypes
+import operator
+import pickle
+from typing import Any, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+# constants: src/Automaton.h:16-41, src/AutomatonItemsIter.h
+EMPTY, TRIE, AHOCORASICK = 0, 1, 2
+STORE_INTS, STORE_LENGTH, STORE_ANY = 10, 20, 30
+KEY_STRING, KEY_SEQUENCE = 100, 200
+MATCH_EXACT_LENGTH, MATCH_AT_MOST_PREFIX, MATCH_AT_LEAST_PREFIX = 0, 1, 2
+
+_INT_MIN, _INT_MAX = -(2 ** 31), 2 ** 31 - 1
+_LETTER_DTYPE = {1: np.uint8, 2: np.dtype("<u2"), 4: np.dtype("<u4")}
+
+
+def _to_c_int(v: int) -> int:
+    """Py_BuildValue("i", x) truncation of a Py_ssize_t."""
+    return ((int(v) + 2 ** 31) % 2 ** 32) - 2 ** 31
+
+
+def _parse_c_int(x, name="an integer"):
+    """PyArg 'i' format: int-like, must fit a C int."""
+    if isinstance(x, float):
+        raise TypeError(f"'float' object cannot be interpreted as an integer")
+    v = operator.index(x)
+    if not _INT_MIN <= v <= _INT_MAX:
+        raise OverflowError("signed integer is greater than maximum" if v > 0 else "signed integer is less than minimum")
+    return v
+
+
+_libc = ctypes.CDLL(None)
+_libc.iswspace.argtypes = [ctypes.c_uint]
+_libc.iswspace.restype = ctypes.c_int
+
+
+def _space_mask(letters: np.ndarray, bytes_flavour: bool) -> np.ndarray:
+    """iswspace() of every letter, as the reference evaluates it (src/AutomatonSearchIter.c:270-274).
+    The bytes flavour widens through a signed char first (src/utils.c:199-202)."""
+    if letters.size == 0:
+        return np.zeros(0, dtype=bool)
+    vals = letters.astype(np.uint32)
+    if bytes_flavour and letters.dtype == np.uint8:
+        vals = letters.astype(np.int8).astype(np.int16).astype(np.uint16).astype(np.uint32)
+    uniq = np.unique(vals)
+    spaces = np.array([u for u in uniq.tolist() if _libc.iswspace(u)], dtype=np.uint32)
+    return np.isin(vals, spaces)
+
+
+class Matches:
+    """Result of a batch search: parallel int32 arrays in the reference's order
+    (hay_id, then end_index ascending, then longest key first)."""
+
+    __slots__ = ("hay_id", "end_index", "key_id", "_values")
+
+    def __init__(self, rec: np.ndarray, values: list):
+        self.hay_id = rec["hay_id"]
+        self.end_index = rec["end_index"]
+        self.key_id = rec["key_id"]
+        self._values = values
+
+    def __len__(self):
+        return len(self.hay_id)
+
+    def values(self) -> list:
+        v = self._values
+        return [v[k] for k in self.key_id.tolist()]
+
+    def __iter__(self):
+        v = self._values
+        return iter([(h, e, v[k]) for h, e, k in zip(self.hay_id.tolist(), self.end_index.tolist(), self.key_id.tolist())])
+
+    def per_haystack(self, n_hay: int) -> List[List[Tuple[int, Any]]]:
+        """[[(end_index, value), ...] for each haystack] -- what looping iter() would give."""
+        out: List[List[Tuple[int, Any]]] = [[] for _ in range(n_hay)]
+        v = self._values
+        for h, e, k in zip(self.hay_id.tolist(), self.end_index.tolist(), self.key_id.tolist()):
+            out[h].append((e, v[k]))
+        return out
+
+
+class Automaton:
+    """Drop-in for ``ahocorasick.Automaton`` (src/Automaton.c:96-181 constructor)."""
+
+    _UNICODE = True           # flavour; the bytes flavour subclass overrides it
+
+    # ------------------------------------------------------------------ construction
+    def __init__(self, *args):
+        store, key_type = STORE_ANY, KEY_STRING
+        # src/Automaton.c:150-173: "ii" or "i"; anything else silently keeps the defaults
+        if len(args) == 2 and all(isinstance(a, int) for a in args):
+            store, key_type = args
+            self._check_store(store)
+            self._check_key_type(key_type)
+        elif len(args) == 1 and isinstance(args[0], int):
+            store = args[0]
+            self._check_store(store)
+        self._store = store
+        self._key_type = key_type
+        self._L = self._letter_bytes()
+        self._lib = N.lib()
+        self._trie = self._lib.acb_trie_new(self._L)
+        if not self._trie:
+            raise MemoryError(N.last_error())
+        self._key_ids: dict = {}          # key object -> key_id
+        self._key_objs: list = []         # key_id -> key object (None once removed)
+        self._values: list = []           # key_id -> value
+        self._version = 0
+        self._table = None                # acb_table* (device), created lazily
+        self._table_device = None
+        self._out_buf = None
+
+    @staticmethod
+    def _check_store(store):
+        if store not in (STORE_INTS, STORE_LENGTH, STORE_ANY):
+            raise ValueError("store value must be one of ahocorasick.STORE_LENGTH, STORE_INTS or STORE_ANY")
+
+    @staticmethod
+    def _check_key_type(key_type):
+        if key_type not in (KEY_STRING, KEY_SEQUENCE):
+            raise ValueError("key_type must have value KEY_STRING or KEY_SEQUENCE")
+
+    def _letter_bytes(self) -> int:
+        if self._key_type == KEY_SEQUENCE:
+            return 4 if self._UNICODE else 2      # TRIE_LETTER_TYPE, src/common.h:51-67
+        return 4 if self._UNICODE else 1
+
+    def __del__(self):
+        try:
+            self._drop_table()
+            if self._trie:
+                self._lib.acb_trie_free(self._trie)
+                self._trie = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ marshalling (src/utils.c:145-289)
+    def _letters(self, obj, required: bool = False) -> np.ndarray:
+        """key / haystack object -> array of letters (dtype by letter width)."""
+        if self._key_type == KEY_SEQUENCE:
+            if not isinstance(obj, tuple):
+                raise TypeError("tuple required" if required else "argument is not a supported sequence type")
+            hi = 2 ** 32 - 1 if self._UNICODE else 65535
+            out = np.empty(len(obj), dtype=_LETTER_DTYPE[self._L])
+            for i, item in enumerate(obj):
+                try:
+                    v = operator.index(item)
+                except TypeError:
+                    raise ValueError(f"item #{i} is not a number") from None
+                if v < 0 or v > hi:
+                    raise ValueError(f"item #{i}: value {v} outside range [0..{hi}]")
+                out[i] = v
+            return out
+        if self._UNICODE:
+            if not isinstance(obj, str):
+                raise TypeError("string required" if required else "string expected")
+            return np.frombuffer(obj.encode("utf-32-le", "surrogatepass"), dtype="<u4")
+        if not isinstance(obj, bytes):
+            raise TypeError("bytes required" if required else "bytes expected")
+        return np.frombuffer(obj, dtype=np.uint8)
+
+    def _hashable(self, key):
+        return key
+
+    # ------------------------------------------------------------------ dict-like part (host trie)
+    @property
+    def kind(self) -> int:
+        return self._lib.acb_trie_kind(self._trie)
+
+    @property
+    def store(self) -> int:
+        return self._store
+
+    def __len__(self):
+        return self._lib.acb_trie_count(self._trie)
+
+    def add_word(self, *args) -> bool:
+        """src/Automaton.c:201-300."""
+        if not args:
+            raise TypeError("add_word() requires a key")      # PyTuple_GetItem -> IndexError in the reference
+        key = args[0]
+        letters = self._letters(key)
+        n = len(letters)
+        if self._store == STORE_ANY:
+            if len(args) < 2:
+                raise ValueError("A value object is required as second argument.")
+            value = args[1]
+        elif self._store == STORE_INTS:
+            if len(args) >= 2:
+                v = args[1]
+                if not isinstance(v, (int, float, np.integer)) and not hasattr(v, "__index__"):
+                    raise TypeError("An integer value is required as second argument.")
+                try:
+                    iv = operator.index(v) if not isinstance(v, float) else None
+                except TypeError:
+                    iv = None
+                if iv is None:
+                    raise TypeError("'float' object cannot be interpreted as an integer")
+                if not -(2 ** 63) <= iv < 2 ** 63:
+                    raise ValueError("Python int too large to convert to C ssize_t")
+                value = _to_c_int(iv)
+            else:
+                value = _to_c_int(len(self) + 1)               # :238-243 default
+        else:
+            value = n                                           # STORE_LENGTH :245-247
+        if n == 0:
+            return False                                        # :257,295
+        hk = self._hashable(key)
+        kid = self._key_ids.get(hk)
+        new_id = len(self._values) if kid is None else kid
+        raw = letters.tobytes()
+        prev = ctypes.c_int32(-1)
+        N.check(self._lib.acb_trie_add_word(self._trie, raw, len(raw), new_id, ctypes.byref(prev)))
+        self._drop_table()                                      # kind is TRIE again (src/trie.c:60)
+        if kid is None:
+            self._key_ids[hk] = new_id
+            self._key_objs.append(key)
+            self._values.append(value)
+            self._version += 1                                  # :283-284
+            return True
+        self._values[kid] = value                               # replaced, version unchanged (A10)
+        return False
+
+    def _lookup(self, key):
+        letters = self._letters(key)
+        raw = letters.tobytes()
+        kid = ctypes.c_int32(-1)
+        pre = ctypes.c_int32(0)
+        N.check(self._lib.acb_trie_find(self._trie, raw, len(raw), ctypes.byref(kid), ctypes.byref(pre)))
+        return kid.value, bool(pre.value)
+
+    def exists(self, key) -> bool:
+        return self._lookup(key)[0] >= 0
+
+    __contains__ = exists
+
+    def match(self, key) -> bool:
+        if self.kind == EMPTY:
+            self._letters(key)
+            return False
+        return self._lookup(key)[1]
+
+    def longest_prefix(self, key) -> int:
+        letters = self._letters(key)
+        raw = letters.tobytes()
+        return int(self._lib.acb_trie_longest_prefix(self._trie, raw, len(raw)))
+
+    _MISSING = object()
+
+    def get(self, *args):
+        if not 1 <= len(args) <= 2:
+            raise TypeError(f"get() takes one or two arguments ({len(args)} given)")
+        kid, _ = self._lookup(args[0])
+        if kid >= 0:
+            return self._values[kid]
+        if len(args) == 2:
+            return args[1]
+        raise KeyError(args[0])
+
+    def _remove(self, key):
+        letters = self._letters(key)
+        if len(letters) == 0:
+            return None
+        raw = letters.tobytes()
+        kid = ctypes.c_int32(-1)
+        N.check(self._lib.acb_trie_remove_word(self._trie, raw, len(raw), ctypes.byref(kid)))
+        if kid.value < 0:
+            return None
+        k = kid.value
+        value = self._values[k]
+        self._key_ids.pop(self._hashable(self._key_objs[k]), None)
+        self._key_objs[k] = None
+        self._values[k] = None
+        self._version += 1
+        self._drop_table()
+        return (value,)
+
+    def remove_word(self, key) -> bool:
+        return self._remove(key) is not None
+
+    def pop(self, key):
+        r = self._remove(key)
+        if r is None:
+            raise KeyError(key)
+        return r[0]
+
+    def clear(self) -> None:
+        N.check(self._lib.acb_trie_clear(self._trie))
+        self._key_ids.clear()
+        self._key_objs = []
+        self._values = []
+        self._version += 1
+        self._drop_table()
+
+    # keys / values / items (src/AutomatonItemsIter.c) -- host-only enumeration
+    def _select(self, args):
+        prefix = None
+        wildcard = None
+        how = MATCH_EXACT_LENGTH
+        if len(args) >= 1 and args[0] is not None:
+            prefix = args[0]
+            self._letters(prefix)
+        if len(args) >= 2 and args[1] is not None:
+            wildcard = args[1]
+            wl = self._letters(wildcard)
+            if len(wl) != 1:
+                raise ValueError("Wildcard must be a single character.")
+        if len(args) >= 3:
+            how = args[2]
+            if how not in (MATCH_EXACT_LENGTH, MATCH_AT_MOST_PREFIX, MATCH_AT_LEAST_PREFIX):
+                raise ValueError("The optional how third argument must be one of: "
+                                 "MATCH_EXACT_LENGTH, MATCH_AT_LEAST_PREFIX or MATCH_AT_LEAST_PREFIX")
+        version = self._version
+        live = [(k, self._values[i]) for i, k in enumerate(self._key_objs) if k is not None]
+        if prefix is None:
+            sel = live
+        else:
+            p = list(self._letters(prefix).tolist())
+            w = None if wildcard is None else int(self._letters(wildcard)[0])
+            sel = []
+            for k, v in live:
+                kl = self._letters(k).tolist()
+                if w is None:
+                    ok = kl[:len(p)] == p
+                else:
+                    if how == MATCH_EXACT_LENGTH and len(kl) != len(p):
+                        continue
+                    if how == MATCH_AT_MOST_PREFIX and len(kl) > len(p):
+                        continue
+                    if how == MATCH_AT_LEAST_PREFIX and len(kl) < len(p):
+                        continue
+                    m = min(len(kl), len(p))
+                    ok = all(p[i] == w or p[i] == kl[i] for i in range(m))
+                if ok:
+                    sel.append((k, v))
+        return version, sel
+
+    def _guarded(self, version, seq):
+        for x in seq:
+            if version != self._version:
+                raise ValueError("underlaying automaton has changed, iterator is not valid anymore")
+            yield x
+
+    def keys(self, *args):
+        ver, sel = self._select(args)
+        return self._guarded(ver, [k for k, _ in sel])
+
+    def values(self, *args):
+        ver, sel = self._select(args)
+        return self._guarded(ver, [v for _, v in sel])
+
+    def items(self, *args):
+        ver, sel = self._select(args)
+        return self._guarded(ver, sel)
+
+    def __iter__(self):
+        return self.keys()
+
+    def get_stats(self) -> dict:
+        nodes = int(self._lib.acb_trie_nodes(self._trie))
+        links = int(self._lib.acb_trie_links(self._trie))
+        node_bytes = 28                                   # arena Node in csrc/acb_host.cpp
+        return dict(nodes_count=nodes, words_count=len(self), longest_word=int(self._lib.acb_trie_longest_word(self._trie)),
+                    links_count=links, sizeof_node=node_bytes, total_size=nodes * node_bytes + links * 12)
+
+    def __sizeof__(self):
+        return object.__sizeof__(self) + self.get_stats()["total_size"]
+
+    def __reduce__(self):
+        items = [(k, self._values[i]) for i, k in enumerate(self._key_objs) if k is not None]
+        return (_rebuild, (type(self)._UNICODE, self._store, self._key_type, items, self.kind == AHOCORASICK))
+
+    # ------------------------------------------------------------------ automaton
+    def make_automaton(self):
+        """src/Automaton.c:560-649 -> None when built, False when there was nothing to do."""
+        built = ctypes.c_int32(0)
+        N.check(self._lib.acb_trie_make_automaton(self._trie, ctypes.byref(built)))
+        if not built.value:
+            return False
+        self._version += 1                                 # :640
+        self._drop_table()
+        return None
+
+    def _drop_table(self):
+        if self._table is not None:
+            self._lib.acb_table_free(self._table)
+            self._table = None
+
+    def _ensure_table(self, device: Optional[int] = None):
+        if device is None:
+            device = _default_device()
+        if self._table is not None and self._table_device == device:
+            return self._table
+        self._drop_table()
+        tb = ctypes.c_void_p()
+        N.check(self._lib.acb_table_upload(self._trie, device, ctypes.byref(tb)))
+        self._table = tb
+        self._table_device = device
+        return tb
+
+    def flat(self) -> dict:
+        """White-box view of the flattened automaton (numpy copies) -- used by tests and docs."""
+        fv = N.FlatView()
+        N.check(self._lib.acb_trie_flat_view(self._trie, ctypes.byref(fv)))
+        S, K = fv.n_states, fv.n_classes
+
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].astype(dt, copy=True)
+        n_out = int(np.ctypeslib.as_array(fv.out_ptr, shape=(S + 1,))[S])
+        return dict(
+            n_states=S, n_classes=K, n_keys=fv.n_keys, letter_bytes=fv.letter_bytes,
+            min_key_bytes=fv.min_key_bytes, max_key_bytes=fv.max_key_bytes,
+            byte_class=arr(fv.byte_class, 256, np.uint8), goto_cm=arr(fv.goto_cm, K * S, np.int32).reshape(K, S),
+            fail=arr(fv.fail, S, np.int32), key_of=arr(fv.key_of, S, np.int32), out_ptr=arr(fv.out_ptr, S + 1, np.int32),
+            out_idx=arr(fv.out_idx, n_out, np.int32), key_len=arr(fv.key_len, fv.n_keys, np.int32),
+            gram_bytes=fv.gram_bytes, stride=fv.stride, log2_bits1=fv.log2_bits1, log2_bits2=fv.log2_bits2,
+            bitmap1=arr(fv.bitmap1, 1 << (fv.log2_bits1 - 5), np.uint32), bitmap2=arr(fv.bitmap2, 1 << (fv.log2_bits2 - 5), np.uint32))
+
+    # ------------------------------------------------------------------ GPU scan plumbing
+    def _scan_flat(self, flat: np.ndarray, offsets: Optional[np.ndarray], n_hay: int, stride_bytes: int,
+                   algo: str = "auto", sort: bool = True, device: Optional[int] = None) -> np.ndarray:
+        """flat uint8 buffer (+ int64 byte offsets or a fixed stride) -> sorted match records."""
+        tb = self._ensure_table(device)
+        total = int(flat.size)
+        cap = max(1 << 12, 2 * n_hay)
+        found = ctypes.c_int64(0)
+        while True:
+            if self._out_buf is None or len(self._out_buf) < cap:
+                self._out_buf = np.empty(cap, dtype=N.MATCH_DTYPE)
+            out = self._out_buf
+            rc = self._lib.acb_scan_host(tb, N.ptr(flat) if total else None, total,
+                                         N.ptr(offsets) if offsets is not None else None, n_hay, stride_bytes,
+                                         N.ptr(out), len(out), ctypes.byref(found), N.ALGOS[algo], 1 if sort else 0)
+            if rc == N.ACB_EOVERFLOW:
+                cap = int(found.value) + 1024
+                continue
+            N.check(rc)
+            return out[:found.value].copy()
+
+    def _scan_one(self, letters: np.ndarray, algo: str = "auto") -> np.ndarray:
+        flat = np.ascontiguousarray(letters).view(np.uint8)
+        if flat.size == 0:
+            return np.empty(0, dtype=N.MATCH_DTYPE)
+        return self._scan_flat(flat, None, 1, int(flat.size), algo=algo)
+
+    def _require_automaton(self):
+        if self.kind != AHOCORASICK:
+            raise AttributeError("Not an Aho-Corasick automaton yet: call add_word to add some keys and call "
+                                 "make_automaton to convert the trie to an automaton.")
+
+    # ------------------------------------------------------------------ search API of the reference
+    def iter(self, *args, **kwargs):
+        """src/Automaton.c:875-966: iter(string, [start, [end]], ignore_white_space=False)."""
+        self._require_automaton()
+        names = ("string", "start", "end", "ignore_white_space")
+        if len(args) > 4:
+            raise TypeError(f"function takes at most 4 arguments ({len(args)} given)")
+        vals = dict(zip(names, args))
+        for k, v in kwargs.items():
+            if k not in names:
+                raise TypeError(f"'{k}' is an invalid keyword argument for this function")
+            if k in vals:
+                raise TypeError(f"argument for function given by name ('{k}') and position")
+            vals[k] = v
+        if "string" not in vals:
+            raise TypeError("function missing required argument 'string' (pos 1)")
+        start = _parse_c_int(vals.get("start", -1))
+        end = _parse_c_int(vals.get("end", -1))
+        iws = _parse_c_int(vals.get("ignore_white_space", -1)) == 1          # :897-899 (A6)
+        letters = self._letters(vals["string"], required=True)
+        n = len(letters)
+        if start == -1:
+            start = 0                                                         # -1 = "not given" (A2)
+        if end == -1:
+            end = n
+        # the reference does not validate the range (A1: out-of-bounds read); parity is defined for
+        # 0 <= start <= end <= len, anything else is clamped
+        start = min(max(start, 0), n)
+        end = min(max(end, 0), n)
+        return AutomatonSearchIter(self, letters, start, end, iws)
+
+    def find_all(self, *args):
+        """src/Automaton.c:652-719: find_all(string, callback, [start, [end]])."""
+        if self.kind != AHOCORASICK:
+            return None                                                        # :666-667 (A4)
+        if len(args) < 1:
+            raise IndexError("tuple index out of range")
+        letters = self._letters(args[0])
+        if len(args) < 2:
+            raise IndexError("tuple index out of range")
+        callback = args[1]
+        if not callable(callback):
+            raise TypeError("The callback argument must be a callable such as a function.")
+        start, end = _parse_start_end(args, 2, 3, 0, len(letters))
+        if end > start:
+            rec = self._scan_one(letters[start:end])
+            values = self._values
+            for e, k in zip(rec["end_index"].tolist(), rec["key_id"].tolist()):
+                callback(e + start, values[k])
+        return None
+
+    def iter_long(self, *args):
+        raise NotImplementedError("iter_long is outside the B200 hot path in this round (SURVEY.md section 8(f) #1)")
+
+    def dump(self):
+        """(nodes, edges, fail) in the spirit of src/Automaton.c:1100-1180, with int state ids."""
+        f = self.flat()
+        S = f["n_states"]
+        inv = {int(c): b for b, c in enumerate(f["byte_class"].tolist()) if c != 0 or f["n_classes"] == 256}
+        nodes = [(s, int(f["key_of"][s] >= 0)) for s in range(S)]
+        edges = []
+        for c in range(f["n_classes"]):
+            col = f["goto_cm"][c]
+            for s in np.nonzero(col >= 0)[0].tolist():
+                edges.append((s, bytes([inv[c]]), int(col[s])))
+        fail = [(s, int(f["fail"][s])) for s in range(1, S)]
+        return nodes, edges, fail
+
+    # ------------------------------------------------------------------ the batch entry (new)
+    def find_all_batch(self, haystacks, *, algo: str = "auto", sort: bool = True, device: Optional[int] = None) -> Matches:
+        """Search a whole batch on the GPU.
+
+        haystacks: a sequence of bytes / str / tuple objects (as `iter` accepts), or a 2-D
+        C-contiguous uint8 array [n, stride] (bytes flavour: one haystack per row), or a pair
+        (flat uint8 array, int64 byte offsets of length n+1).
+
+        Equivalent to ``[(h, e, v) for h, hay in enumerate(haystacks) for e, v in A.iter(hay)]``
+        of the reference, returned as arrays.
+        """
+        self._require_automaton()
+        L = self._L
+        if isinstance(haystacks, np.ndarray):
+            if haystacks.dtype != np.uint8 or haystacks.ndim != 2 or not haystacks.flags.c_contiguous:
+                raise TypeError("array batches must be 2-D C-contiguous uint8 [n_haystacks, stride_bytes]")
+            n, stride = haystacks.shape
+            if stride % L:
+                raise ValueError("row length must be a multiple of the letter width")
+            rec = self._scan_flat(haystacks.reshape(-1), None, n, stride, algo=algo, sort=sort, device=device) if n and stride else np.empty(0, dtype=N.MATCH_DTYPE)
+            return Matches(rec, self._values)
+        if isinstance(haystacks, tuple) and len(haystacks) == 2 and isinstance(haystacks[0], np.ndarray) and isinstance(haystacks[1], np.ndarray):
+            flat = np.ascontiguousarray(haystacks[0], dtype=np.uint8).reshape(-1)
+            offs = np.ascontiguousarray(haystacks[1], dtype=np.int64)
+            if offs.ndim != 1 or len(offs) < 1 or offs[0] != 0 or offs[-1] != flat.size or np.any(np.diff(offs) < 0) or np.any(offs % L):
+                raise ValueError("offsets must be non-decreasing multiples of the letter width, start at 0 and end at len(flat)")
+            n = len(offs) - 1
+            rec = self._scan_flat(flat, offs, n, 0, algo=algo, sort=sort, device=device) if n and flat.size else np.empty(0, dtype=N.MATCH_DTYPE)
+            return Matches(rec, self._values)
+        parts = [np.ascontiguousarray(self._letters(h, required=True)).view(np.uint8) for h in haystacks]
+        n = len(parts)
+        lens = np.fromiter((p.size for p in parts), dtype=np.int64, count=n)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        flat = np.concatenate(parts) if n else np.empty(0, dtype=np.uint8)
+        rec = self._scan_flat(flat, offs, n, 0, algo=algo, sort=sort, device=device) if n and flat.size else np.empty(0, dtype=N.MATCH_DTYPE)
+        return Matches(rec, self._values)
+
+
+class AutomatonSearchIter:
+    """Result of `Automaton.iter()` (src/AutomatonSearchIter.c).  Matches of the current chunk are
+    produced by one GPU scan when the chunk is installed; `set()` continues the stream."""
+
+    def __init__(self, A: Automaton, letters: np.ndarray, start: int, end: int, ignore_ws: bool):
+        self._A = A
+        self._version = A._version                                  # :84
+        self._ignore_ws = ignore_ws
+        self._shift = 0
+        self._hist = letters[:0]                                    # consumed letters that can still start a match
+        self._pending: list = []
+        self._install(letters, start, end)
+        self._index = start - 1                                     # :123
+
+    def _install(self, letters, start, end):
+        """Scan letters[start:end] as the continuation of the stream."""
+        A = self._A
+        seg = letters[start:end]
+        if self._ignore_ws:
+            keep = ~_space_mask(seg, not A._UNICODE and A._key_type == KEY_STRING)
+            pos = np.nonzero(keep)[0] + start                       # original index of every kept letter
+            seg = seg[keep]
+        else:
+            pos = None
+        nh = len(self._hist)
+        data = np.concatenate([self._hist, seg]) if nh else seg
+        rec = A._scan_one(data) if len(data) else np.empty(0, dtype=N.MATCH_DTYPE)
+        ends = rec["end_index"]
+        sel = ends >= nh                                            # matches ending inside the history were reported before
+        ends = ends[sel] - nh
+        kids = rec["key_id"][sel]
+        idx = pos[ends] if pos is not None else ends + start
+        self._matches = list(zip(idx.tolist(), kids.tolist()))
+        self._cursor = 0
+        self._seg = seg
+        self._seg_pos = pos
+        self._start = start
+        self._end = end
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        A = self._A
+        if self._version != A._version:
+            raise ValueError("underlaying automaton has changed, iterator is not valid anymore")   # :247-250
+        if self._pending:                                           # outputs left over from before set()
+            k = self._pending.pop(0)
+            return (self._index + self._shift, A._values[k])
+        if self._cursor < len(self._matches):
+            i, k = self._matches[self._cursor]
+            self._cursor += 1
+            self._index = i
+            return (i + self._shift, A._values[k])
+        self._index = max(self._end, self._index + 1)               # where the reference's index stops
+        raise StopIteration
+
+    def set(self, *args):
+        """src/AutomatonSearchIter.c:303-368: set(string, reset=False)."""
+        if not args:
+            raise IndexError("tuple index out of range")
+        A = self._A
+        letters = A._letters(args[0])
+        reset = bool(args[1]) if len(args) > 1 else False
+        if reset:
+            self._hist = letters[:0]
+            self._shift = 0
+            self._pending = []
+        else:
+            # letters consumed so far = everything up to and including the current index
+            consumed_upto = self._index
+            if self._seg_pos is not None:
+                ncons = int(np.searchsorted(self._seg_pos, consumed_upto, side="right"))
+            else:
+                ncons = min(max(consumed_upto - self._start + 1, 0), len(self._seg))
+            keep = max(int(A._lib.acb_trie_longest_word(A._trie)) - 1, 0)
+            hist = np.concatenate([self._hist, self._seg[:ncons]])
+            self._hist = hist[len(hist) - keep:] if keep else hist[:0]
+            # outputs of the current position not yet returned stay pending (iter->output survives set())
+            if not self._pending:
+                self._pending = [k for i, k in self._matches[self._cursor:] if i == self._index]
+            self._shift += self._index if self._index >= 0 else 0   # :344-352
+        self._install(letters, 0, len(letters))
+        self._index = -1                                            # :354
+        return None
+
+
+# ---------------------------------------------------------------------- helpers
+def _parse_start_end(args, i_start, i_end, lo, hi):
+    """src/utils.c:293-359 (negative end is len-1+end, sic -- SURVEY A3)."""
+    start, end = lo, hi
+    if len(args) <= i_start:
+        return start, end
+    start = operator.index(args[i_start])
+    if start < 0:
+        start = hi + start
+    if start < lo or start >= hi:
+        raise IndexError(f"start index not in range {lo}..{hi}")
+    if len(args) <= i_end:
+        return start, end
+    end = operator.index(args[i_end])
+    if end < 0:
+        end = hi - 1 + end
+    if end < lo or end > hi:
+        raise IndexError(f"end index not in range {lo}..{hi}")
+    return start, end
+
+
+def _default_device() -> int:
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+def _rebuild(unicode_flavour, store, key_type, items, built):
+    from . import flavour
+    mod = flavour("unicode" if unicode_flavour else "bytes")
+    A = mod.Automaton(store, key_type)
+    for k, v in items:
+        if store == STORE_LENGTH:
+            A.add_word(k)
+        else:
+            A.add_word(k, v)
+    if built:
+        A.make_automaton()
+    return A
+
+
+def load(path, deserializer=pickle.loads):
+    raise NotImplementedError("save/load are outside the B200 hot path in this round (SURVEY.md section 8(f) #2)")

@@ -1,0 +1,638 @@
+/*
+ * acb_device.cu -- sm_100a scan kernels and the device half of the C ABI.
+ *
+ * Two kernels search a batch of haystacks stored back to back in HBM:
+ *
+ *  acb_filter_kernel<NW,STRIDE>   (ACB_ALGO_FILTER, the fast path)
+ *      Start-anchored search.  Every candidate start position is first tested
+ *      against a gram bitmap held in shared memory (stage 1), survivors against a
+ *      second, independent bitmap in global memory (stage 2), and only the few
+ *      that pass both walk the trie through the column-major goto table (stage 3).
+ *      No failure links are followed: an occurrence is found exactly once, by the
+ *      walk that starts at its first byte, so the result set equals what the
+ *      reference produces by walking fail chains at every position
+ *      (src/AutomatonSearchIter.c:157-197, src/Automaton.c:693-714).
+ *
+ *  acb_dfa_kernel                 (ACB_ALGO_DFA)
+ *      The textbook automaton: goto, else fail until root (src/trie.c:177-194),
+ *      outputs from CSR lists.  One lane per 64-byte span with a max_key-1 byte
+ *      warm-up.  Slower (every byte is a dependent L2 lookup) but insensitive to
+ *      key-set shape; also used to cross-check the filter kernel on the GPU.
+ *
+ * Match records are compacted per warp in shared memory and appended to the
+ * global buffer with one atomicAdd per warp flush.
+ */
+#include "acb_internal.h"
+#include "acb_hash.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            acb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,      \
+                          __LINE__, cudaGetErrorString(_e));                                 \
+            return ACB_ECUDA;                                                                \
+        }                                                                                    \
+    } while (0)
+
+namespace {
+
+constexpr int kThreads      = 1024;               /* one CTA per SM                         */
+constexpr int kWarps        = kThreads / 32;
+constexpr int kChunk        = 16;                 /* bytes per lane per iteration           */
+constexpr int kWarpBytes    = 32 * kChunk;        /* 512 B per warp iteration               */
+constexpr int kItersPerBlk  = 32;
+constexpr int kBlockBytes   = kWarpBytes * kItersPerBlk;   /* 16 KiB work unit per warp      */
+constexpr int kQueueCap     = 64;                 /* stage-1 survivors queued per warp      */
+constexpr int kStageCap     = 32;                 /* match records staged per warp          */
+constexpr uint32_t kFull    = 0xffffffffu;
+constexpr int32_t  kTermBit = 0x40000000;         /* goto entry flag: child ends a key      */
+constexpr int32_t  kIdMask  = 0x3fffffff;
+
+constexpr int kDfaSpan      = 64;                 /* bytes per lane in the DFA kernel       */
+constexpr int kDfaThreads   = 256;
+
+std::atomic<long long> g_launches{0};
+thread_local float g_last_ms = 0.f;
+std::atomic<int> g_timing{0};
+
+struct ScanParams {
+    const uint8_t *hay;
+    long long total;
+    const long long *offsets;      /* nullptr => fixed stride */
+    long long n_hay;
+    long long stride_bytes;
+    const uint8_t *cls;
+    const int32_t *gto;            /* flagged goto (kTermBit) */
+    const int32_t *fail;
+    const int32_t *key_of;
+    const int32_t *out_ptr;
+    const int32_t *out_idx;
+    const int32_t *key_len;
+    int32_t S;
+    int32_t L;
+    int32_t gram;
+    int32_t max_key_bytes;
+    const uint32_t *bm1;
+    const uint32_t *bm2;
+    int32_t log1, log2;
+    uint32_t mul1[ACB_MAX_WINDOWS];
+    uint32_t mul2[ACB_MAX_WINDOWS];
+    acb_match *out;
+    long long cap;
+    unsigned long long *count;
+    unsigned int *work_ctr;
+    long long n_blocks;
+};
+
+/* ---------------------------------------------------------------- helpers */
+
+__device__ __forceinline__ uint4 load_chunk(const uint8_t *hay, long long off, long long total) {
+    if (off + kChunk <= total) return __ldg(reinterpret_cast<const uint4 *>(hay + off));
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (off < total) {                       /* ragged tail of the buffer: byte-wise, zero filled */
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int i = 0; i < kChunk && off + i < total; i++) w[i >> 2] |= (uint32_t)hay[off + i] << (8 * (i & 3));
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return v;
+}
+
+__device__ __forceinline__ void find_haystack(const ScanParams &p, long long q, long long &h, long long &hs, long long &he) {
+    if (p.offsets == nullptr) {
+        h = q / p.stride_bytes;
+        hs = h * p.stride_bytes;
+        he = hs + p.stride_bytes;
+    } else {
+        long long lo = 0, hi = p.n_hay;       /* largest h with offsets[h] <= q */
+        while (hi - lo > 1) {
+            long long mid = (lo + hi) >> 1;
+            if (__ldg(p.offsets + mid) <= q) lo = mid; else hi = mid;
+        }
+        h = lo;
+        hs = __ldg(p.offsets + lo);
+        he = __ldg(p.offsets + lo + 1);
+    }
+}
+
+struct WarpStage {            /* per-warp match staging in shared memory */
+    acb_match *buf;
+    int *cnt;
+};
+
+__device__ __forceinline__ void emit(const ScanParams &p, const WarpStage &ws, int32_t h, int32_t e, int32_t k) {
+    acb_match m;
+    m.hay_id = h;
+    m.end_index = e;
+    m.key_id = k;
+    int slot = atomicAdd(ws.cnt, 1);
+    if (slot < kStageCap) {
+        ws.buf[slot] = m;
+    } else {                                  /* staging full: straight to global */
+        unsigned long long g = atomicAdd(p.count, 1ULL);
+        if (g < (unsigned long long)p.cap) p.out[g] = m;
+    }
+}
+
+/* all 32 lanes must call; flushes the staged records with one global atomic */
+__device__ __forceinline__ void flush_stage(const ScanParams &p, const WarpStage &ws, int lane) {
+    __syncwarp();
+    int n = *ws.cnt;
+    if (n > kStageCap) n = kStageCap;
+    if (n > 0) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.count, (unsigned long long)n);
+        base = __shfl_sync(kFull, base, 0);
+        if (lane < n && base + lane < (unsigned long long)p.cap) p.out[base + lane] = ws.buf[lane];
+    }
+    __syncwarp();
+    if (lane == 0) *ws.cnt = 0;
+    __syncwarp();
+}
+
+/* stage 3: walk the trie from every candidate start covered by the probe at q */
+template <int STRIDE>
+__device__ __forceinline__ void walk_candidates(const ScanParams &p, const WarpStage &ws, long long q) {
+    long long h, hs, he;
+    find_haystack(p, q, h, hs, he);
+    const int L = p.L;
+    for (int j = 0; j < STRIDE; j += L) {
+        long long start = q - j;
+        if (start < hs) break;
+        int32_t st = 0;
+        for (long long i = start; i < he; ++i) {
+            int c = __ldg(p.cls + p.hay[i]);
+            int32_t nx = __ldg(p.gto + (long long)c * p.S + st);
+            if (nx < 0) break;
+            st = nx & kIdMask;
+            if (nx & kTermBit) {
+                int32_t k = __ldg(p.key_of + st);
+                emit(p, ws, (int32_t)h, (int32_t)((i - hs + 1) / L - 1), k);
+            }
+        }
+    }
+}
+
+/* drain n (<= 32) queued stage-1 survivors: stage 2 then stage 3.  Warp-collective. */
+template <int STRIDE>
+__device__ __forceinline__ void drain(const ScanParams &p, const WarpStage &ws, const uint32_t *queue,
+                                      int &qhead, int &qn, int n, long long base, int lane) {
+    __syncwarp();
+    bool act = lane < n;
+    uint32_t e = act ? queue[(qhead + lane) & (kQueueCap - 1)] : 0u;
+    qhead = (qhead + n) & (kQueueCap - 1);
+    qn -= n;
+    if (act) {
+        long long q = base + e;
+        if (q + p.gram <= p.total) {
+            uint32_t h2 = acb_hash_bytes(p.hay + q, p.gram, p.mul2);
+            uint32_t idx = h2 >> (32 - p.log2);
+            if ((__ldg(p.bm2 + (idx >> 5)) >> (idx & 31)) & 1u) walk_candidates<STRIDE>(p, ws, q);
+        }
+    }
+    flush_stage(p, ws, lane);
+}
+
+/* ------------------------------------------------------- the filter kernel */
+
+template <int NW, int STRIDE>
+__global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const ScanParams p) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int nwords = 1 << (p.log1 - 5);
+    uint32_t *s_bm = smem;
+    uint32_t *s_queue = s_bm + nwords;                                   /* kWarps * kQueueCap   */
+    acb_match *s_stage = reinterpret_cast<acb_match *>(s_queue + kWarps * kQueueCap);   /* kWarps * kStageCap */
+    int *s_cnt = reinterpret_cast<int *>(s_stage + kWarps * kStageCap);  /* kWarps               */
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {   /* stage-1 bitmap -> shared memory, 16 B per thread per step */
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.bm1);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_bm);
+        for (int i = tid; i < nwords / 4; i += kThreads) dst[i] = __ldg(src + i);
+        if (tid < kWarps) s_cnt[tid] = 0;
+    }
+    __syncthreads();
+
+    uint32_t *queue = s_queue + warp * kQueueCap;
+    WarpStage ws;
+    ws.buf = s_stage + warp * kStageCap;
+    ws.cnt = s_cnt + warp;
+    const int shift1 = 32 - p.log1;
+    uint32_t mul[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) mul[k] = p.mul1[k];
+
+    for (;;) {
+        unsigned int blk = 0;
+        if (lane == 0) blk = atomicAdd(p.work_ctr, 1u);
+        blk = __shfl_sync(kFull, blk, 0);
+        if ((long long)blk >= p.n_blocks) break;
+        const long long base = (long long)blk * kBlockBytes;
+        int qhead = 0, qn = 0;
+
+        uint4 cur = load_chunk(p.hay, base + lane * kChunk, p.total);
+#pragma unroll 1
+        for (int it = 0; it < kItersPerBlk; ++it) {
+            const long long off = base + (long long)it * kWarpBytes + lane * kChunk;
+            if (base + (long long)it * kWarpBytes >= p.total) break;       /* warp-uniform */
+            /* prefetch the next iteration (on the last one only lane 0's chunk is needed, as look-ahead) */
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (it + 1 < kItersPerBlk || lane == 0) nxt = load_chunk(p.hay, off + kWarpBytes, p.total);
+
+            uint32_t W[4 + NW];
+            W[0] = cur.x; W[1] = cur.y; W[2] = cur.z; W[3] = cur.w;
+            {   /* look-ahead words: the next lane's chunk; lane 31 takes lane 0's next-iteration chunk */
+                const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
+                const uint32_t nw[4] = {nxt.x, nxt.y, nxt.z, nxt.w};
+#pragma unroll
+                for (int k = 0; k < NW; k++) {
+                    uint32_t a = __shfl_down_sync(kFull, cw[k], 1);
+                    uint32_t b = __shfl_sync(kFull, nw[k], 0);
+                    W[4 + k] = (lane == 31) ? b : a;
+                }
+            }
+            uint32_t hits = 0;
+#pragma unroll
+            for (int t = 0; t < kChunk; t += STRIDE) {
+                uint32_t h = 0;
+#pragma unroll
+                for (int k = 0; k < NW; k++) {
+                    const int wi = (t >> 2) + k;
+                    uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
+                    h += w * mul[k];
+                }
+                const uint32_t idx = h >> shift1;
+                const uint32_t word = s_bm[idx >> 5];
+                hits |= ((word >> (idx & 31)) & 1u) << t;
+            }
+            if (off + kChunk > p.total) {                                   /* positions past the end */
+                long long valid = p.total - off;
+                hits = (valid <= 0) ? 0u : (hits & ((1u << valid) - 1u));
+            }
+            /* queue the survivors (ballot-ranked append into the warp's ring) */
+            unsigned any = __ballot_sync(kFull, hits != 0);
+            while (any) {
+                if (hits) {
+                    int t = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    int rank = __popc(any & ((1u << lane) - 1u));
+                    queue[(qhead + qn + rank) & (kQueueCap - 1)] = (uint32_t)(it * kWarpBytes + lane * kChunk + t);
+                }
+                qn += __popc(any);
+                if (qn >= 32) drain<STRIDE>(p, ws, queue, qhead, qn, 32, base, lane);
+                any = __ballot_sync(kFull, hits != 0);
+            }
+            cur = nxt;
+        }
+        if (qn > 0) drain<STRIDE>(p, ws, queue, qhead, qn, qn, base, lane);
+    }
+    /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        unsigned int done = atomicAdd(p.work_ctr + 1, 1u);
+        if (done == gridDim.x - 1) {
+            p.work_ctr[0] = 0u;
+            p.work_ctr[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+/* ---------------------------------------------------------- the DFA kernel */
+
+__global__ void __launch_bounds__(kDfaThreads) acb_dfa_kernel(const ScanParams p) {
+    const long long span = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long a = span * kDfaSpan;
+    if (a >= p.total) return;
+    const long long b = (a + kDfaSpan < p.total) ? a + kDfaSpan : p.total;
+    long long h, hs, he;
+    find_haystack(p, a, h, hs, he);
+    /* with variable offsets, position a may sit in a run of empty haystacks: find_haystack
+       returns the last h with offsets[h] <= a, which is the non-empty one containing a */
+    long long i = a - p.max_key_bytes;               /* warm-up start, letter aligned */
+    if (i < hs) i = hs;
+    int32_t st = 0;
+    const int L = p.L;
+    for (; i < b; ++i) {
+        while (i >= he) {                             /* crossed into the next haystack(s) */
+            h += 1; hs = he;
+            he = (p.offsets == nullptr) ? hs + p.stride_bytes : __ldg(p.offsets + h + 1);
+            st = 0;
+        }
+        const long long col = (long long)__ldg(p.cls + p.hay[i]) * p.S;
+        int32_t nx;
+        while ((nx = __ldg(p.gto + col + st)) < 0 && st != 0) st = __ldg(p.fail + st);   /* src/trie.c:182-190 */
+        st = (nx < 0) ? 0 : (nx & kIdMask);
+        if (i >= a && st != 0 && ((i + 1 - hs) % L) == 0) {
+            const int32_t o0 = __ldg(p.out_ptr + st), o1 = __ldg(p.out_ptr + st + 1);
+            for (int32_t o = o0; o < o1; ++o) {
+                const int32_t k = __ldg(p.out_idx + o);
+                const long long kb = (long long)__ldg(p.key_len + k) * L;
+                if (i + 1 - kb < hs) continue;        /* cannot happen (state resets at hs); defensive */
+                unsigned long long g = atomicAdd(p.count, 1ULL);
+                if (g < (unsigned long long)p.cap) {
+                    acb_match m;
+                    m.hay_id = (int32_t)h;
+                    m.end_index = (int32_t)((i - hs + 1) / L - 1);
+                    m.key_id = k;
+                    p.out[g] = m;
+                }
+            }
+        }
+    }
+}
+
+} // namespace
+
+/* ------------------------------------------------------------- the table */
+
+struct acb_table {
+    int device = 0;
+    int sm_count = 0;
+    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log2 = 15;
+    int32_t min_key_bytes = 0, max_key_bytes = 0;
+    uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
+    uint8_t *d_cls = nullptr;
+    int32_t *d_goto = nullptr, *d_fail = nullptr, *d_keyof = nullptr, *d_outptr = nullptr, *d_outidx = nullptr, *d_keylen = nullptr;
+    uint32_t *d_bm1 = nullptr, *d_bm2 = nullptr;
+    unsigned int *d_work = nullptr;
+    long long dev_bytes = 0;
+    std::vector<int32_t> key_len;            /* host copy, for sorting records */
+    /* workspace of acb_scan_host */
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint8_t *w_hay = nullptr; size_t w_hay_cap = 0;
+    long long *w_off = nullptr; size_t w_off_cap = 0;
+    acb_match *w_out = nullptr; size_t w_out_cap = 0;
+    unsigned long long *w_count = nullptr;
+    unsigned long long *h_count = nullptr;   /* pinned */
+    acb_match *h_out = nullptr; size_t h_out_cap = 0;   /* pinned staging for the records */
+};
+
+extern "C" int acb_device_count(int32_t *n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { acb_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); if (n) *n = 0; return ACB_ECUDA; }
+    if (n) *n = c;
+    return ACB_OK;
+}
+
+template <typename T>
+static int upload(T **dst, const T *src, size_t n, long long &acc) {
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    bytes = (bytes + 15) & ~(size_t)15;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(dst), bytes));
+    CUDA_TRY(cudaMemset(*dst, 0, bytes));
+    if (n) CUDA_TRY(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    acc += (long long)bytes;
+    return ACB_OK;
+}
+
+extern "C" void acb_table_free(acb_table *tb) {
+    if (!tb) return;
+    cudaSetDevice(tb->device);
+    cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
+    cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_bm2);
+    cudaFree(tb->d_work); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
+    if (tb->h_count) cudaFreeHost(tb->h_count);
+    if (tb->h_out) cudaFreeHost(tb->h_out);
+    if (tb->ev0) cudaEventDestroy(tb->ev0);
+    if (tb->ev1) cudaEventDestroy(tb->ev1);
+    if (tb->stream) cudaStreamDestroy(tb->stream);
+    delete tb;
+}
+
+extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) {
+    if (!t || !out) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    *out = nullptr;
+    acb_flat_view f;
+    int rc = acb_trie_flat_view(t, &f);
+    if (rc != ACB_OK) return rc;
+    if (f.n_states > kIdMask) { acb_set_error("too many states for the device table (%d)", f.n_states); return ACB_ERANGE; }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { acb_set_error("no such CUDA device %d (have %d)", device, ndev); return ACB_ECUDA; }
+    CUDA_TRY(cudaSetDevice(device));
+    acb_table *tb = new (std::nothrow) acb_table();
+    if (!tb) { acb_set_error("out of memory"); return ACB_ENOMEM; }
+    tb->device = device;
+    cudaDeviceProp prop;
+    rc = ACB_OK;
+    do {
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { acb_set_error("cudaGetDeviceProperties failed"); rc = ACB_ECUDA; break; }
+        tb->sm_count = prop.multiProcessorCount;
+        tb->S = f.n_states; tb->K = f.n_classes; tb->L = f.letter_bytes; tb->n_keys = f.n_keys;
+        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log2 = f.log2_bits2;
+        tb->min_key_bytes = f.min_key_bytes; tb->max_key_bytes = f.max_key_bytes;
+        acb_hash_multipliers(tb->gram, 1, tb->mul1);
+        acb_hash_multipliers(tb->gram, 2, tb->mul2);
+        tb->key_len.assign(f.key_len, f.key_len + f.n_keys);
+        /* goto entries get a flag bit when the child ends a key, saving a key_of lookup per step */
+        std::vector<int32_t> flagged((size_t)f.n_classes * f.n_states);
+        for (size_t i = 0; i < flagged.size(); i++) {
+            int32_t v = f.goto_cm[i];
+            flagged[i] = (v >= 0 && f.key_of[v] >= 0) ? (v | kTermBit) : v;
+        }
+        if ((rc = upload(&tb->d_cls, f.byte_class, 256, tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_goto, flagged.data(), flagged.size(), tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_fail, f.fail, (size_t)f.n_states, tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_keyof, f.key_of, (size_t)f.n_states, tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_outptr, f.out_ptr, (size_t)f.n_states + 1, tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_outidx, f.out_idx, (size_t)f.out_ptr[f.n_states], tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_keylen, f.key_len, (size_t)f.n_keys, tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_bm1, f.bitmap1, (size_t)1 << (f.log2_bits1 - 5), tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_bm2, f.bitmap2, (size_t)1 << (f.log2_bits2 - 5), tb->dev_bytes))) break;
+        unsigned int zero[2] = {0, 0};      /* [0] next work unit, [1] CTAs finished (re-armed by the kernel) */
+        if ((rc = upload(&tb->d_work, zero, 2, tb->dev_bytes))) break;
+    } while (0);
+    if (rc != ACB_OK) { acb_table_free(tb); return rc; }
+    *out = tb;
+    return ACB_OK;
+}
+
+extern "C" int64_t acb_table_device_bytes(const acb_table *tb) { return tb ? tb->dev_bytes : 0; }
+extern "C" int64_t acb_launch_count(void) { return g_launches.load(); }
+extern "C" int acb_set_kernel_timing(int enabled) { g_timing.store(enabled ? 1 : 0); return ACB_OK; }
+extern "C" float acb_last_kernel_ms(void) { return g_last_ms; }
+
+/* ------------------------------------------------------------- launching */
+
+static size_t filter_smem_bytes(int log1) {
+    return ((size_t)1 << (log1 - 3)) + (size_t)kWarps * kQueueCap * 4 + (size_t)kWarps * kStageCap * sizeof(acb_match) + (size_t)kWarps * 4;
+}
+
+template <int NW, int STRIDE>
+static int launch_filter_t(const ScanParams &p, int grid, size_t smem, cudaStream_t s) {
+    auto kern = acb_filter_kernel<NW, STRIDE>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return ACB_OK;
+}
+
+template <int NW>
+static int launch_filter_s(const ScanParams &p, int stride, int grid, size_t smem, cudaStream_t s) {
+    switch (stride) {
+        case 1:  return launch_filter_t<NW, 1>(p, grid, smem, s);
+        case 2:  return launch_filter_t<NW, 2>(p, grid, smem, s);
+        case 4:  return launch_filter_t<NW, 4>(p, grid, smem, s);
+        case 8:  return launch_filter_t<NW, 8>(p, grid, smem, s);
+        case 16: return launch_filter_t<NW, 16>(p, grid, smem, s);
+    }
+    acb_set_error("unsupported filter stride %d", stride);
+    return ACB_EINVAL;
+}
+
+static int launch_filter(const ScanParams &p, int stride, int grid, size_t smem, cudaStream_t s) {
+    switch ((p.gram + 3) / 4) {
+        case 1: return launch_filter_s<1>(p, stride, grid, smem, s);
+        case 2: return launch_filter_s<2>(p, stride, grid, smem, s);
+        case 3: return launch_filter_s<3>(p, stride, grid, smem, s);
+        case 4: return launch_filter_s<4>(p, stride, grid, smem, s);
+    }
+    acb_set_error("unsupported gram length %d", p.gram);
+    return ACB_EINVAL;
+}
+
+extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t total_bytes,
+                               const int64_t *d_offsets, int64_t n_hay, int64_t stride_bytes,
+                               acb_match *d_out, int64_t cap, int64_t *d_count, void *stream, int algo) {
+    if (!tb || !d_count || total_bytes < 0 || n_hay < 0 || cap < 0 || (cap > 0 && !d_out)) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    if (n_hay > 0x7fffffffLL) { acb_set_error("more than 2^31-1 haystacks in one batch"); return ACB_ERANGE; }
+    if (!d_offsets) {
+        if (stride_bytes <= 0 || stride_bytes % tb->L || stride_bytes * n_hay != total_bytes) {
+            acb_set_error("fixed-stride batch needs stride_bytes > 0, a multiple of letter_bytes, and n_hay*stride == total_bytes");
+            return ACB_EINVAL;
+        }
+        if (stride_bytes / tb->L > 0x7fffffffLL) { acb_set_error("haystack longer than 2^31-1 letters"); return ACB_ERANGE; }
+    }
+    if (total_bytes == 0 || n_hay == 0) return ACB_OK;
+    if (reinterpret_cast<uintptr_t>(d_hay) & 15) { acb_set_error("d_hay must be 16-byte aligned"); return ACB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(tb->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.hay = d_hay; p.total = total_bytes; p.offsets = reinterpret_cast<const long long *>(d_offsets);
+    p.n_hay = n_hay; p.stride_bytes = stride_bytes;
+    p.cls = tb->d_cls; p.gto = tb->d_goto; p.fail = tb->d_fail; p.key_of = tb->d_keyof;
+    p.out_ptr = tb->d_outptr; p.out_idx = tb->d_outidx; p.key_len = tb->d_keylen;
+    p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.max_key_bytes = tb->max_key_bytes;
+    p.bm1 = tb->d_bm1; p.bm2 = tb->d_bm2; p.log1 = tb->log1; p.log2 = tb->log2;
+    memcpy(p.mul1, tb->mul1, sizeof(p.mul1));
+    memcpy(p.mul2, tb->mul2, sizeof(p.mul2));
+    p.out = d_out; p.cap = cap; p.count = reinterpret_cast<unsigned long long *>(d_count);
+    p.work_ctr = tb->d_work;
+    p.n_blocks = (total_bytes + kBlockBytes - 1) / kBlockBytes;
+
+    if (algo == ACB_ALGO_AUTO) algo = ACB_ALGO_FILTER;
+    if (tb->n_keys == 0) return ACB_OK;                     /* empty key set: nothing can match */
+    const bool timing = g_timing.load() != 0;
+    if (timing) {
+        if (!tb->ev0) { CUDA_TRY(cudaEventCreate(&tb->ev0)); CUDA_TRY(cudaEventCreate(&tb->ev1)); }
+        CUDA_TRY(cudaEventRecord(tb->ev0, s));
+    }
+    int rc;
+    if (algo == ACB_ALGO_FILTER) {
+        if (p.n_blocks > 0xfffffff0LL) { acb_set_error("batch too large for one launch"); return ACB_ERANGE; }
+        size_t smem = filter_smem_bytes(tb->log1);
+        int grid = (int)std::min<long long>(tb->sm_count, p.n_blocks);
+        rc = launch_filter(p, tb->stride, grid, smem, s);
+    } else if (algo == ACB_ALGO_DFA) {
+        long long spans = (total_bytes + kDfaSpan - 1) / kDfaSpan;
+        long long grid = (spans + kDfaThreads - 1) / kDfaThreads;
+        if (grid > 0x7fffffffLL) { acb_set_error("batch too large for one launch"); return ACB_ERANGE; }
+        acb_dfa_kernel<<<(unsigned)grid, kDfaThreads, 0, s>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { acb_set_error("DFA kernel launch failed: %s", cudaGetErrorString(e)); return ACB_ECUDA; }
+        g_launches.fetch_add(1);
+        rc = ACB_OK;
+    } else {
+        acb_set_error("unknown algo %d", algo);
+        return ACB_EINVAL;
+    }
+    if (rc != ACB_OK) return rc;
+    if (timing) {
+        CUDA_TRY(cudaEventRecord(tb->ev1, s));
+        CUDA_TRY(cudaEventSynchronize(tb->ev1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, tb->ev0, tb->ev1));
+        g_last_ms = ms;
+    }
+    return ACB_OK;
+}
+
+/* ------------------------------------------------------- host-buffer scan */
+
+template <typename T>
+static int ensure(T **buf, size_t *cap, size_t need) {
+    if (*cap >= need && *buf) return ACB_OK;
+    if (*buf) { cudaFree(*buf); *buf = nullptr; *cap = 0; }
+    size_t n = std::max<size_t>(need + need / 4, 1024);
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(buf), n * sizeof(T)));
+    *cap = n;
+    return ACB_OK;
+}
+
+extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_bytes,
+                             const int64_t *offsets, int64_t n_hay, int64_t stride_bytes,
+                             acb_match *out, int64_t cap, int64_t *n_found, int algo, int sort) {
+    if (!tb || !n_found || total_bytes < 0 || n_hay < 0 || cap < 0) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    *n_found = 0;
+    if (total_bytes == 0 || n_hay == 0) return ACB_OK;
+    CUDA_TRY(cudaSetDevice(tb->device));
+    if (!tb->stream) CUDA_TRY(cudaStreamCreateWithFlags(&tb->stream, cudaStreamNonBlocking));
+    if (!tb->w_count) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->w_count), sizeof(unsigned long long)));
+    if (!tb->h_count) CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&tb->h_count), sizeof(unsigned long long)));
+    int rc;
+    if ((rc = ensure(&tb->w_hay, &tb->w_hay_cap, (size_t)total_bytes + 64))) return rc;
+    if (offsets && (rc = ensure(&tb->w_off, &tb->w_off_cap, (size_t)n_hay + 1))) return rc;
+    if ((rc = ensure(&tb->w_out, &tb->w_out_cap, (size_t)std::max<int64_t>(cap, 1)))) return rc;
+    cudaStream_t s = tb->stream;
+    CUDA_TRY(cudaMemcpyAsync(tb->w_hay, hay, (size_t)total_bytes, cudaMemcpyHostToDevice, s));
+    if (offsets) CUDA_TRY(cudaMemcpyAsync(tb->w_off, offsets, (size_t)(n_hay + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(tb->w_count, 0, sizeof(unsigned long long), s));
+    rc = acb_scan_device(tb, tb->w_hay, total_bytes, offsets ? reinterpret_cast<const int64_t *>(tb->w_off) : nullptr,
+                         n_hay, stride_bytes, tb->w_out, cap, reinterpret_cast<int64_t *>(tb->w_count), s, algo);
+    if (rc != ACB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(tb->h_count, tb->w_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    unsigned long long n = *tb->h_count;
+    *n_found = (int64_t)n;
+    if (n > (unsigned long long)cap) {
+        acb_set_error("match buffer too small: %llu matches, capacity %lld", n, (long long)cap);
+        return ACB_EOVERFLOW;
+    }
+    if (n) {
+        if (tb->h_out_cap < n) {                               /* pinned staging: D2H at full PCIe rate */
+            if (tb->h_out) { cudaFreeHost(tb->h_out); tb->h_out = nullptr; tb->h_out_cap = 0; }
+            size_t want = (size_t)n + (size_t)n / 4 + 1024;
+            CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&tb->h_out), want * sizeof(acb_match)));
+            tb->h_out_cap = want;
+        }
+        CUDA_TRY(cudaMemcpyAsync(tb->h_out, tb->w_out, (size_t)n * sizeof(acb_match), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (sort) {
+            const int32_t *kl = tb->key_len.data();
+            std::sort(tb->h_out, tb->h_out + n, [kl](const acb_match &a, const acb_match &b) {
+                if (a.hay_id != b.hay_id) return a.hay_id < b.hay_id;
+                if (a.end_index != b.end_index) return a.end_index < b.end_index;
+                return kl[a.key_id] > kl[b.key_id];            /* longest first: fail-chain order */
+            });
+        }
+        memcpy(out, tb->h_out, (size_t)n * sizeof(acb_match));
+    }
+    return ACB_OK;
+}

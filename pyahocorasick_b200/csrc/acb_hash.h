@@ -1,0 +1,79 @@
+/*
+ * acb_hash.h -- the gram hash shared by the host (filter construction, acb_host.cpp)
+ * and the device (probing, acb_device.cu).  Both sides MUST compute identical values.
+ *
+ * A gram is g <= 16 consecutive bytes.  It is read as NW = ceil(g/4) little-endian
+ * 32-bit windows w_0..w_{NW-1}; bytes past g inside the last window are cancelled by
+ * giving that window a multiplier whose low 8*(4*NW-g) bits are zero (multiplication
+ * mod 2^32 then ignores the high bytes of the window), so the probe loop needs no
+ * masking instruction.
+ *
+ *      h  = sum_k  w_k * mul[k]      (mod 2^32)
+ *      bit index = h >> (32 - log2_bits)
+ *
+ * Stage 1 (shared-memory bitmap) and stage 2 (global bitmap) use different odd
+ * multiplier sets so that their false positives are independent.
+ */
+#ifndef ACB_HASH_H_INCLUDED
+#define ACB_HASH_H_INCLUDED
+
+#include <stdint.h>
+
+#define ACB_MAX_GRAM 16
+#define ACB_MAX_WINDOWS 4
+
+#if defined(__CUDACC__)
+#define ACB_HD __host__ __device__ __forceinline__
+#else
+#define ACB_HD static inline
+#endif
+
+/* odd 32-bit constants (golden-ratio / murmur / xxhash finalizer primes) */
+#define ACB_S1_M0 0x9E3779B1u
+#define ACB_S1_M1 0x85EBCA77u
+#define ACB_S1_M2 0xC2B2AE3Du
+#define ACB_S1_M3 0x27D4EB2Fu
+#define ACB_S2_M0 0x165667B1u
+#define ACB_S2_M1 0xD3A2646Du
+#define ACB_S2_M2 0xFD7046C5u
+#define ACB_S2_M3 0xB55A4F09u
+
+/* fill mul[0..3] for a gram of g bytes; stage = 1 or 2 */
+ACB_HD void acb_hash_multipliers(int g, int stage, uint32_t mul[ACB_MAX_WINDOWS]) {
+    const uint32_t base1[4] = {ACB_S1_M0, ACB_S1_M1, ACB_S1_M2, ACB_S1_M3};
+    const uint32_t base2[4] = {ACB_S2_M0, ACB_S2_M1, ACB_S2_M2, ACB_S2_M3};
+    int nw = (g + 3) / 4;
+    for (int k = 0; k < ACB_MAX_WINDOWS; k++) {
+        uint32_t m = (stage == 1) ? base1[k] : base2[k];
+        if (k >= nw) m = 0;
+        else if (k == nw - 1) {
+            int unused = 4 * nw - g;          /* high bytes of the last window to ignore */
+            m = (unused >= 4) ? 0u : (m << (8 * unused));
+        }
+        mul[k] = m;
+    }
+}
+
+/* hash of the gram whose windows are already loaded */
+ACB_HD uint32_t acb_hash_windows(const uint32_t w[ACB_MAX_WINDOWS], const uint32_t mul[ACB_MAX_WINDOWS], int nw) {
+    uint32_t h = 0;
+    for (int k = 0; k < nw; k++) h += w[k] * mul[k];
+    return h;
+}
+
+/* hash of g bytes at p (bytes beyond the gram are never read) -- host + slow device path */
+ACB_HD uint32_t acb_hash_bytes(const uint8_t *p, int g, const uint32_t mul[ACB_MAX_WINDOWS]) {
+    uint32_t h = 0;
+    int nw = (g + 3) / 4;
+    for (int k = 0; k < nw; k++) {
+        uint32_t w = 0;
+        for (int b = 0; b < 4; b++) {
+            int i = 4 * k + b;
+            if (i < g) w |= (uint32_t)p[i] << (8 * b);
+        }
+        h += w * mul[k];
+    }
+    return h;
+}
+
+#endif

@@ -1,0 +1,508 @@
+/*
+ * acb_host.cpp -- host side of the B200 Aho-Corasick path: trie arena, failure
+ * links, flattening to int32 tables, gram-filter construction.
+ *
+ * Not a port of the reference's node graph (src/trienode.h:19-42: one malloc per
+ * node, unsorted (letter, child*) pairs scanned linearly).  Here nodes live in one
+ * arena with int32 ids, edges in one open-addressing hash map keyed (node, byte),
+ * and the automaton is emitted as column-major int32 tables ready for upload.
+ *
+ * Behaviour that must equal the reference's is cited inline (paths relative to
+ * /root/reference).
+ */
+#include "acb_internal.h"
+#include "acb_hash.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <unordered_set>
+#include <vector>
+
+/* ------------------------------------------------------------------ errors */
+static thread_local char g_err[512] = "";
+
+extern "C" void acb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *acb_last_error(void) { return g_err; }
+extern "C" int acb_abi_version(void) { return ACB_ABI_VERSION; }
+
+/* ---------------------------------------------------------------- edge map */
+namespace {
+
+struct EdgeMap {                     /* (node << 8 | byte) -> child, open addressing */
+    std::vector<uint64_t> keys;      /* 0 = empty; stored key = real key + 1 */
+    std::vector<int32_t>  vals;
+    size_t mask = 0, used = 0;
+
+    static inline uint64_t mix(uint64_t x) {
+        x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+        return x;
+    }
+    void init(size_t cap_pow2) {
+        keys.assign(cap_pow2, 0);
+        vals.assign(cap_pow2, -1);
+        mask = cap_pow2 - 1;
+        used = 0;
+    }
+    void grow() {
+        std::vector<uint64_t> ok;
+        std::vector<int32_t> ov;
+        ok.swap(keys);
+        ov.swap(vals);
+        init(ok.size() * 2);
+        for (size_t i = 0; i < ok.size(); i++)
+            if (ok[i]) put_raw(ok[i], ov[i]);
+    }
+    void put_raw(uint64_t k1, int32_t v) {
+        size_t i = mix(k1) & mask;
+        while (keys[i]) i = (i + 1) & mask;
+        keys[i] = k1;
+        vals[i] = v;
+        used++;
+    }
+    int32_t get(int32_t node, uint8_t byte) const {
+        if (keys.empty()) return -1;
+        uint64_t k1 = (((uint64_t)(uint32_t)node << 8) | byte) + 1;
+        size_t i = mix(k1) & mask;
+        while (keys[i]) {
+            if (keys[i] == k1) return vals[i];
+            i = (i + 1) & mask;
+        }
+        return -1;
+    }
+    void put(int32_t node, uint8_t byte, int32_t child) {
+        if (keys.empty()) init(1024);
+        if ((used + 1) * 10 > keys.size() * 6) grow();
+        put_raw((((uint64_t)(uint32_t)node << 8) | byte) + 1, child);
+    }
+};
+
+struct Node {
+    int32_t parent;
+    int32_t first_child;
+    int32_t last_child;
+    int32_t next_sibling;
+    int32_t key_id;        /* -1 = not the end of a key ("eow" false) */
+    int32_t live_below;    /* live keys ending at or below this node; 0 = pruned */
+    uint8_t byte;
+};
+
+struct Flat {
+    bool valid = false;
+    int32_t S = 0, K = 0, n_keys = 0;
+    int32_t min_key_bytes = 0, max_key_bytes = 0;
+    uint8_t byte_class[256];
+    std::vector<int32_t> goto_cm, fail, key_of, out_ptr, out_idx, key_len;
+    int32_t gram = 0, stride = 0, log1 = 0, log2 = 0;
+    std::vector<uint32_t> bm1, bm2;
+};
+
+} // namespace
+
+struct acb_trie {
+    int letter_bytes = 1;
+    int kind = ACB_EMPTY;
+    int64_t count = 0;          /* live keys */
+    int64_t longest = 0;        /* letters; like the reference it never shrinks on removal */
+    int64_t live_nodes = 0;     /* nodes with live_below > 0, root included once it exists */
+    std::vector<Node> nodes;
+    EdgeMap edges;
+    Flat flat;
+};
+
+/* ------------------------------------------------------------- trie basics */
+static int32_t new_node(acb_trie *t, int32_t parent, uint8_t byte) {
+    Node n;
+    n.parent = parent;
+    n.first_child = n.last_child = n.next_sibling = -1;
+    n.key_id = -1;
+    n.live_below = 0;
+    n.byte = byte;
+    t->nodes.push_back(n);
+    return (int32_t)(t->nodes.size() - 1);
+}
+
+extern "C" acb_trie *acb_trie_new(int letter_bytes) {
+    if (letter_bytes != 1 && letter_bytes != 2 && letter_bytes != 4) {
+        acb_set_error("letter_bytes must be 1, 2 or 4 (got %d)", letter_bytes);
+        return nullptr;
+    }
+    acb_trie *t = new (std::nothrow) acb_trie();
+    if (!t) { acb_set_error("out of memory"); return nullptr; }
+    t->letter_bytes = letter_bytes;
+    return t;
+}
+
+extern "C" void acb_trie_free(acb_trie *t) { delete t; }
+
+extern "C" int acb_trie_clear(acb_trie *t) {
+    if (!t) return ACB_EINVAL;
+    int lb = t->letter_bytes;
+    *t = acb_trie();
+    t->letter_bytes = lb;
+    return ACB_OK;
+}
+
+extern "C" int acb_trie_add_word(acb_trie *t, const uint8_t *key, int64_t nbytes, int32_t key_id,
+                                 int32_t *prev_key_id) {
+    if (!t || key_id < 0 || nbytes < 0 || (nbytes && !key)) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    if (nbytes % t->letter_bytes) { acb_set_error("key length %lld is not a multiple of letter_bytes", (long long)nbytes); return ACB_EINVAL; }
+    if (nbytes == 0) {                      /* src/Automaton.c:257,295: empty key is ignored */
+        if (prev_key_id) *prev_key_id = -2;
+        return ACB_OK;
+    }
+    if (nbytes > 0x3fffffff) { acb_set_error("key too long"); return ACB_ERANGE; }
+    try {
+        if (t->nodes.empty()) { new_node(t, -1, 0); t->live_nodes = 1; }   /* root, src/trie.c:21-26 */
+        int32_t nd = 0;
+        for (int64_t i = 0; i < nbytes; i++) {
+            int32_t kid = t->edges.get(nd, key[i]);
+            if (kid < 0) {
+                if (t->nodes.size() >= 0x7ffffff0u) { acb_set_error("too many trie nodes for int32 state ids"); return ACB_ERANGE; }
+                kid = new_node(t, nd, key[i]);
+                Node &p = t->nodes[nd];
+                if (p.last_child < 0) p.first_child = kid; else t->nodes[p.last_child].next_sibling = kid;
+                p.last_child = kid;
+                t->edges.put(nd, key[i], kid);
+            }
+            nd = kid;
+        }
+        int32_t prev = t->nodes[nd].key_id;
+        t->nodes[nd].key_id = key_id;
+        if (prev < 0) {                                      /* a new key: src/trie.c:52-56 */
+            t->count += 1;
+            for (int32_t x = nd; x >= 0; x = t->nodes[x].parent) {
+                if (x != 0 && t->nodes[x].live_below == 0) t->live_nodes += 1;   /* the root is always live */
+                t->nodes[x].live_below += 1;
+            }
+            int64_t letters = nbytes / t->letter_bytes;      /* src/Automaton.c:285-286 */
+            if (letters > t->longest) t->longest = letters;
+        }
+        t->kind = ACB_TRIE;                                  /* src/trie.c:60 -- also demotes AHOCORASICK */
+        t->flat.valid = false;
+        if (prev_key_id) *prev_key_id = prev;
+        return ACB_OK;
+    } catch (const std::bad_alloc &) {
+        acb_set_error("out of memory");
+        return ACB_ENOMEM;
+    }
+}
+
+static int32_t walk(const acb_trie *t, const uint8_t *key, int64_t nbytes, int64_t *consumed) {
+    int32_t nd = t->nodes.empty() ? -1 : 0;
+    int64_t i = 0;
+    for (; nd >= 0 && i < nbytes; i++) {
+        int32_t kid = t->edges.get(nd, key[i]);
+        if (kid < 0 || t->nodes[kid].live_below == 0) break;
+        nd = kid;
+    }
+    if (consumed) *consumed = i;
+    return (i == nbytes) ? nd : -1;
+}
+
+extern "C" int acb_trie_find(const acb_trie *t, const uint8_t *key, int64_t nbytes, int32_t *key_id,
+                             int32_t *is_prefix) {
+    if (!t || nbytes < 0) return ACB_EINVAL;
+    int32_t nd = walk(t, key, nbytes, nullptr);
+    if (key_id) *key_id = (nd >= 0 && nbytes > 0) ? t->nodes[nd].key_id : -1;
+    if (is_prefix) *is_prefix = (nd >= 0) ? 1 : 0;
+    return ACB_OK;
+}
+
+extern "C" int64_t acb_trie_longest_prefix(const acb_trie *t, const uint8_t *key, int64_t nbytes) {
+    if (!t || nbytes < 0) return 0;
+    int64_t used = 0;
+    walk(t, key, nbytes, &used);
+    return used / t->letter_bytes;      /* only whole letters count */
+}
+
+extern "C" int acb_trie_remove_word(acb_trie *t, const uint8_t *key, int64_t nbytes, int32_t *key_id) {
+    if (!t || nbytes < 0) return ACB_EINVAL;
+    if (key_id) *key_id = -1;
+    if (nbytes == 0) return ACB_OK;
+    int32_t nd = walk(t, key, nbytes, nullptr);
+    if (nd < 0 || t->nodes[nd].key_id < 0) return ACB_OK;
+    if (key_id) *key_id = t->nodes[nd].key_id;
+    t->nodes[nd].key_id = -1;
+    t->count -= 1;
+    for (int32_t x = nd; x >= 0; x = t->nodes[x].parent) {
+        t->nodes[x].live_below -= 1;
+        if (x != 0 && t->nodes[x].live_below == 0) t->live_nodes -= 1;
+    }
+    t->kind = ACB_TRIE;                  /* src/trie.c:134 -- stays TRIE even when no key is left */
+    t->flat.valid = false;
+    return ACB_OK;
+}
+
+extern "C" int acb_trie_kind(const acb_trie *t) { return t ? t->kind : ACB_EMPTY; }
+extern "C" int64_t acb_trie_count(const acb_trie *t) { return t ? t->count : 0; }
+extern "C" int64_t acb_trie_longest_word(const acb_trie *t) { return t ? t->longest : 0; }
+extern "C" int64_t acb_trie_nodes(const acb_trie *t) { return t ? t->live_nodes : 0; }
+extern "C" int64_t acb_trie_links(const acb_trie *t) { return (t && t->live_nodes > 0) ? t->live_nodes - 1 : 0; }
+
+/* ---------------------------------------------------------- gram filter */
+namespace {
+
+struct FilterChoice {
+    int g = 0, s = 0, log1 = 0, log2 = 0;
+    double cost = 1e300;
+};
+
+static inline void set_bit(std::vector<uint32_t> &bm, uint32_t idx) { bm[idx >> 5] |= 1u << (idx & 31); }
+
+/* distinct grams of the m-prefixes at offsets 0, L, .., s-L */
+static void collect_grams(const std::vector<std::vector<uint8_t>> &prefixes, int g, int s, int L,
+                          std::vector<std::vector<uint8_t>> &out) {
+    struct H {
+        size_t operator()(const std::vector<uint8_t> &v) const {
+            uint64_t h = 1469598103934665603ULL;
+            for (uint8_t b : v) { h ^= b; h *= 1099511628211ULL; }
+            return (size_t)h;
+        }
+    };
+    std::unordered_set<std::vector<uint8_t>, H> seen;
+    for (const auto &p : prefixes)
+        for (int j = 0; j + L <= s; j += L) {
+            if (j + g > (int)p.size()) break;
+            std::vector<uint8_t> gr(p.begin() + j, p.begin() + j + g);
+            if (seen.insert(gr).second) out.push_back(std::move(gr));
+        }
+}
+
+static int ceil_log2_u64(uint64_t x) {
+    int l = 0;
+    while (((uint64_t)1 << l) < x && l < 62) l++;
+    return l;
+}
+
+} // namespace
+
+static void build_filter(acb_trie *t, Flat &f) {
+    const int L = t->letter_bytes;
+    const int m = f.min_key_bytes;
+    /* m-prefixes = live nodes at byte depth m (every live key is at least m long) */
+    std::vector<std::vector<uint8_t>> prefixes;
+    {
+        /* BFS ids are depth-ordered; recover depth by walking (cheap: done once) */
+        std::vector<int32_t> depth(t->nodes.size(), -1);
+        std::vector<int32_t> stack;
+        if (!t->nodes.empty() && t->nodes[0].live_below > 0) { depth[0] = 0; stack.push_back(0); }
+        while (!stack.empty()) {
+            int32_t nd = stack.back();
+            stack.pop_back();
+            if (depth[nd] == m) {
+                std::vector<uint8_t> p(m);
+                int32_t x = nd;
+                for (int i = m - 1; i >= 0; i--) { p[i] = t->nodes[x].byte; x = t->nodes[x].parent; }
+                prefixes.push_back(std::move(p));
+                continue;
+            }
+            for (int32_t c = t->nodes[nd].first_child; c >= 0; c = t->nodes[c].next_sibling)
+                if (t->nodes[c].live_below > 0) { depth[c] = depth[nd] + 1; stack.push_back(c); }
+        }
+    }
+    int forced_g = 0, forced_s = 0, forced_l1 = 0;
+    if (const char *env = getenv("ACB_FILTER")) sscanf(env, "%d,%d,%d", &forced_g, &forced_s, &forced_l1);
+
+    const double Kb = std::max(1, f.K - 1);
+    FilterChoice best;
+    std::vector<std::vector<uint8_t>> best_grams;
+    for (int s = L; s <= 16; s *= 2) {
+        if (forced_s && s != forced_s) continue;
+        int gmax = std::min(ACB_MAX_GRAM, m - s + L);
+        if (gmax < L) break;
+        gmax -= gmax % L;
+        std::vector<int> gs;
+        gs.push_back(gmax);
+        for (int g = 12; g >= 4; g -= 4) if (g < gmax && g % L == 0) gs.push_back(g);
+        for (int g : gs) {
+            if (forced_g && g != forced_g) continue;
+            std::vector<std::vector<uint8_t>> grams;
+            collect_grams(prefixes, g, s, L, grams);
+            const double E = (double)grams.size();
+            int log1 = std::min(20, std::max(13, ceil_log2_u64((uint64_t)(E * 64.0) + 1)));
+            if (forced_l1) log1 = forced_l1;
+            int log2 = std::min(30, std::max(15, ceil_log2_u64((uint64_t)(E * 128.0) + 1)));
+            double space = std::pow(Kb, (double)g);
+            double p_true = std::min(1.0, E / space);
+            double fill1 = std::min(1.0, E / std::pow(2.0, log1));
+            double fill2 = std::min(1.0, E / std::pow(2.0, log2));
+            int nw = (g + 3) / 4;
+            double pass1 = p_true + (1 - p_true) * fill1;
+            double pass2 = p_true + (1 - p_true) * fill1 * fill2;
+            double cost = ((4.0 + 3.0 * nw) + pass1 * 40.0 + pass2 * (s / L) * 150.0) / s;
+            if (cost < best.cost) {
+                best.g = g; best.s = s; best.log1 = log1; best.log2 = log2; best.cost = cost;
+                best_grams.swap(grams);
+            }
+        }
+    }
+    f.gram = best.g;
+    f.stride = best.s;
+    f.log1 = best.log1;
+    f.log2 = best.log2;
+    f.bm1.assign((size_t)1 << (best.log1 - 5), 0);
+    f.bm2.assign((size_t)1 << (best.log2 - 5), 0);
+    uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
+    acb_hash_multipliers(best.g, 1, mul1);
+    acb_hash_multipliers(best.g, 2, mul2);
+    for (const auto &gr : best_grams) {
+        set_bit(f.bm1, acb_hash_bytes(gr.data(), best.g, mul1) >> (32 - best.log1));
+        set_bit(f.bm2, acb_hash_bytes(gr.data(), best.g, mul2) >> (32 - best.log2));
+    }
+}
+
+/* ----------------------------------------------- make_automaton + flatten */
+extern "C" int acb_trie_make_automaton(acb_trie *t, int32_t *built) {
+    if (!t) return ACB_EINVAL;
+    if (built) *built = 0;
+    if (t->kind != ACB_TRIE) return ACB_OK;              /* src/Automaton.c:574-575 */
+    try {
+        Flat &f = t->flat;
+        f = Flat();
+        const int64_t S64 = t->live_nodes;
+        if (S64 <= 0 || S64 > 0x7ffffff0) { acb_set_error("state count out of range"); return ACB_ERANGE; }
+        const int32_t S = (int32_t)S64;
+
+        /* byte classes: 0 = byte on no edge; 1.. in byte order */
+        bool present[256] = {false};
+        int np = 0;
+        for (size_t i = 1; i < t->nodes.size(); i++)
+            if (t->nodes[i].live_below > 0 && !present[t->nodes[i].byte]) { present[t->nodes[i].byte] = true; np++; }
+        int32_t K;
+        if (np == 256) {
+            /* every byte value occurs on some edge: no "other" class, class = byte */
+            for (int b = 0; b < 256; b++) f.byte_class[b] = (uint8_t)b;
+            K = 256;
+        } else {
+            K = 1;
+            for (int b = 0; b < 256; b++) f.byte_class[b] = present[b] ? (uint8_t)K++ : (uint8_t)0;
+        }
+        if ((int64_t)K * S64 > ((int64_t)1 << 33)) {
+            acb_set_error("goto table would need %lld entries (K=%d classes x S=%d states)", (long long)K * S64, K, S);
+            return ACB_ERANGE;
+        }
+
+        /* BFS numbering (root = 0), children in insertion order */
+        std::vector<int32_t> order;            /* new id -> arena id */
+        std::vector<int32_t> newid(t->nodes.size(), -1);
+        order.reserve(S);
+        order.push_back(0);
+        newid[0] = 0;
+        for (size_t h = 0; h < order.size(); h++) {
+            const Node &nd = t->nodes[order[h]];
+            for (int32_t c = nd.first_child; c >= 0; c = t->nodes[c].next_sibling)
+                if (t->nodes[c].live_below > 0) { newid[c] = (int32_t)order.size(); order.push_back(c); }
+        }
+        if ((int32_t)order.size() != S) { acb_set_error("internal: live node count mismatch"); return ACB_EINVAL; }
+
+        f.S = S;
+        f.K = K;
+        f.goto_cm.assign((size_t)K * S, -1);
+        f.fail.assign(S, 0);
+        f.key_of.assign(S, -1);
+        std::vector<int32_t> depth(S, 0);
+        int32_t max_id = -1;
+        for (int32_t s = 1; s < S; s++) {
+            const Node &nd = t->nodes[order[s]];
+            int32_t ps = newid[nd.parent];
+            f.goto_cm[(size_t)f.byte_class[nd.byte] * S + ps] = s;
+            depth[s] = depth[ps] + 1;
+        }
+        int32_t minb = 0x7fffffff, maxb = 0;
+        for (int32_t s = 0; s < S; s++) {
+            int32_t k = t->nodes[order[s]].key_id;
+            f.key_of[s] = k;
+            if (k >= 0) { max_id = std::max(max_id, k); minb = std::min(minb, depth[s]); maxb = std::max(maxb, depth[s]); }
+        }
+        f.n_keys = max_id + 1;
+        if (max_id < 0) minb = 0;                            /* every key was removed: root-only automaton */
+        f.min_key_bytes = minb;
+        f.max_key_bytes = maxb;
+        f.key_len.assign(f.n_keys, 0);
+        for (int32_t s = 0; s < S; s++) if (f.key_of[s] >= 0) f.key_len[f.key_of[s]] = depth[s] / t->letter_bytes;
+
+        /* failure links: src/Automaton.c:582-637.  BFS order guarantees fail[] of
+         * shallower states is final when a state is processed. */
+        f.fail[0] = -1;                                      /* root has no fail link */
+        for (int32_t s = 1; s < S; s++) {
+            const Node &nd = t->nodes[order[s]];
+            int32_t ps = newid[nd.parent];
+            if (ps == 0) { f.fail[s] = 0; continue; }       /* depth-1 states fail to the root, :582-596 */
+            const size_t col = (size_t)f.byte_class[nd.byte] * S;
+            int32_t st = f.fail[ps];
+            while (st != 0 && f.goto_cm[col + st] < 0) st = f.fail[st];   /* :621-629 */
+            int32_t g = f.goto_cm[col + st];
+            f.fail[s] = (g >= 0) ? g : 0;                                 /* :631-633 */
+        }
+
+        /* CSR output lists: keys on s, fail(s), fail(fail(s)).. (longest first) */
+        std::vector<int32_t> osuf(S, -1), cnt(S, 0);
+        int64_t total = 0;
+        for (int32_t s = 1; s < S; s++) {
+            int32_t fl = f.fail[s];
+            osuf[s] = (fl > 0) ? ((f.key_of[fl] >= 0) ? fl : osuf[fl]) : -1;
+            cnt[s] = (f.key_of[s] >= 0 ? 1 : 0) + (osuf[s] >= 0 ? cnt[osuf[s]] : 0);
+            total += cnt[s];
+            if (total > 0x7fffffff) { acb_set_error("output lists exceed int32 (%lld entries)", (long long)total); return ACB_ERANGE; }
+        }
+        f.out_ptr.assign((size_t)S + 1, 0);
+        for (int32_t s = 0; s < S; s++) f.out_ptr[s + 1] = f.out_ptr[s] + cnt[s];
+        f.out_idx.assign((size_t)total, -1);
+        for (int32_t s = 1; s < S; s++) {
+            int32_t w = f.out_ptr[s];
+            for (int32_t x = (f.key_of[s] >= 0) ? s : osuf[s]; x >= 0; x = osuf[x]) f.out_idx[w++] = f.key_of[x];
+        }
+
+        if (f.n_keys > 0) build_filter(t, f);
+        else {                                               /* nothing can ever match */
+            f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.log2 = 15;
+            f.bm1.assign((size_t)1 << (13 - 5), 0);
+            f.bm2.assign((size_t)1 << (15 - 5), 0);
+        }
+        f.valid = true;
+        t->kind = ACB_AHOCORASICK;                           /* :639 */
+        if (built) *built = 1;
+        return ACB_OK;
+    } catch (const std::bad_alloc &) {
+        t->flat = Flat();
+        acb_set_error("out of memory while flattening");
+        return ACB_ENOMEM;
+    }
+}
+
+extern "C" int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out) {
+    if (!t || !out) return ACB_EINVAL;
+    if (t->kind != ACB_AHOCORASICK || !t->flat.valid) { acb_set_error("not an Aho-Corasick automaton yet"); return ACB_ESTATE; }
+    const Flat &f = t->flat;
+    memset(out, 0, sizeof(*out));
+    out->n_states = f.S;
+    out->n_classes = f.K;
+    out->n_keys = f.n_keys;
+    out->letter_bytes = t->letter_bytes;
+    out->min_key_bytes = f.min_key_bytes;
+    out->max_key_bytes = f.max_key_bytes;
+    out->byte_class = f.byte_class;
+    out->goto_cm = f.goto_cm.data();
+    out->fail = f.fail.data();
+    out->key_of = f.key_of.data();
+    out->out_ptr = f.out_ptr.data();
+    out->out_idx = f.out_idx.data();
+    out->key_len = f.key_len.data();
+    out->gram_bytes = f.gram;
+    out->stride = f.stride;
+    out->log2_bits1 = f.log1;
+    out->log2_bits2 = f.log2;
+    out->bitmap1 = f.bm1.data();
+    out->bitmap2 = f.bm2.data();
+    return ACB_OK;
+}

@@ -1,0 +1,151 @@
+"""Test-only, pure-Python emulation of the DEVICE algorithm (csrc/acb_device.cu) on the
+flattened tables produced by the host core.  It exists so that the CPU test-suite can
+exercise the host logic (filter construction, flattening, the Python API layer) without
+a GPU; it is never imported by the product.
+
+emul_filter() restates acb_filter_kernel: stage-1 bitmap probe at every `stride`-th byte,
+stage-2 bitmap, then the trie walk from each candidate start.  emul_dfa() restates
+acb_dfa_kernel (goto / fail / CSR outputs).  Both return records sorted the way
+acb_scan_host sorts them.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+M32 = 0xFFFFFFFF
+S1 = (0x9E3779B1, 0x85EBCA77, 0xC2B2AE3D, 0x27D4EB2F)
+S2 = (0x165667B1, 0xD3A2646D, 0xFD7046C5, 0xB55A4F09)
+
+
+def multipliers(g, stage):
+    base = S1 if stage == 1 else S2
+    nw = (g + 3) // 4
+    out = []
+    for k in range(4):
+        m = base[k]
+        if k >= nw:
+            m = 0
+        elif k == nw - 1:
+            unused = 4 * nw - g
+            m = (m << (8 * unused)) & M32
+        out.append(m)
+    return out
+
+
+def hash_bytes(buf, q, g, mul):
+    """zero-filled past the end of buf, exactly like the kernel's guarded loads"""
+    h = 0
+    nw = (g + 3) // 4
+    n = len(buf)
+    for k in range(nw):
+        w = 0
+        for b in range(4):
+            i = 4 * k + b
+            if i < g and q + i < n:
+                w |= int(buf[q + i]) << (8 * b)
+        h = (h + w * mul[k]) & M32
+    return h
+
+
+def _bit(bm, idx):
+    return (int(bm[idx >> 5]) >> (idx & 31)) & 1
+
+
+def _bounds(q, offsets, stride, n_hay):
+    if offsets is None:
+        h = q // stride
+        return h, h * stride, h * stride + stride
+    h = int(np.searchsorted(offsets, q, side="right")) - 1
+    return h, int(offsets[h]), int(offsets[h + 1])
+
+
+def _sorted(recs, key_len):
+    recs.sort(key=lambda r: (r[0], r[1], -int(key_len[r[2]])))
+    return recs
+
+
+def emul_filter(f, buf, offsets=None, stride_bytes=0):
+    L, g, s = f["letter_bytes"], f["gram_bytes"], f["stride"]
+    S = f["n_states"]
+    mul1, mul2 = multipliers(g, 1), multipliers(g, 2)
+    l1, l2 = f["log2_bits1"], f["log2_bits2"]
+    total = len(buf)
+    n_hay = (len(offsets) - 1) if offsets is not None else total // stride_bytes
+    cls, gto, key_of = f["byte_class"], f["goto_cm"], f["key_of"]
+    recs = []
+    if f["n_keys"] == 0:
+        return recs
+    for q in range(0, total, s):
+        if not _bit(f["bitmap1"], hash_bytes(buf, q, g, mul1) >> (32 - l1)):
+            continue
+        if q + g > total:
+            continue
+        if not _bit(f["bitmap2"], hash_bytes(buf, q, g, mul2) >> (32 - l2)):
+            continue
+        h, hs, he = _bounds(q, offsets, stride_bytes, n_hay)
+        for j in range(0, s, L):
+            start = q - j
+            if start < hs:
+                break
+            st = 0
+            for i in range(start, he):
+                nx = int(gto[cls[buf[i]], st])
+                if nx < 0:
+                    break
+                st = nx
+                k = int(key_of[st])
+                if k >= 0:
+                    recs.append((h, (i - hs + 1) // L - 1, k))
+    return _sorted(recs, f["key_len"])
+
+
+def emul_dfa(f, buf, offsets=None, stride_bytes=0, span=64):
+    L = f["letter_bytes"]
+    total = len(buf)
+    n_hay = (len(offsets) - 1) if offsets is not None else total // stride_bytes
+    cls, gto, fail = f["byte_class"], f["goto_cm"], f["fail"]
+    out_ptr, out_idx, key_len = f["out_ptr"], f["out_idx"], f["key_len"]
+    maxb = f["max_key_bytes"]
+    recs = []
+    for a in range(0, total, span):
+        b = min(a + span, total)
+        h, hs, he = _bounds(a, offsets, stride_bytes, n_hay)
+        i = max(hs, a - maxb)
+        st = 0
+        while i < b:
+            while i >= he:
+                h += 1
+                hs = he
+                he = hs + stride_bytes if offsets is None else int(offsets[h + 1])
+                st = 0
+            c = cls[buf[i]]
+            nx = int(gto[c, st])
+            while nx < 0 and st != 0:
+                st = int(fail[st])
+                nx = int(gto[c, st])
+            st = 0 if nx < 0 else nx
+            if i >= a and st != 0 and (i + 1 - hs) % L == 0:
+                for o in range(int(out_ptr[st]), int(out_ptr[st + 1])):
+                    k = int(out_idx[o])
+                    recs.append((h, (i - hs + 1) // L - 1, k))
+            i += 1
+    return _sorted(recs, key_len)
+
+
+def install(monkeypatch_or_none, algo="filter"):
+    """Route Automaton._scan_flat through the emulation (CPU tests of the host logic only)."""
+    from pyahocorasick_b200 import _native as N
+    from pyahocorasick_b200 import automaton as am
+
+    def fake_scan_flat(self, flat, offsets, n_hay, stride_bytes, algo=algo, sort=True, device=None):
+        f = self.flat()
+        fn = emul_dfa if algo == "dfa" else emul_filter
+        recs = fn(f, np.asarray(flat, dtype=np.uint8), offsets, stride_bytes)
+        out = np.empty(len(recs), dtype=N.MATCH_DTYPE)
+        for i, r in enumerate(recs):
+            out[i] = r
+        return out
+
+    if monkeypatch_or_none is not None:
+        monkeypatch_or_none.setattr(am.Automaton, "_scan_flat", fake_scan_flat)
+    return fake_scan_flat

@@ -1,0 +1,132 @@
+"""White-box checks of the host core: flattened goto/fail/output tables and the gram filter."""
+import numpy as np
+import pytest
+
+import emul
+import oracle
+import pyahocorasick_b200 as ac
+from pyahocorasick_b200 import synth
+
+B = ac.flavour("bytes")
+
+
+def _brute_fail(keys):
+    """fail(s) by definition: longest proper suffix of the state's string that is a trie node."""
+    pref = {b""}
+    for k in keys:
+        for i in range(1, len(k) + 1):
+            pref.add(k[:i])
+    out = {}
+    for p in pref:
+        if not p:
+            continue
+        f = b""
+        for i in range(1, len(p)):
+            if p[i:] in pref:
+                f = p[i:]
+                break
+        out[p] = f
+    return out
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_tables_match_definitions(seed):
+    rng = np.random.Generator(np.random.PCG64(100 + seed))
+    keys = synth.draw_keys(rng, np.frombuffer(b"abc", dtype=np.uint8), 40, 1, 7)
+    A = synth.build_automaton(keys)
+    f = A.flat()
+    S = f["n_states"]
+    # reconstruct every state's string by walking goto from the root
+    inv = {int(c): b for b, c in enumerate(f["byte_class"].tolist()) if c}
+    strings = {0: b""}
+    for s in range(S):                       # BFS numbering: parents come first
+        for c in range(1, f["n_classes"]):
+            t = int(f["goto_cm"][c, s])
+            if t >= 0:
+                assert t > s and t not in strings
+                strings[t] = strings[s] + bytes([inv[c]])
+    assert len(strings) == S
+    lens = [len(strings[s]) for s in range(S)]
+    assert lens == sorted(lens)              # depth-ordered ids
+    bf = _brute_fail(keys)
+    ids = {v: k for k, v in strings.items()}
+    assert f["fail"][0] == -1
+    for s in range(1, S):
+        assert strings[int(f["fail"][s])] == bf[strings[s]]
+    # key_of / key_len / CSR outputs: every key that is a suffix of the state's string, longest first
+    for s in range(S):
+        want = [i for i, k in sorted(enumerate(keys), key=lambda t: -len(t[1])) if strings[s].endswith(k)]
+        got = f["out_idx"][f["out_ptr"][s]:f["out_ptr"][s + 1]].tolist()
+        assert got == want
+        assert f["key_of"][s] == (keys.index(strings[s]) if strings[s] in keys else -1)
+    assert f["key_len"].tolist() == [len(k) for k in keys]
+    assert f["min_key_bytes"] == min(map(len, keys)) and f["max_key_bytes"] == max(map(len, keys))
+    assert A.get_stats()["nodes_count"] == S
+
+
+CASES = [
+    (b"ab", 30, 1, 6), (b"ab", 30, 3, 9), (b"ACGT", 400, 12, 20), (b"ACGT", 300, 20, 20),
+    (synth.ALNUM.tobytes(), 500, 4, 16), (synth.ALNUM.tobytes(), 500, 5, 9), (synth.ALNUM.tobytes(), 300, 9, 30),
+    (bytes(range(256)), 300, 2, 4), (synth.ALNUM.tobytes(), 200, 17, 40),
+]
+
+
+@pytest.mark.parametrize("alpha,nk,lo,hi", CASES)
+def test_filter_never_loses_a_match(alpha, nk, lo, hi):
+    """emulated filter kernel == emulated DFA kernel == the oracle, on fixed-stride and ragged batches."""
+    rng = np.random.Generator(np.random.PCG64(nk * 31 + lo))
+    al = np.frombuffer(alpha, dtype=np.uint8)
+    keys = synth.draw_keys(rng, al, nk, lo, hi)
+    A = synth.build_automaton(keys)
+    f = A.flat()
+    assert f["gram_bytes"] + f["stride"] - 1 <= f["min_key_bytes"]
+    O = oracle.OracleAutomaton()
+    for i, k in enumerate(keys):
+        O.add_word(k, i)
+    O.make_automaton()
+    nh, hl = 24, 96
+    hay = synth.random_haystacks(rng, al, nh, hl)
+    synth.plant(rng, hay, keys, np.arange(nh))
+    flat = hay.reshape(-1)
+    off = np.arange(nh + 1, dtype=np.int64) * hl
+    want = [tuple(r) for r in O.scan_batch_bytes(flat, off).tolist()]
+    assert want
+    assert emul.emul_filter(f, flat, None, hl) == want
+    assert emul.emul_dfa(f, flat, None, hl) == want
+    cuts = np.sort(rng.integers(0, flat.size + 1, size=17))
+    roff = np.concatenate([[0, 0], cuts, [flat.size]]).astype(np.int64)
+    want2 = [tuple(r) for r in O.scan_batch_bytes(flat, roff).tolist()]
+    assert emul.emul_filter(f, flat, roff, 0) == want2
+    assert emul.emul_dfa(f, flat, roff, 0) == want2
+
+
+def test_filter_choice_for_baseline_configs():
+    w = synth.make("C2", scale=0.001)
+    f = synth.build_automaton(w.keys).flat()
+    assert (f["gram_bytes"], f["stride"], f["log2_bits1"]) == (4, 1, 20)
+    fill = np.unpackbits(f["bitmap1"].view(np.uint8)).mean()
+    assert 0.005 < fill < 0.012
+
+
+def test_state_machine_and_removal():
+    A = B.Automaton()
+    assert A.kind == ac.EMPTY and A.make_automaton() is False
+    assert A.add_word(b"", 1) is False and A.kind == ac.EMPTY
+    assert A.add_word(b"he", 1) and A.add_word(b"hers", 2) and not A.add_word(b"he", 3)
+    assert A.kind == ac.TRIE and len(A) == 2 and A.get(b"he") == 3
+    assert A.make_automaton() is None and A.kind == ac.AHOCORASICK and A.make_automaton() is False
+    assert A.add_word(b"she", 4) and A.kind == ac.TRIE              # demoted (src/trie.c:60)
+    A.make_automaton()
+    assert A.remove_word(b"hers") and not A.remove_word(b"hers") and A.kind == ac.TRIE
+    assert not A.exists(b"hers") and A.match(b"he") and not A.match(b"her") and A.longest_prefix(b"hexx") == 2
+    A.make_automaton()
+    assert A.get_stats()["nodes_count"] == 6                        # root, h, he, s, sh, she
+    assert A.pop(b"she") == 4 and sorted(A.keys()) == [b"he"]
+    with pytest.raises(KeyError):
+        A.pop(b"she")
+    A.clear()
+    assert A.kind == ac.EMPTY and len(A) == 0
+    with pytest.raises(ValueError):
+        B.Automaton(-42)
+    with pytest.raises(ValueError):
+        B.Automaton(ac.STORE_ANY, -42)

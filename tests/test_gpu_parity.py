@@ -1,0 +1,229 @@
+"""Parity of the CUDA path (through the C ABI) with the reference -- run with `-m gpu` on a B200.
+
+Bar: bit-exact records (integer/index work).  Sources of truth, in order:
+  1. tests/golden/*.json  -- produced by the unmodified reference (both flavours);
+  2. oracle.OracleAutomaton -- the pinned C restatement, on seeded random batches at sizes it
+     finishes in seconds; the compiled reference (oracle/_ref) too when it travelled along;
+  3. at BASELINE.json's full sizes: properties that need no CPU run -- every planted
+     occurrence is reported, no duplicates, each reported record really is an occurrence
+     (sampled), and the two independent kernels (filter / DFA) agree exactly.
+"""
+import numpy as np
+import pytest
+
+import oracle
+import pyahocorasick_b200 as ac
+from golden_driver import all_scenarios, run_ops
+from pyahocorasick_b200 import automaton as am
+from pyahocorasick_b200 import synth
+
+pytestmark = pytest.mark.gpu
+B = ac.flavour("bytes")
+
+SC = all_scenarios()
+
+
+@pytest.mark.parametrize("algo", ["filter", "dfa"])
+@pytest.mark.parametrize("sc", SC, ids=[s["name"] for s in SC])
+def test_golden_on_gpu(sc, algo, monkeypatch):
+    real = am.Automaton._scan_flat
+
+    def forced(self, flat, offsets, n_hay, stride_bytes, algo=algo, sort=True, device=None, _a=algo):
+        return real(self, flat, offsets, n_hay, stride_bytes, algo=_a, sort=sort, device=device)
+    monkeypatch.setattr(am.Automaton, "_scan_flat", forced)
+    bad = run_ops(ac.flavour(sc["flavour"]), sc, record=False)
+    assert not bad, bad[:3]
+
+
+def _oracle_for(keys):
+    O = oracle.OracleAutomaton()
+    for i, k in enumerate(keys):
+        O.add_word(k, i)
+    O.make_automaton()
+    return O
+
+
+def _records(m):
+    return list(zip(m.hay_id.tolist(), m.end_index.tolist(), m.key_id.tolist()))
+
+
+def _want_sorted(O, keys, flat, off):
+    rec = O.scan_batch_bytes(flat, off).tolist()
+    # oracle order inside one (hay, end) is fail-chain order = longest key first: already what sort=True gives
+    return [tuple(r) for r in rec]
+
+
+CASES = [
+    # name, alphabet, n_keys, (lo, hi), n_hay, hay_len
+    ("alnum_4_16", synth.ALNUM, 10_000, (4, 16), 4000, 256),
+    ("alnum_1_5", synth.ALNUM, 300, (1, 5), 500, 300),
+    ("ab_1_8", np.frombuffer(b"ab", dtype=np.uint8), 40, (1, 8), 300, 500),
+    ("dna_20", synth.DNA, 5000, (20, 20), 3000, 150),
+    ("dna_8_12", synth.DNA, 3000, (8, 12), 1000, 150),
+    ("allbytes_2_6", np.arange(256, dtype=np.uint8), 5000, (2, 6), 1000, 777),
+    ("hi_bytes", np.array([0, 1, 127, 128, 200, 255], dtype=np.uint8), 200, (1, 6), 500, 333),
+    ("long_keys", synth.ALNUM, 2000, (17, 40), 800, 1000),
+]
+
+
+@pytest.mark.parametrize("algo", ["filter", "dfa"])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_random_batches_match_oracle(case, algo):
+    name, alpha, nk, (lo, hi), nh, hl = case
+    rng = np.random.Generator(np.random.PCG64(sum(name.encode()) * 7919))
+    keys = synth.draw_keys(rng, alpha, nk, lo, hi)
+    hay = synth.random_haystacks(rng, alpha, nh, hl)
+    synth.plant(rng, hay, keys, np.arange(0, nh, 2))
+    A = synth.build_automaton(keys)
+    O = _oracle_for(keys)
+    # fixed stride
+    off = np.arange(nh + 1, dtype=np.int64) * hl
+    want = _want_sorted(O, keys, hay.reshape(-1), off)
+    assert len(want) > 0
+    got = _records(A.find_all_batch(hay, algo=algo))
+    assert got == want
+    # ragged offsets, with empty haystacks and odd alignment
+    cuts = np.sort(rng.integers(0, hay.size + 1, size=nh))
+    cuts[5::7] = cuts[4::7][:len(cuts[5::7])]                 # repeated offsets = empty haystacks
+    roff = np.concatenate([[0, 0], np.sort(cuts), [hay.size, hay.size]]).astype(np.int64)
+    want2 = _want_sorted(O, keys, hay.reshape(-1), roff)
+    got2 = _records(A.find_all_batch((hay.reshape(-1), roff), algo=algo))
+    assert got2 == want2
+    # list-of-bytes entry point
+    hs = [hay[i, : int(rng.integers(0, hl + 1))].tobytes() for i in range(0, min(nh, 200))]
+    loff = np.concatenate([[0], np.cumsum([len(h) for h in hs])]).astype(np.int64)
+    lflat = np.frombuffer(b"".join(hs), dtype=np.uint8)
+    want3 = _want_sorted(O, keys, lflat, loff) if lflat.size else []
+    assert _records(A.find_all_batch(hs, algo=algo)) == want3
+
+
+@pytest.mark.skipif(not oracle.ref_available("bytes"), reason="oracle/_ref did not travel")
+def test_reference_extension_agrees_on_c2_sample():
+    """The unmodified reference (compiled into oracle/_ref) on a C2 sub-sample."""
+    ref = oracle.ref_module("bytes")
+    w = synth.make("C2", scale=0.005)
+    R = ref.Automaton(ref.STORE_INTS)
+    for i, k in enumerate(w.keys):
+        R.add_word(k, i)
+    R.make_automaton()
+    A = synth.build_automaton(w.keys)
+    want = oracle.ref_scan_batch(R, [row.tobytes() for row in w.haystacks])
+    for algo in ("filter", "dfa"):
+        m = A.find_all_batch(w.haystacks, algo=algo)
+        assert list(zip(m.hay_id.tolist(), m.end_index.tolist(), m.values())) == want
+
+
+def test_pathological_overlaps():
+    keys = [b"a" * k for k in range(1, 33)] + [b"a" * 31 + b"b", b"ba", b"ab"]
+    A = synth.build_automaton(keys)
+    O = _oracle_for(keys)
+    hay = np.frombuffer((b"a" * 200 + b"b") * 20, dtype=np.uint8).reshape(1, -1).copy()
+    off = np.array([0, hay.size], dtype=np.int64)
+    want = _want_sorted(O, keys, hay.reshape(-1), off)
+    for algo in ("filter", "dfa"):
+        assert _records(A.find_all_batch(hay, algo=algo)) == want
+
+
+def test_unicode_and_sequence_flavours_on_gpu():
+    U = ac.flavour("unicode")
+    A = U.Automaton()
+    words = ["wy", "ważyć", "aż", "waży", "ż", "中文", "\U0001F629", "a\U0001F629b"]
+    for i, w in enumerate(words):
+        A.add_word(w, (i, w))
+    A.make_automaton()
+    text = "wyważyć 中文 a\U0001F629b ż" * 50
+    Ro = oracle.OracleAutomaton()
+    for i, w in enumerate(words):
+        Ro.add_word(w, i)
+    Ro.make_automaton()
+    want = [(e, (v, words[v])) for e, v in Ro.find_all(text)]
+    assert list(A.iter(text)) == want
+    S = U.Automaton(U.STORE_INTS, U.KEY_SEQUENCE)
+    seqs = [(1, 2, 3), (2, 3), (2 ** 32 - 1, 0), (70000, 1)]
+    for i, s in enumerate(seqs):
+        S.add_word(s, i)
+    S.make_automaton()
+    hay = (0, 1, 2, 3, 2 ** 32 - 1, 0, 70000, 1, 2, 3) * 30
+    So = oracle.OracleAutomaton()
+    for i, s in enumerate(seqs):
+        So.add_word(s, i)
+    So.make_automaton()
+    assert list(S.iter(hay)) == So.find_all(hay)
+
+
+# ------------------------------------------------------------------ BASELINE.json sizes
+def _check_full(w, A, sample=20000):
+    m_f = A.find_all_batch(w.haystacks, algo="filter")
+    rec_f = np.stack([m_f.hay_id, m_f.end_index, m_f.key_id], axis=1).astype(np.int64)
+    # (1) every planted occurrence is reported
+    stride = w.haystacks.shape[1]
+    def pack(h, e, k):
+        return (h * stride + e) * (len(w.keys) + 1) + k
+    got = pack(rec_f[:, 0], rec_f[:, 1], rec_f[:, 2])
+    planted = pack(w.planted_hay, w.planted_end, w.planted_key)
+    assert np.isin(planted, got).all()
+    # (2) no duplicates
+    assert len(np.unique(got)) == len(got)
+    # (3) sortedness in the reference's order
+    klen = np.fromiter((len(k) for k in w.keys), dtype=np.int64, count=len(w.keys))
+    order = np.lexsort((-klen[rec_f[:, 2]], rec_f[:, 1], rec_f[:, 0]))
+    assert (order == np.arange(len(order))).all()
+    # (4) a sample of reported records really are occurrences
+    rng = np.random.Generator(np.random.PCG64(7))
+    for i in rng.integers(0, len(rec_f), size=min(sample, len(rec_f))).tolist():
+        h, e, k = rec_f[i]
+        key = w.keys[k]
+        assert w.haystacks[h, e - len(key) + 1:e + 1].tobytes() == key
+    # (5) the independent DFA kernel agrees exactly
+    m_d = A.find_all_batch(w.haystacks, algo="dfa")
+    assert np.array_equal(m_d.hay_id, m_f.hay_id) and np.array_equal(m_d.end_index, m_f.end_index) and np.array_equal(m_d.key_id, m_f.key_id)
+    return len(got)
+
+
+def test_full_size_c2_properties():
+    w = synth.make("C2", scale=1.0)
+    A = synth.build_automaton(w.keys)
+    n = _check_full(w, A)
+    assert n >= w.n_hay
+
+
+def test_c3_dna_properties():
+    w = synth.make("C3", scale=0.1)          # 1 M reads x 150 B, 100 k 20-mers
+    A = synth.build_automaton(w.keys)
+    _check_full(w, A)
+
+
+def test_c4_long_haystacks_properties():
+    w = synth.make("C4", scale=0.25)         # 64 x 4 MiB, keys straddling every 16 KiB work unit
+    A = synth.build_automaton(w.keys)
+    _check_full(w, A)
+
+
+def test_c5_100k_keys_properties():
+    w = synth.make("C5", scale=0.125)        # 1 M x 256 B (one GPU's shard), 100 k keys
+    A = synth.build_automaton(w.keys)
+    _check_full(w, A)
+
+
+def test_device_resident_entry_and_overflow_retry():
+    import ctypes
+    import torch
+    from pyahocorasick_b200 import _native as N
+    w = synth.make("C2", scale=0.01)
+    A = synth.build_automaton(w.keys)
+    want = _records(A.find_all_batch(w.haystacks))
+    tb = A._ensure_table(0)
+    d_hay = torch.from_numpy(w.haystacks).cuda()
+    d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_out = torch.empty((8, 3), dtype=torch.int32, device="cuda")            # far too small
+    st = torch.cuda.current_stream().cuda_stream
+    L = N.lib()
+    N.check(L.acb_scan_device(tb, d_hay.data_ptr(), d_hay.numel(), None, w.n_hay, 256, d_out.data_ptr(), 8, d_cnt.data_ptr(), st, 0))
+    torch.cuda.synchronize()
+    assert int(d_cnt.item()) == len(want)                                    # counted, not stored
+    d_out = torch.empty((len(want), 3), dtype=torch.int32, device="cuda")
+    d_cnt.zero_()
+    N.check(L.acb_scan_device(tb, d_hay.data_ptr(), d_hay.numel(), None, w.n_hay, 256, d_out.data_ptr(), len(want), d_cnt.data_ptr(), st, 0))
+    torch.cuda.synchronize()
+    got = sorted(map(tuple, d_out.cpu().numpy().tolist()))
+    assert got == sorted(want)
