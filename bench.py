@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="haystacks in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--variant", default="planted", choices=["planted", "sparse"], help="sparse = pure random haystacks (diagnostic)")
     return ap.parse_args()
 
 
@@ -211,7 +212,7 @@ def main():
     scale = args.scale if args.scale is not None else default_scale(cfg)
 
     # ---- workload (every rank: same keys, its own shard of haystacks) -------------------------
-    w = synth.make(cfg, scale=scale)
+    w = synth.make(cfg, scale=scale, planted=(args.variant == "planted"))
     if world > 1 and rank > 0:                         # different haystack bytes per rank, same shape
         rng = np.random.Generator(np.random.PCG64(9000 + rank))
         hay = synth.random_haystacks(rng, synth.DNA if cfg == "C3" else synth.ALNUM, *w.haystacks.shape)
@@ -339,7 +340,7 @@ def main():
             "metric": "haystack GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC[cfg] + ("" if scale == default_scale(cfg) else f" [SCALED x{scale}: not a valid bench number]"),
+            "config": {"workload": WORKLOAD_DESC[cfg] + ("" if args.variant == "planted" else " [SPARSE variant: no planted keys]") + ("" if scale == default_scale(cfg) else f" [SCALED x{scale}: not a valid bench number]"),
                        "n_haystacks_per_gpu": n_hay, "haystack_bytes": stride, "n_keys": len(w.keys),
                        "l2": f"batch {total / 1e6:.0f} MB per GPU > 126 MB L2, no flush needed" if total > 126e6 else "batch smaller than L2",
                        "algo": args.algo, "parallelism": f"batch-sharded x{world}, NCCL all-gather of match counts" if world > 1 else "single GPU"},

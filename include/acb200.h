@@ -112,13 +112,15 @@ typedef struct acb_flat_view {
     const int32_t *out_ptr;       /* [S+1]  CSR over out_idx                                  */
     const int32_t *out_idx;       /* key ids on the chain s, fail(s), ... (longest first)     */
     const int32_t *key_len;       /* [n_keys] key length in LETTERS (0 = unused id)           */
-    /* prefilter (see DESIGN.md "gram filter") */
+    /* prefilter (see DESIGN.md "filter kernel") */
     int32_t        gram_bytes;    /* g : bytes hashed per probe                               */
     int32_t        stride;        /* s : probe every s-th byte position                       */
     int32_t        log2_bits1;    /* stage-1 bitmap (shared memory) has 2^log2_bits1 bits     */
     int32_t        log2_bits2;    /* stage-2 bitmap (global memory) has 2^log2_bits2 bits     */
-    const uint32_t *bitmap1;
-    const uint32_t *bitmap2;
+    int32_t        log2_anchor_slots; /* anchor table has 2^n slots of 8 uint32 (32 B)        */
+    const uint32_t *bitmap1;      /* bit index = hash1(gram) >> (32 - log2_bits1)             */
+    const uint32_t *bitmap2;      /* bit index = hash2(gram) >> (32 - log2_bits2)             */
+    const uint32_t *anchors;      /* slot: tag(hash2|1, 0=empty), key_id(-1=MULTI), j|len<<8, 20 bytes */
 } acb_flat_view;
 
 int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out);
@@ -149,12 +151,20 @@ enum {
  *                when every haystack is `stride_bytes` long (haystack h = [h*stride, (h+1)*stride))
  *   d_out/cap  : match records; records beyond cap are counted but not stored
  *   d_count    : device int64; incremented by the number of matches found
- *                (the caller zeroes it; order of records is unspecified)
+ *                (the caller zeroes it; order of records is unspecified).  The filter
+ *                path keeps an internal candidate list sized for 1/8 of the probe
+ *                positions; if a pathological key set overflows it, *d_count is set to
+ *                -1: call acb_table_reserve_candidates(tb, 1) and scan again
+ *                (acb_scan_host does this by itself).
+ * One scan at a time per table: the table owns the scratch buffers of the scan.
  */
 int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t total_bytes,
                     const int64_t *d_offsets, int64_t n_hay, int64_t stride_bytes,
                     acb_match *d_out, int64_t cap, int64_t *d_count,
                     void *stream, int algo);
+
+/* worst_case != 0: size the candidate list for every probe position (never overflows) */
+int acb_table_reserve_candidates(acb_table *tb, int worst_case);
 
 /* Batch scan, HOST buffers: H2D copy of haystacks (+offsets), the kernel, and D2H of
  * the count and the records, all inside the call (this is what `e2e` times).

@@ -26,8 +26,9 @@ class FlatView(ctypes.Structure):
         ("key_of", ctypes.POINTER(ctypes.c_int32)), ("out_ptr", ctypes.POINTER(ctypes.c_int32)),
         ("out_idx", ctypes.POINTER(ctypes.c_int32)), ("key_len", ctypes.POINTER(ctypes.c_int32)),
         ("gram_bytes", ctypes.c_int32), ("stride", ctypes.c_int32),
-        ("log2_bits1", ctypes.c_int32), ("log2_bits2", ctypes.c_int32),
+        ("log2_bits1", ctypes.c_int32), ("log2_bits2", ctypes.c_int32), ("log2_anchor_slots", ctypes.c_int32),
         ("bitmap1", ctypes.POINTER(ctypes.c_uint32)), ("bitmap2", ctypes.POINTER(ctypes.c_uint32)),
+        ("anchors", ctypes.POINTER(ctypes.c_uint32)),
     ]
 
 
@@ -69,6 +70,7 @@ def lib() -> ctypes.CDLL:
         "acb_table_upload": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp)]),
         "acb_table_free": (None, [vp]),
         "acb_table_device_bytes": (i64, [vp]),
+        "acb_table_reserve_candidates": (ctypes.c_int, [vp, ctypes.c_int]),
         "acb_scan_device": (ctypes.c_int, [vp, vp, i64, vp, i64, i64, vp, i64, vp, vp, ctypes.c_int]),
         "acb_scan_host": (ctypes.c_int, [vp, vp, i64, vp, i64, i64, vp, i64, pi64, ctypes.c_int, ctypes.c_int]),
         "acb_launch_count": (i64, []),
@@ -89,7 +91,7 @@ EXPORTED_SYMBOLS = [
     "acb_trie_new", "acb_trie_free", "acb_trie_clear", "acb_trie_add_word", "acb_trie_remove_word",
     "acb_trie_find", "acb_trie_longest_prefix", "acb_trie_make_automaton", "acb_trie_kind",
     "acb_trie_count", "acb_trie_longest_word", "acb_trie_nodes", "acb_trie_links", "acb_trie_flat_view",
-    "acb_device_count", "acb_table_upload", "acb_table_free", "acb_table_device_bytes",
+    "acb_device_count", "acb_table_upload", "acb_table_free", "acb_table_device_bytes", "acb_table_reserve_candidates",
     "acb_scan_device", "acb_scan_host", "acb_launch_count", "acb_set_kernel_timing",
     "acb_last_kernel_ms", "acb_last_error", "acb_abi_version",
 ]

@@ -429,7 +429,10 @@ class Automaton:
             fail=arr(fv.fail, S, np.int32), key_of=arr(fv.key_of, S, np.int32), out_ptr=arr(fv.out_ptr, S + 1, np.int32),
             out_idx=arr(fv.out_idx, n_out, np.int32), key_len=arr(fv.key_len, fv.n_keys, np.int32),
             gram_bytes=fv.gram_bytes, stride=fv.stride, log2_bits1=fv.log2_bits1, log2_bits2=fv.log2_bits2,
-            bitmap1=arr(fv.bitmap1, 1 << (fv.log2_bits1 - 5), np.uint32), bitmap2=arr(fv.bitmap2, 1 << (fv.log2_bits2 - 5), np.uint32))
+            log2_anchor_slots=fv.log2_anchor_slots,
+            bitmap1=arr(fv.bitmap1, 1 << (fv.log2_bits1 - 5), np.uint32),
+            bitmap2=arr(fv.bitmap2, 1 << (fv.log2_bits2 - 5), np.uint32),
+            anchors=arr(fv.anchors, 8 << fv.log2_anchor_slots, np.uint32).reshape(-1, 8))
 
     # ------------------------------------------------------------------ GPU scan plumbing
     def _scan_flat(self, flat: np.ndarray, offsets: Optional[np.ndarray], n_hay: int, stride_bytes: int,

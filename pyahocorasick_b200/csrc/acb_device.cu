@@ -1,16 +1,18 @@
 /*
  * acb_device.cu -- sm_100a scan kernels and the device half of the C ABI.
  *
- * Two kernels search a batch of haystacks stored back to back in HBM:
+ * ACB_ALGO_FILTER (the fast path) is two launches per <= 2 GiB segment of the batch:
  *
- *  acb_filter_kernel<NW,STRIDE>   (ACB_ALGO_FILTER, the fast path)
- *      Start-anchored search.  Every candidate start position is first tested
- *      against a gram bitmap held in shared memory (stage 1), survivors against a
- *      second, independent bitmap in global memory (stage 2), and only the few
- *      that pass both walk the trie through the column-major goto table (stage 3).
- *      No failure links are followed: an occurrence is found exactly once, by the
- *      walk that starts at its first byte, so the result set equals what the
- *      reference produces by walking fail chains at every position
+ *  acb_filter_kernel<NW,STRIDE> streams the haystack bytes once (stage 1) and appends the
+ *  few surviving probe positions to a candidate list; acb_verify_kernel resolves them.
+ *      Start-anchored search.  Every probe position is first tested against a gram
+ *      bitmap held in shared memory (stage 1).  Survivors look their gram up in the
+ *      anchor table in global memory (stage 2, one 32-byte slot): a UNIQUE anchor
+ *      carries the only key that can match there, which is compared with the text
+ *      directly; a MULTI anchor (keys sharing that prefix) walks the trie through
+ *      the column-major goto table (stage 3).  No failure links are followed: an
+ *      occurrence is found exactly once, from its first byte, so the result set
+ *      equals what the reference produces by walking fail chains at every position
  *      (src/AutomatonSearchIter.c:157-197, src/Automaton.c:693-714).
  *
  *  acb_dfa_kernel                 (ACB_ALGO_DFA)
@@ -47,19 +49,20 @@
 
 namespace {
 
-constexpr int kThreads      = 1024;               /* one CTA per SM                         */
+constexpr int kThreads      = 1024;               /* filter kernel: one CTA per SM                 */
 constexpr int kWarps        = kThreads / 32;
-constexpr int kChunk        = 16;                 /* bytes per lane per iteration           */
-constexpr int kWarpBytes    = 32 * kChunk;        /* 512 B per warp iteration               */
-constexpr int kItersPerBlk  = 32;
-constexpr int kBlockBytes   = kWarpBytes * kItersPerBlk;   /* 16 KiB work unit per warp      */
-constexpr int kQueueCap     = 64;                 /* stage-1 survivors queued per warp      */
-constexpr int kStageCap     = 32;                 /* match records staged per warp          */
+constexpr int kBlockBytes   = 4096;               /* work unit per warp grab (filter kernel)       */
+constexpr int kQueueCap     = 64;                 /* stage-1 survivors queued per warp (smem)      */
+constexpr int kStageCap     = 32;                 /* match records staged per warp (smem)          */
 constexpr uint32_t kFull    = 0xffffffffu;
-constexpr int32_t  kTermBit = 0x40000000;         /* goto entry flag: child ends a key      */
+constexpr int32_t  kTermBit = 0x40000000;         /* goto entry flag: child ends a key             */
 constexpr int32_t  kIdMask  = 0x3fffffff;
+constexpr long long kSegBytes = 1LL << 31;        /* candidates are uint32 offsets into a segment  */
 
-constexpr int kDfaSpan      = 64;                 /* bytes per lane in the DFA kernel       */
+constexpr int kVerThreads   = 256;
+constexpr int kVerWarps     = kVerThreads / 32;
+
+constexpr int kDfaSpan      = 64;                 /* bytes per lane in the DFA kernel              */
 constexpr int kDfaThreads   = 256;
 
 std::atomic<long long> g_launches{0};
@@ -85,26 +88,29 @@ struct ScanParams {
     int32_t max_key_bytes;
     const uint32_t *bm1;
     const uint32_t *bm2;
-    int32_t log1, log2;
+    const uint4 *anchors;          /* 2 x uint4 per slot */
+    int32_t log1, log2, logA;
     uint32_t mul1[ACB_MAX_WINDOWS];
     uint32_t mul2[ACB_MAX_WINDOWS];
     acb_match *out;
     long long cap;
     unsigned long long *count;
-    unsigned int *work_ctr;
-    long long n_blocks;
+    /* filter -> verify hand-over */
+    long long seg_begin, seg_end;  /* byte range of this launch pair */
+    long long n_blocks;            /* work units in the segment */
+    uint2 *cand;                   /* candidates: {probe position relative to seg_begin, hash2(gram)|1} */
+    unsigned long long cand_cap;
+    unsigned long long *cand_count;
+    unsigned int *work_ctr;        /* [0] next work unit, [1] filter CTAs done, [2] verify CTAs done */
 };
 
 /* ---------------------------------------------------------------- helpers */
 
-__device__ __forceinline__ uint4 load_chunk(const uint8_t *hay, long long off, long long total) {
-    if (off + kChunk <= total) return __ldg(reinterpret_cast<const uint4 *>(hay + off));
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (off < total) {                       /* ragged tail of the buffer: byte-wise, zero filled */
-        uint32_t w[4] = {0, 0, 0, 0};
-        for (int i = 0; i < kChunk && off + i < total; i++) w[i >> 2] |= (uint32_t)hay[off + i] << (8 * (i & 3));
-        v = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+/* aligned 32-bit word at byte offset a (a % 4 == 0), zero filled past the end of the buffer */
+__device__ __forceinline__ uint32_t load_word(const uint8_t *hay, long long a, long long total) {
+    if (a + 4 <= total) return __ldg(reinterpret_cast<const uint32_t *>(hay + a));
+    uint32_t v = 0;
+    for (int b = 0; b < 4; b++) if (a + b < total) v |= (uint32_t)hay[a + b] << (8 * b);
     return v;
 }
 
@@ -160,141 +166,234 @@ __device__ __forceinline__ void flush_stage(const ScanParams &p, const WarpStage
     __syncwarp();
 }
 
-/* stage 3: walk the trie from every candidate start covered by the probe at q */
-template <int STRIDE>
-__device__ __forceinline__ void walk_candidates(const ScanParams &p, const WarpStage &ws, long long q) {
-    long long h, hs, he;
-    find_haystack(p, q, h, hs, he);
+/* stage 3 (MULTI anchors only): walk the trie from the root at `start` */
+__device__ __forceinline__ void walk_from(const ScanParams &p, const WarpStage &ws, long long start,
+                                          long long h, long long hs, long long he) {
     const int L = p.L;
-    for (int j = 0; j < STRIDE; j += L) {
-        long long start = q - j;
-        if (start < hs) break;
-        int32_t st = 0;
-        for (long long i = start; i < he; ++i) {
-            int c = __ldg(p.cls + p.hay[i]);
-            int32_t nx = __ldg(p.gto + (long long)c * p.S + st);
-            if (nx < 0) break;
-            st = nx & kIdMask;
-            if (nx & kTermBit) {
-                int32_t k = __ldg(p.key_of + st);
-                emit(p, ws, (int32_t)h, (int32_t)((i - hs + 1) / L - 1), k);
-            }
+    int32_t st = 0;
+    for (long long i = start; i < he; ++i) {
+        int c = __ldg(p.cls + p.hay[i]);
+        int32_t nx = __ldg(p.gto + (long long)c * p.S + st);
+        if (nx < 0) break;
+        st = nx & kIdMask;
+        if (nx & kTermBit) {
+            int32_t k = __ldg(p.key_of + st);
+            emit(p, ws, (int32_t)h, (int32_t)((i - hs + 1) / L - 1), k);
         }
     }
 }
 
-/* drain n (<= 32) queued stage-1 survivors: stage 2 then stage 3.  Warp-collective. */
-template <int STRIDE>
-__device__ __forceinline__ void drain(const ScanParams &p, const WarpStage &ws, const uint32_t *queue,
-                                      int &qhead, int &qn, int n, long long base, int lane) {
-    __syncwarp();
-    bool act = lane < n;
-    uint32_t e = act ? queue[(qhead + lane) & (kQueueCap - 1)] : 0u;
-    qhead = (qhead + n) & (kQueueCap - 1);
-    qn -= n;
-    if (act) {
-        long long q = base + e;
-        if (q + p.gram <= p.total) {
-            uint32_t h2 = acb_hash_bytes(p.hay + q, p.gram, p.mul2);
-            uint32_t idx = h2 >> (32 - p.log2);
-            if ((__ldg(p.bm2 + (idx >> 5)) >> (idx & 31)) & 1u) walk_candidates<STRIDE>(p, ws, q);
-        }
+/* do the n (<= 20) text bytes at x equal the packed bytes kw?  (zero fill past the end of the buffer) */
+__device__ __forceinline__ bool text_equals(const ScanParams &p, long long x, int n, const uint32_t kw[5]) {
+    const long long x0 = x & ~3LL;
+    const int sh = (int)(x & 3) * 8;
+    uint32_t w[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) w[i] = load_word(p.hay, x0 + 4 * i, p.total);
+    uint32_t diff = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        uint32_t t = __funnelshift_r(w[i], w[i + 1], sh);
+        int nb = n - 4 * i;                                   /* bytes of this word that count */
+        uint32_t mask = nb >= 4 ? 0xffffffffu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+        diff |= (t ^ kw[i]) & mask;
     }
-    flush_stage(p, ws, lane);
+    return diff == 0;
 }
 
 /* ------------------------------------------------------- the filter kernel */
+/* Stage 1.  Persistent CTAs; every warp grabs 4 KiB work units.  Per iteration a lane owns 32
+ * consecutive bytes (two 16-byte loads, prefetched one iteration ahead), hashes the gram at
+ * each probe position and tests it against the bitmap in shared memory.  Survivors are queued
+ * per warp in shared memory together with hash2 of their gram (re-read through L1) and written,
+ * 32 at a time, to the global candidate list.  Work units that lie completely inside the buffer
+ * run a variant without any bounds check (GUARD = false). */
+
+__device__ __forceinline__ uint32_t lds_word(uint32_t saddr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+struct FilterCtx {
+    const uint8_t *seg;        /* hay + seg_begin */
+    uint32_t seg_len;          /* bytes of this segment: positions >= seg_len belong to the next launch */
+    long long total_rel;       /* total - seg_begin: bytes that exist from seg onwards */
+    uint32_t sbm;              /* shared-memory address of the bitmap */
+    uint32_t mul_word;         /* umulhi(h, mul_word) = bitmap word index */
+    uint32_t four;             /* == 4, opaque to the compiler so the address is one IMAD (FMA pipe) */
+    int sh_bit;                /* h >> sh_bit: bit index (low 5 bits, wrap shift) */
+    uint32_t lt_mask;
+    int lane;
+    uint2 *queue;
+    uint2 *cand;
+    unsigned long long cand_cap;
+    unsigned long long *cand_count;
+};
+
+template <bool GUARD>
+__device__ __forceinline__ uint4 ld_chunk(const FilterCtx &c, uint32_t rel) {
+    if (!GUARD || (long long)rel + 16 <= c.total_rel) return __ldg(reinterpret_cast<const uint4 *>(c.seg + rel));
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 16; i++) if ((long long)rel + i < c.total_rel) w[i >> 2] |= (uint32_t)c.seg[rel + i] << (8 * (i & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <bool GUARD>
+__device__ __forceinline__ uint32_t ld_word(const FilterCtx &c, uint32_t rel) {       /* rel % 4 == 0 */
+    if (!GUARD || (long long)rel + 4 <= c.total_rel) return __ldg(reinterpret_cast<const uint32_t *>(c.seg + rel));
+    uint32_t v = 0;
+    for (int b = 0; b < 4; b++) if ((long long)rel + b < c.total_rel) v |= (uint32_t)c.seg[rel + b] << (8 * b);
+    return v;
+}
+
+constexpr int kFChunk = 32;                       /* bytes per lane per iteration   */
+constexpr int kFWarpBytes = 32 * kFChunk;         /* 1 KiB per warp iteration       */
+constexpr int kFIters = kBlockBytes / kFWarpBytes;
+
+template <int NW, int STRIDE, bool GUARD>
+__device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (&mul)[NW], const uint32_t (&mul2)[NW],
+                                            uint32_t rel0, int &qhead, int &qtail) {
+    constexpr int kProbes = kFChunk / STRIDE;
+    const int lane = c.lane;
+    uint4 cur0 = ld_chunk<GUARD>(c, rel0 + lane * kFChunk);
+    uint4 cur1 = ld_chunk<GUARD>(c, rel0 + lane * kFChunk + 16);
+#pragma unroll 1
+    for (int it = 0; it < kFIters; ++it) {
+        const uint32_t pos0 = rel0 + it * kFWarpBytes + lane * kFChunk;
+        if (GUARD && rel0 + it * kFWarpBytes >= c.seg_len) break;                  /* warp-uniform */
+        /* prefetch the next iteration; past the unit only lane 0's first chunk is needed (look-ahead) */
+        uint4 nxt0 = make_uint4(0, 0, 0, 0), nxt1 = make_uint4(0, 0, 0, 0);
+        if (it + 1 < kFIters) {
+            nxt0 = ld_chunk<GUARD>(c, pos0 + kFWarpBytes);
+            nxt1 = ld_chunk<GUARD>(c, pos0 + kFWarpBytes + 16);
+        } else if (lane == 0) {
+            nxt0 = ld_chunk<GUARD>(c, pos0 + kFWarpBytes);
+        }
+        uint32_t W[8 + NW];
+        W[0] = cur0.x; W[1] = cur0.y; W[2] = cur0.z; W[3] = cur0.w;
+        W[4] = cur1.x; W[5] = cur1.y; W[6] = cur1.z; W[7] = cur1.w;
+        {   /* look-ahead words: the next lane's first chunk; lane 31 takes lane 0's next-iteration chunk */
+            const uint32_t cw[4] = {cur0.x, cur0.y, cur0.z, cur0.w};
+            const uint32_t nw[4] = {nxt0.x, nxt0.y, nxt0.z, nxt0.w};
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                uint32_t a = __shfl_down_sync(kFull, cw[k], 1);
+                uint32_t b = __shfl_sync(kFull, nw[k], 0);
+                W[8 + k] = (lane == 31) ? b : a;
+            }
+        }
+        /* one bitmap probe per position; hit bits are shifted into `acc` from the top */
+        uint32_t acc = 0;
+#pragma unroll
+        for (int t = 0; t < kFChunk; t += STRIDE) {
+            uint32_t h = 0;
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                const int wi = (t >> 2) + k;
+                uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
+                h += w * mul[k];
+            }
+            const uint32_t word = lds_word(__umulhi(h, c.mul_word) * c.four + c.sbm);
+            const uint32_t bit0 = __funnelshift_r(word, 0u, h >> c.sh_bit);        /* word >> (idx & 31) */
+            acc = __funnelshift_r(acc, bit0, 1);                                   /* (acc >> 1) | (bit0 << 31) */
+        }
+        uint32_t hits = (kProbes == 32) ? acc : (acc >> (32 - kProbes));           /* bit i = probe i */
+        if (GUARD && pos0 + kFChunk > c.seg_len) {                                 /* probes that start past the segment */
+            const int valid = (pos0 >= c.seg_len) ? 0 : ((int)(c.seg_len - pos0) + STRIDE - 1) / STRIDE;
+            hits = (valid <= 0) ? 0u : ((valid >= 32) ? hits : (hits & ((1u << valid) - 1u)));
+        }
+        /* queue the survivors (ballot-ranked append into the warp's ring) with hash2 of their gram */
+        unsigned any = __ballot_sync(kFull, hits != 0);
+        while (any) {
+            if (hits) {
+                const uint32_t x = pos0 + (__ffs(hits) - 1) * STRIDE;
+                hits &= hits - 1;
+                /* re-read the gram: an L1 hit, this warp loaded the line one iteration ago */
+                const uint32_t xa = x & ~3u;
+                const int sh = (int)(x & 3u) * 8;
+                uint32_t tag = 0, w0 = ld_word<GUARD>(c, xa);
+#pragma unroll
+                for (int k = 0; k < NW; k++) {
+                    const uint32_t w1 = ld_word<GUARD>(c, xa + 4 * (k + 1));
+                    tag += __funnelshift_r(w0, w1, sh) * mul2[k];
+                    w0 = w1;
+                }
+                c.queue[(qtail + __popc(any & c.lt_mask)) & (kQueueCap - 1)] = make_uint2(x, tag | 1u);
+            }
+            qtail += __popc(any);
+            if (qtail - qhead >= 32) {                                             /* spill 32 candidates to global */
+                __syncwarp();
+                unsigned long long g = 0;
+                if (lane == 0) g = atomicAdd(c.cand_count, 32ULL);
+                g = __shfl_sync(kFull, g, 0);
+                if (g + lane < c.cand_cap) c.cand[g + lane] = c.queue[(qhead + lane) & (kQueueCap - 1)];
+                qhead += 32;
+                __syncwarp();
+            }
+            any = __ballot_sync(kFull, hits != 0);
+        }
+        cur0 = nxt0;
+        cur1 = nxt1;
+    }
+}
 
 template <int NW, int STRIDE>
 __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const ScanParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int nwords = 1 << (p.log1 - 5);
     uint32_t *s_bm = smem;
-    uint32_t *s_queue = s_bm + nwords;                                   /* kWarps * kQueueCap   */
-    acb_match *s_stage = reinterpret_cast<acb_match *>(s_queue + kWarps * kQueueCap);   /* kWarps * kStageCap */
-    int *s_cnt = reinterpret_cast<int *>(s_stage + kWarps * kStageCap);  /* kWarps               */
+    uint2 *s_queue = reinterpret_cast<uint2 *>(s_bm + nwords);           /* kWarps * kQueueCap */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {   /* stage-1 bitmap -> shared memory, 16 B per thread per step */
         const uint4 *src = reinterpret_cast<const uint4 *>(p.bm1);
         uint4 *dst = reinterpret_cast<uint4 *>(s_bm);
         for (int i = tid; i < nwords / 4; i += kThreads) dst[i] = __ldg(src + i);
-        if (tid < kWarps) s_cnt[tid] = 0;
     }
     __syncthreads();
 
-    uint32_t *queue = s_queue + warp * kQueueCap;
-    WarpStage ws;
-    ws.buf = s_stage + warp * kStageCap;
-    ws.cnt = s_cnt + warp;
-    const int shift1 = 32 - p.log1;
-    uint32_t mul[NW];
+    FilterCtx c;
+    c.seg = p.hay + p.seg_begin;
+    c.seg_len = (uint32_t)(p.seg_end - p.seg_begin);                     /* <= 2^31 */
+    c.total_rel = p.total - p.seg_begin;
+    c.sbm = (uint32_t)__cvta_generic_to_shared(s_bm);
+    c.mul_word = 1u << (p.log1 - 5);
+    c.four = 4u + (uint32_t)(p.log1 >> 8);                               /* always 4 */
+    c.sh_bit = 32 - p.log1;
+    c.lt_mask = (1u << lane) - 1u;
+    c.lane = lane;
+    c.queue = s_queue + warp * kQueueCap;
+    c.cand = p.cand;
+    c.cand_cap = p.cand_cap;
+    c.cand_count = p.cand_count;
+    uint32_t mul[NW], mul2[NW];
 #pragma unroll
-    for (int k = 0; k < NW; k++) mul[k] = p.mul1[k];
+    for (int k = 0; k < NW; k++) { mul[k] = p.mul1[k]; mul2[k] = p.mul2[k]; }
+    int qhead = 0, qtail = 0;                    /* ring positions; the queue persists across work units */
+    /* units below this index need no bounds checks: unit, look-ahead and gram re-reads stay inside both
+       the segment and the buffer */
+    long long interior_end = c.total_rel - 64 < (long long)c.seg_len ? c.total_rel - 64 : (long long)c.seg_len;
+    const long long n_interior = interior_end < kBlockBytes ? 0 : interior_end / kBlockBytes;
 
     for (;;) {
         unsigned int blk = 0;
         if (lane == 0) blk = atomicAdd(p.work_ctr, 1u);
         blk = __shfl_sync(kFull, blk, 0);
         if ((long long)blk >= p.n_blocks) break;
-        const long long base = (long long)blk * kBlockBytes;
-        int qhead = 0, qn = 0;
-
-        uint4 cur = load_chunk(p.hay, base + lane * kChunk, p.total);
-#pragma unroll 1
-        for (int it = 0; it < kItersPerBlk; ++it) {
-            const long long off = base + (long long)it * kWarpBytes + lane * kChunk;
-            if (base + (long long)it * kWarpBytes >= p.total) break;       /* warp-uniform */
-            /* prefetch the next iteration (on the last one only lane 0's chunk is needed, as look-ahead) */
-            uint4 nxt = make_uint4(0, 0, 0, 0);
-            if (it + 1 < kItersPerBlk || lane == 0) nxt = load_chunk(p.hay, off + kWarpBytes, p.total);
-
-            uint32_t W[4 + NW];
-            W[0] = cur.x; W[1] = cur.y; W[2] = cur.z; W[3] = cur.w;
-            {   /* look-ahead words: the next lane's chunk; lane 31 takes lane 0's next-iteration chunk */
-                const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
-                const uint32_t nw[4] = {nxt.x, nxt.y, nxt.z, nxt.w};
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    uint32_t a = __shfl_down_sync(kFull, cw[k], 1);
-                    uint32_t b = __shfl_sync(kFull, nw[k], 0);
-                    W[4 + k] = (lane == 31) ? b : a;
-                }
-            }
-            uint32_t hits = 0;
-#pragma unroll
-            for (int t = 0; t < kChunk; t += STRIDE) {
-                uint32_t h = 0;
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    const int wi = (t >> 2) + k;
-                    uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
-                    h += w * mul[k];
-                }
-                const uint32_t idx = h >> shift1;
-                const uint32_t word = s_bm[idx >> 5];
-                hits |= ((word >> (idx & 31)) & 1u) << t;
-            }
-            if (off + kChunk > p.total) {                                   /* positions past the end */
-                long long valid = p.total - off;
-                hits = (valid <= 0) ? 0u : (hits & ((1u << valid) - 1u));
-            }
-            /* queue the survivors (ballot-ranked append into the warp's ring) */
-            unsigned any = __ballot_sync(kFull, hits != 0);
-            while (any) {
-                if (hits) {
-                    int t = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    int rank = __popc(any & ((1u << lane) - 1u));
-                    queue[(qhead + qn + rank) & (kQueueCap - 1)] = (uint32_t)(it * kWarpBytes + lane * kChunk + t);
-                }
-                qn += __popc(any);
-                if (qn >= 32) drain<STRIDE>(p, ws, queue, qhead, qn, 32, base, lane);
-                any = __ballot_sync(kFull, hits != 0);
-            }
-            cur = nxt;
+        const uint32_t rel0 = blk * (uint32_t)kBlockBytes;
+        if ((long long)blk < n_interior) filter_unit<NW, STRIDE, false>(c, mul, mul2, rel0, qhead, qtail);
+        else filter_unit<NW, STRIDE, true>(c, mul, mul2, rel0, qhead, qtail);
+    }
+    {   /* leftovers */
+        __syncwarp();
+        const int n = qtail - qhead;
+        if (n > 0) {
+            unsigned long long g = 0;
+            if (lane == 0) g = atomicAdd(p.cand_count, (unsigned long long)n);
+            g = __shfl_sync(kFull, g, 0);
+            if (lane < n && g + lane < p.cand_cap) p.cand[g + lane] = c.queue[(qhead + lane) & (kQueueCap - 1)];
         }
-        if (qn > 0) drain<STRIDE>(p, ws, queue, qhead, qn, qn, base, lane);
     }
     /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
     __syncthreads();
@@ -304,6 +403,97 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const ScanParam
         if (done == gridDim.x - 1) {
             p.work_ctr[0] = 0u;
             p.work_ctr[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+/* ------------------------------------------------------- the verify kernel */
+/* Stage 2/3.  Warps stream the candidate list.  A candidate's tag (hash2 of its gram) is first
+ * tested against the stage-2 bitmap; the few that pass are compacted into a per-warp list and
+ * resolved 32 at a time through the anchor table (open addressing, 32-byte slots):
+ * UNIQUE anchor -> the single key that can match is compared with the text;
+ * MULTI anchor  -> exact gram compare, then a trie walk from the root. */
+
+__device__ __forceinline__ void resolve(const ScanParams &p, const WarpStage &ws, uint2 c) {
+    const long long q = p.seg_begin + (long long)c.x;
+    const uint32_t tag = c.y;
+    const uint32_t amask = (1u << p.logA) - 1u;
+    uint32_t slot = tag >> (32 - p.logA);
+    long long h = -1, hs = 0, he = 0;
+    for (;;) {
+        const uint4 e0 = __ldg(p.anchors + 2 * (size_t)slot);
+        if (e0.x == 0u) break;                                 /* empty slot ends the probe sequence */
+        if (e0.x == tag) {
+            const uint4 e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
+            const uint32_t kw[5] = {e0.w, e1.x, e1.y, e1.z, e1.w};
+            const int j = (int)(e0.z & 0xffu), len = (int)((e0.z >> 8) & 0xffu);
+            const int32_t kid = (int32_t)e0.y;
+            if (h < 0) find_haystack(p, q, h, hs, he);
+            const long long start = q - j;
+            if (start >= hs) {
+                if (kid >= 0) {                                /* UNIQUE: the only key that can match at start */
+                    if (start + len <= he && text_equals(p, start, len, kw))
+                        emit(p, ws, (int32_t)h, (int32_t)((start + len - hs) / p.L - 1), kid);
+                } else if (q + len <= he && text_equals(p, q, len, kw)) {   /* MULTI: exact gram, then the trie */
+                    walk_from(p, ws, start, h, hs, he);
+                }
+            }
+        }
+        slot = (slot + 1) & amask;
+    }
+}
+
+__global__ void __launch_bounds__(kVerThreads) acb_verify_kernel(const ScanParams p) {
+    __shared__ acb_match s_stage[kVerWarps * kStageCap];
+    __shared__ int s_cnt[kVerWarps];
+    __shared__ uint2 s_list[kVerWarps * 64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < kVerWarps) s_cnt[tid] = 0;
+    __syncthreads();
+    WarpStage ws;
+    ws.buf = s_stage + warp * kStageCap;
+    ws.cnt = s_cnt + warp;
+    uint2 *list = s_list + warp * 64;
+    int lhead = 0, ltail = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int sh2 = 32 - p.log2;
+
+    const unsigned long long found = *p.cand_count;
+    const unsigned long long n = found < p.cand_cap ? found : p.cand_cap;
+    const unsigned long long gwarp = (unsigned long long)blockIdx.x * kVerWarps + warp;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * kVerWarps;
+    for (unsigned long long w0 = gwarp * 32; w0 < n; w0 += nwarps * 32) {
+        const unsigned long long i = w0 + lane;
+        uint2 c = make_uint2(0, 0);
+        bool pass = false;
+        if (i < n) {
+            c = p.cand[i];
+            const uint32_t idx = c.y >> sh2;
+            pass = (__ldg(p.bm2 + (idx >> 5)) >> (idx & 31)) & 1u;
+        }
+        const unsigned m = __ballot_sync(kFull, pass);
+        if (pass) list[(ltail + __popc(m & lt_mask)) & 63] = c;
+        ltail += __popc(m);
+        if (ltail - lhead >= 32) {
+            __syncwarp();
+            resolve(p, ws, list[(lhead + lane) & 63]);
+            lhead += 32;
+            flush_stage(p, ws, lane);
+        }
+    }
+    __syncwarp();
+    if (lane < ltail - lhead) resolve(p, ws, list[(lhead + lane) & 63]);
+    flush_stage(p, ws, lane);
+    /* last CTA out: re-arm the candidate counter; flag an overflowed candidate list in *count */
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        unsigned int done = atomicAdd(p.work_ctr + 2, 1u);
+        if (done == gridDim.x - 1) {
+            if (found > p.cand_cap) *p.count = ~0ULL;       /* results incomplete: caller must retry */
+            *p.cand_count = 0ULL;
+            p.work_ctr[2] = 0u;
             __threadfence();
         }
     }
@@ -360,13 +550,17 @@ __global__ void __launch_bounds__(kDfaThreads) acb_dfa_kernel(const ScanParams p
 struct acb_table {
     int device = 0;
     int sm_count = 0;
-    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log2 = 15;
+    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log2 = 15, logA = 10;
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     uint8_t *d_cls = nullptr;
     int32_t *d_goto = nullptr, *d_fail = nullptr, *d_keyof = nullptr, *d_outptr = nullptr, *d_outidx = nullptr, *d_keylen = nullptr;
-    uint32_t *d_bm1 = nullptr, *d_bm2 = nullptr;
+    uint32_t *d_bm1 = nullptr, *d_bm2 = nullptr, *d_anchors = nullptr;
     unsigned int *d_work = nullptr;
+    uint2 *d_cand = nullptr;                 /* candidate list (filter -> verify) */
+    unsigned long long cand_cap = 0;
+    unsigned long long *d_cand_count = nullptr;
+    bool cand_worst_case = false;
     long long dev_bytes = 0;
     std::vector<int32_t> key_len;            /* host copy, for sorting records */
     /* workspace of acb_scan_host */
@@ -403,8 +597,8 @@ extern "C" void acb_table_free(acb_table *tb) {
     if (!tb) return;
     cudaSetDevice(tb->device);
     cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
-    cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_bm2);
-    cudaFree(tb->d_work); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
+    cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_bm2); cudaFree(tb->d_anchors);
+    cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->d_cand_count); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
     if (tb->h_count) cudaFreeHost(tb->h_count);
     if (tb->h_out) cudaFreeHost(tb->h_out);
     if (tb->ev0) cudaEventDestroy(tb->ev0);
@@ -433,7 +627,7 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { acb_set_error("cudaGetDeviceProperties failed"); rc = ACB_ECUDA; break; }
         tb->sm_count = prop.multiProcessorCount;
         tb->S = f.n_states; tb->K = f.n_classes; tb->L = f.letter_bytes; tb->n_keys = f.n_keys;
-        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log2 = f.log2_bits2;
+        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log2 = f.log2_bits2; tb->logA = f.log2_anchor_slots;
         tb->min_key_bytes = f.min_key_bytes; tb->max_key_bytes = f.max_key_bytes;
         acb_hash_multipliers(tb->gram, 1, tb->mul1);
         acb_hash_multipliers(tb->gram, 2, tb->mul2);
@@ -453,8 +647,11 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if ((rc = upload(&tb->d_keylen, f.key_len, (size_t)f.n_keys, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_bm1, f.bitmap1, (size_t)1 << (f.log2_bits1 - 5), tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_bm2, f.bitmap2, (size_t)1 << (f.log2_bits2 - 5), tb->dev_bytes))) break;
-        unsigned int zero[2] = {0, 0};      /* [0] next work unit, [1] CTAs finished (re-armed by the kernel) */
-        if ((rc = upload(&tb->d_work, zero, 2, tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_anchors, f.anchors, (size_t)8 << f.log2_anchor_slots, tb->dev_bytes))) break;
+        unsigned int zero[4] = {0, 0, 0, 0};   /* work counters, re-armed by the kernels themselves */
+        if ((rc = upload(&tb->d_work, zero, 4, tb->dev_bytes))) break;
+        unsigned long long zero64 = 0;
+        if ((rc = upload(&tb->d_cand_count, &zero64, 1, tb->dev_bytes))) break;
     } while (0);
     if (rc != ACB_OK) { acb_table_free(tb); return rc; }
     *out = tb;
@@ -462,6 +659,11 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
 }
 
 extern "C" int64_t acb_table_device_bytes(const acb_table *tb) { return tb ? tb->dev_bytes : 0; }
+extern "C" int acb_table_reserve_candidates(acb_table *tb, int worst_case) {
+    if (!tb) return ACB_EINVAL;
+    tb->cand_worst_case = worst_case != 0;
+    return ACB_OK;
+}
 extern "C" int64_t acb_launch_count(void) { return g_launches.load(); }
 extern "C" int acb_set_kernel_timing(int enabled) { g_timing.store(enabled ? 1 : 0); return ACB_OK; }
 extern "C" float acb_last_kernel_ms(void) { return g_last_ms; }
@@ -469,12 +671,13 @@ extern "C" float acb_last_kernel_ms(void) { return g_last_ms; }
 /* ------------------------------------------------------------- launching */
 
 static size_t filter_smem_bytes(int log1) {
-    return ((size_t)1 << (log1 - 3)) + (size_t)kWarps * kQueueCap * 4 + (size_t)kWarps * kStageCap * sizeof(acb_match) + (size_t)kWarps * 4;
+    return ((size_t)1 << (log1 - 3)) + (size_t)kWarps * kQueueCap * sizeof(uint2);
 }
 
 template <int NW, int STRIDE>
-static int launch_filter_t(const ScanParams &p, int grid, size_t smem, cudaStream_t s) {
+static int launch_filter_t(const ScanParams &p, int grid, cudaStream_t s) {
     auto kern = acb_filter_kernel<NW, STRIDE>;
+    const size_t smem = filter_smem_bytes(p.log1);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
@@ -483,27 +686,39 @@ static int launch_filter_t(const ScanParams &p, int grid, size_t smem, cudaStrea
 }
 
 template <int NW>
-static int launch_filter_s(const ScanParams &p, int stride, int grid, size_t smem, cudaStream_t s) {
+static int launch_filter_s(const ScanParams &p, int stride, int grid, cudaStream_t s) {
     switch (stride) {
-        case 1:  return launch_filter_t<NW, 1>(p, grid, smem, s);
-        case 2:  return launch_filter_t<NW, 2>(p, grid, smem, s);
-        case 4:  return launch_filter_t<NW, 4>(p, grid, smem, s);
-        case 8:  return launch_filter_t<NW, 8>(p, grid, smem, s);
-        case 16: return launch_filter_t<NW, 16>(p, grid, smem, s);
+        case 1:  return launch_filter_t<NW, 1>(p, grid, s);
+        case 2:  return launch_filter_t<NW, 2>(p, grid, s);
+        case 4:  return launch_filter_t<NW, 4>(p, grid, s);
+        case 8:  return launch_filter_t<NW, 8>(p, grid, s);
+        case 16: return launch_filter_t<NW, 16>(p, grid, s);
     }
     acb_set_error("unsupported filter stride %d", stride);
     return ACB_EINVAL;
 }
 
-static int launch_filter(const ScanParams &p, int stride, int grid, size_t smem, cudaStream_t s) {
+static int launch_filter(const ScanParams &p, int stride, int grid, cudaStream_t s) {
     switch ((p.gram + 3) / 4) {
-        case 1: return launch_filter_s<1>(p, stride, grid, smem, s);
-        case 2: return launch_filter_s<2>(p, stride, grid, smem, s);
-        case 3: return launch_filter_s<3>(p, stride, grid, smem, s);
-        case 4: return launch_filter_s<4>(p, stride, grid, smem, s);
+        case 1: return launch_filter_s<1>(p, stride, grid, s);
+        case 2: return launch_filter_s<2>(p, stride, grid, s);
+        case 3: return launch_filter_s<3>(p, stride, grid, s);
+        case 4: return launch_filter_s<4>(p, stride, grid, s);
     }
     acb_set_error("unsupported gram length %d", p.gram);
     return ACB_EINVAL;
+}
+
+/* candidate list capacity for a segment of `seg` bytes: 1/8 of the probe positions by default,
+ * every probe position once a scan has reported an overflow (acb_scan_host retries that way) */
+static int ensure_candidates(acb_table *tb, long long seg, bool worst_case) {
+    unsigned long long probes = (unsigned long long)(seg / tb->stride + 1);
+    unsigned long long want = worst_case ? probes : std::max<unsigned long long>(1ULL << 20, probes / 8);
+    if (tb->d_cand && tb->cand_cap >= want) return ACB_OK;
+    if (tb->d_cand) { cudaFree(tb->d_cand); tb->d_cand = nullptr; tb->cand_cap = 0; }
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_cand), (size_t)want * sizeof(uint2)));
+    tb->cand_cap = want;
+    return ACB_OK;
 }
 
 extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t total_bytes,
@@ -530,12 +745,12 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     p.cls = tb->d_cls; p.gto = tb->d_goto; p.fail = tb->d_fail; p.key_of = tb->d_keyof;
     p.out_ptr = tb->d_outptr; p.out_idx = tb->d_outidx; p.key_len = tb->d_keylen;
     p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.max_key_bytes = tb->max_key_bytes;
-    p.bm1 = tb->d_bm1; p.bm2 = tb->d_bm2; p.log1 = tb->log1; p.log2 = tb->log2;
+    p.bm1 = tb->d_bm1; p.bm2 = tb->d_bm2; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
+    p.log1 = tb->log1; p.log2 = tb->log2; p.logA = tb->logA;
     memcpy(p.mul1, tb->mul1, sizeof(p.mul1));
     memcpy(p.mul2, tb->mul2, sizeof(p.mul2));
     p.out = d_out; p.cap = cap; p.count = reinterpret_cast<unsigned long long *>(d_count);
     p.work_ctr = tb->d_work;
-    p.n_blocks = (total_bytes + kBlockBytes - 1) / kBlockBytes;
 
     if (algo == ACB_ALGO_AUTO) algo = ACB_ALGO_FILTER;
     if (tb->n_keys == 0) return ACB_OK;                     /* empty key set: nothing can match */
@@ -544,12 +759,22 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
         if (!tb->ev0) { CUDA_TRY(cudaEventCreate(&tb->ev0)); CUDA_TRY(cudaEventCreate(&tb->ev1)); }
         CUDA_TRY(cudaEventRecord(tb->ev0, s));
     }
-    int rc;
     if (algo == ACB_ALGO_FILTER) {
-        if (p.n_blocks > 0xfffffff0LL) { acb_set_error("batch too large for one launch"); return ACB_ERANGE; }
-        size_t smem = filter_smem_bytes(tb->log1);
-        int grid = (int)std::min<long long>(tb->sm_count, p.n_blocks);
-        rc = launch_filter(p, tb->stride, grid, smem, s);
+        int rc = ensure_candidates(tb, std::min<long long>(total_bytes, kSegBytes), tb->cand_worst_case);
+        if (rc != ACB_OK) return rc;
+        p.cand = tb->d_cand; p.cand_cap = tb->cand_cap; p.cand_count = tb->d_cand_count;
+        for (long long seg = 0; seg < total_bytes; seg += kSegBytes) {
+            p.seg_begin = seg;
+            p.seg_end = std::min<long long>(seg + kSegBytes, total_bytes);
+            p.n_blocks = (p.seg_end - p.seg_begin + kBlockBytes - 1) / kBlockBytes;
+            int grid = (int)std::min<long long>(tb->sm_count, p.n_blocks);
+            rc = launch_filter(p, tb->stride, grid, s);
+            if (rc != ACB_OK) return rc;
+            acb_verify_kernel<<<tb->sm_count * 4, kVerThreads, 0, s>>>(p);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { acb_set_error("verify kernel launch failed: %s", cudaGetErrorString(e)); return ACB_ECUDA; }
+            g_launches.fetch_add(1);
+        }
     } else if (algo == ACB_ALGO_DFA) {
         long long spans = (total_bytes + kDfaSpan - 1) / kDfaSpan;
         long long grid = (spans + kDfaThreads - 1) / kDfaThreads;
@@ -558,12 +783,10 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { acb_set_error("DFA kernel launch failed: %s", cudaGetErrorString(e)); return ACB_ECUDA; }
         g_launches.fetch_add(1);
-        rc = ACB_OK;
     } else {
         acb_set_error("unknown algo %d", algo);
         return ACB_EINVAL;
     }
-    if (rc != ACB_OK) return rc;
     if (timing) {
         CUDA_TRY(cudaEventRecord(tb->ev1, s));
         CUDA_TRY(cudaEventSynchronize(tb->ev1));
@@ -610,6 +833,11 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
     CUDA_TRY(cudaMemcpyAsync(tb->h_count, tb->w_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     unsigned long long n = *tb->h_count;
+    if (n == ~0ULL) {                                           /* candidate list overflowed: redo with room for every probe */
+        if (tb->cand_worst_case) { acb_set_error("candidate list overflow even at worst-case capacity"); return ACB_ECUDA; }
+        tb->cand_worst_case = true;
+        return acb_scan_host(tb, hay, total_bytes, offsets, n_hay, stride_bytes, out, cap, n_found, algo, sort);
+    }
     *n_found = (int64_t)n;
     if (n > (unsigned long long)cap) {
         acb_set_error("match buffer too small: %llu matches, capacity %lld", n, (long long)cap);

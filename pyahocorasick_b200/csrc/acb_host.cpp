@@ -102,8 +102,8 @@ struct Flat {
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint8_t byte_class[256];
     std::vector<int32_t> goto_cm, fail, key_of, out_ptr, out_idx, key_len;
-    int32_t gram = 0, stride = 0, log1 = 0, log2 = 0;
-    std::vector<uint32_t> bm1, bm2;
+    int32_t gram = 0, stride = 0, log1 = 0, log2 = 0, logA = 0;
+    std::vector<uint32_t> bm1, bm2, anchors;
 };
 
 } // namespace
@@ -253,7 +253,7 @@ extern "C" int64_t acb_trie_links(const acb_trie *t) { return (t && t->live_node
 namespace {
 
 struct FilterChoice {
-    int g = 0, s = 0, log1 = 0, log2 = 0;
+    int g = 0, s = 0, log1 = 0;
     double cost = 1e300;
 };
 
@@ -286,19 +286,51 @@ static int ceil_log2_u64(uint64_t x) {
 
 } // namespace
 
+/* unique key below node v (live_below == 1): its id and all of its bytes */
+static int32_t unique_key_below(const acb_trie *t, int32_t v, std::vector<uint8_t> &bytes) {
+    bytes.clear();
+    std::vector<uint8_t> up;
+    for (int32_t x = v; x > 0; x = t->nodes[x].parent) up.push_back(t->nodes[x].byte);
+    bytes.assign(up.rbegin(), up.rend());
+    int32_t x = v;
+    while (t->nodes[x].key_id < 0) {
+        int32_t nxt = -1;
+        for (int32_t c = t->nodes[x].first_child; c >= 0; c = t->nodes[c].next_sibling)
+            if (t->nodes[c].live_below > 0) { nxt = c; break; }
+        if (nxt < 0) return -1;            /* cannot happen for live_below == 1 */
+        bytes.push_back(t->nodes[nxt].byte);
+        x = nxt;
+    }
+    return t->nodes[x].key_id;
+}
+
+/* Gram filter + anchor table (DESIGN.md "filter kernel").
+ *
+ * Every occurrence of a key K at byte position p contains exactly one probe position
+ * q = p + j, q a multiple of the stride s, with j in {0, L, .., s-L}; the g bytes at q are
+ * K[j..j+g).  Stage 1 is a bitmap over hash1(gram) (shared memory), stage 2 a bitmap over
+ * hash2(gram) (global memory).  The anchor table maps hash2(gram) to the
+ * trie nodes at depth j+g whose last g bytes are that gram:
+ *   - a node with exactly one key below it (and that key <= 20 bytes) becomes a UNIQUE entry
+ *     carrying the key itself: the device compares the text at q-j with the key directly;
+ *   - otherwise the whole (gram, j) group collapses to one MULTI entry carrying the gram: the
+ *     device walks the trie from the root at q-j.
+ * Entry = 8 x uint32: tag (hash2|1, 0 = empty), key_id (-1 = MULTI), j | len<<8, 20 key/gram bytes. */
 static void build_filter(acb_trie *t, Flat &f) {
     const int L = t->letter_bytes;
     const int m = f.min_key_bytes;
-    /* m-prefixes = live nodes at byte depth m (every live key is at least m long) */
+    /* live nodes down to depth m, with depths */
+    std::vector<int32_t> depth(t->nodes.size(), -1);
+    std::vector<int32_t> upto_m;           /* nodes with 1 <= depth <= m */
     std::vector<std::vector<uint8_t>> prefixes;
     {
-        /* BFS ids are depth-ordered; recover depth by walking (cheap: done once) */
-        std::vector<int32_t> depth(t->nodes.size(), -1);
         std::vector<int32_t> stack;
-        if (!t->nodes.empty() && t->nodes[0].live_below > 0) { depth[0] = 0; stack.push_back(0); }
+        depth[0] = 0;
+        stack.push_back(0);
         while (!stack.empty()) {
             int32_t nd = stack.back();
             stack.pop_back();
+            if (depth[nd] > 0) upto_m.push_back(nd);
             if (depth[nd] == m) {
                 std::vector<uint8_t> p(m);
                 int32_t x = nd;
@@ -331,33 +363,98 @@ static void build_filter(acb_trie *t, Flat &f) {
             const double E = (double)grams.size();
             int log1 = std::min(20, std::max(13, ceil_log2_u64((uint64_t)(E * 64.0) + 1)));
             if (forced_l1) log1 = forced_l1;
-            int log2 = std::min(30, std::max(15, ceil_log2_u64((uint64_t)(E * 128.0) + 1)));
             double space = std::pow(Kb, (double)g);
             double p_true = std::min(1.0, E / space);
             double fill1 = std::min(1.0, E / std::pow(2.0, log1));
-            double fill2 = std::min(1.0, E / std::pow(2.0, log2));
             int nw = (g + 3) / 4;
             double pass1 = p_true + (1 - p_true) * fill1;
-            double pass2 = p_true + (1 - p_true) * fill1 * fill2;
-            double cost = ((4.0 + 3.0 * nw) + pass1 * 40.0 + pass2 * (s / L) * 150.0) / s;
+            /* per byte: probe instructions + anchor lookups for stage-1 survivors + key compares */
+            double cost = ((4.0 + 3.0 * nw) + pass1 * 40.0 + p_true * (s / L) * 40.0) / s;
             if (cost < best.cost) {
-                best.g = g; best.s = s; best.log1 = log1; best.log2 = log2; best.cost = cost;
+                best.g = g; best.s = s; best.log1 = log1; best.cost = cost;
                 best_grams.swap(grams);
             }
         }
     }
-    f.gram = best.g;
-    f.stride = best.s;
+    const int g = best.g, s = best.s;
+    f.gram = g;
+    f.stride = s;
     f.log1 = best.log1;
-    f.log2 = best.log2;
     f.bm1.assign((size_t)1 << (best.log1 - 5), 0);
-    f.bm2.assign((size_t)1 << (best.log2 - 5), 0);
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
-    acb_hash_multipliers(best.g, 1, mul1);
-    acb_hash_multipliers(best.g, 2, mul2);
-    for (const auto &gr : best_grams) {
-        set_bit(f.bm1, acb_hash_bytes(gr.data(), best.g, mul1) >> (32 - best.log1));
-        set_bit(f.bm2, acb_hash_bytes(gr.data(), best.g, mul2) >> (32 - best.log2));
+    acb_hash_multipliers(g, 1, mul1);
+    acb_hash_multipliers(g, 2, mul2);
+    for (const auto &gr : best_grams) set_bit(f.bm1, acb_hash_bytes(gr.data(), g, mul1) >> (32 - best.log1));
+
+    /* ---- anchor table ---- */
+    struct Cand { std::vector<uint8_t> gram; int j; int32_t node; };
+    std::vector<Cand> cands;
+    for (int32_t nd : upto_m) {
+        int d = depth[nd];
+        int j = d - g;
+        if (j < 0 || j > s - L || (j % L)) continue;
+        Cand c;
+        c.gram.resize(g);
+        int32_t x = nd;
+        for (int i = g - 1; i >= 0; i--) { c.gram[i] = t->nodes[x].byte; x = t->nodes[x].parent; }
+        c.j = j;
+        c.node = nd;
+        cands.push_back(std::move(c));
+    }
+    std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) {
+        if (a.j != b.j) return a.j < b.j;
+        return a.gram < b.gram;
+    });
+    struct Entry { uint32_t w[8]; };
+    std::vector<Entry> entries;
+    std::vector<uint8_t> kb;
+    auto pack = [](Entry &e, uint32_t tag, int32_t key_id, int j, int len, const uint8_t *bytes) {
+        memset(&e, 0, sizeof(e));
+        e.w[0] = tag;
+        e.w[1] = (uint32_t)key_id;
+        e.w[2] = (uint32_t)j | ((uint32_t)len << 8);
+        for (int i = 0; i < len && i < 20; i++) e.w[3 + (i >> 2)] |= (uint32_t)bytes[i] << (8 * (i & 3));
+    };
+    for (size_t a = 0; a < cands.size();) {
+        size_t b = a;
+        while (b < cands.size() && cands[b].j == cands[a].j && cands[b].gram == cands[a].gram) b++;
+        uint32_t tag = acb_hash_bytes(cands[a].gram.data(), g, mul2) | 1u;
+        bool multi = false;
+        std::vector<Entry> group;
+        for (size_t i = a; i < b && !multi; i++) {
+            const Node &nd = t->nodes[cands[i].node];
+            if (nd.live_below != 1) { multi = true; break; }
+            int32_t kid = unique_key_below(t, cands[i].node, kb);
+            if (kid < 0 || kb.size() > 20) { multi = true; break; }
+            Entry e;
+            pack(e, tag, kid, cands[a].j, (int)kb.size(), kb.data());
+            group.push_back(e);
+        }
+        if (multi) {
+            Entry e;
+            pack(e, tag, -1, cands[a].j, g, cands[a].gram.data());
+            entries.push_back(e);
+        } else {
+            entries.insert(entries.end(), group.begin(), group.end());
+        }
+        a = b;
+    }
+    /* stage-2 bitmap over the tags (bit index = high bits of hash2): rejects almost every stage-1
+     * false positive with one load, so that only real anchors reach the table below */
+    int log2 = std::min(30, std::max(15, ceil_log2_u64((uint64_t)entries.size() * 128 + 1)));
+    f.log2 = log2;
+    f.bm2.assign((size_t)1 << (log2 - 5), 0);
+    for (const Entry &e : entries) set_bit(f.bm2, e.w[0] >> (32 - log2));
+    int logA = std::max(10, ceil_log2_u64((uint64_t)entries.size() * 4 + 1));     /* load factor <= 1/4 */
+    if (logA > 28) logA = 28;
+    while (((size_t)1 << logA) < entries.size() + entries.size() / 4 + 1) logA++;
+    f.logA = logA;
+    const size_t slots = (size_t)1 << logA, mask = slots - 1;
+    f.anchors.assign(slots * 8, 0);
+    for (const Entry &e : entries) {
+        size_t i = e.w[0] >> (32 - logA);                   /* slot from the high bits of hash2 */
+        while (f.anchors[i * 8] != 0) i = (i + 1) & mask;
+        memcpy(&f.anchors[i * 8], e.w, sizeof(e.w));
     }
 }
 
@@ -465,9 +562,10 @@ extern "C" int acb_trie_make_automaton(acb_trie *t, int32_t *built) {
 
         if (f.n_keys > 0) build_filter(t, f);
         else {                                               /* nothing can ever match */
-            f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.log2 = 15;
+            f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.log2 = 15; f.logA = 10;
             f.bm1.assign((size_t)1 << (13 - 5), 0);
             f.bm2.assign((size_t)1 << (15 - 5), 0);
+            f.anchors.assign(((size_t)1 << 10) * 8, 0);
         }
         f.valid = true;
         t->kind = ACB_AHOCORASICK;                           /* :639 */
@@ -502,7 +600,9 @@ extern "C" int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out) {
     out->stride = f.stride;
     out->log2_bits1 = f.log1;
     out->log2_bits2 = f.log2;
+    out->log2_anchor_slots = f.logA;
     out->bitmap1 = f.bm1.data();
     out->bitmap2 = f.bm2.data();
+    out->anchors = f.anchors.data();
     return ACB_OK;
 }

@@ -4,7 +4,7 @@ exercise the host logic (filter construction, flattening, the Python API layer) 
 a GPU; it is never imported by the product.
 
 emul_filter() restates acb_filter_kernel: stage-1 bitmap probe at every `stride`-th byte,
-stage-2 bitmap, then the trie walk from each candidate start.  emul_dfa() restates
+then the anchor table (UNIQUE anchors compare the key, MULTI anchors walk the trie).  emul_dfa() restates
 acb_dfa_kernel (goto / fail / CSR outputs).  Both return records sorted the way
 acb_scan_host sorts them.
 """
@@ -64,14 +64,35 @@ def _sorted(recs, key_len):
     return recs
 
 
-def emul_filter(f, buf, offsets=None, stride_bytes=0):
-    L, g, s = f["letter_bytes"], f["gram_bytes"], f["stride"]
-    S = f["n_states"]
-    mul1, mul2 = multipliers(g, 1), multipliers(g, 2)
-    l1, l2 = f["log2_bits1"], f["log2_bits2"]
-    total = len(buf)
-    n_hay = (len(offsets) - 1) if offsets is not None else total // stride_bytes
+def _walk(f, buf, start, h, hs, he, recs):
+    L = f["letter_bytes"]
     cls, gto, key_of = f["byte_class"], f["goto_cm"], f["key_of"]
+    st = 0
+    for i in range(start, he):
+        nx = int(gto[cls[buf[i]], st])
+        if nx < 0:
+            break
+        st = nx
+        k = int(key_of[st])
+        if k >= 0:
+            recs.append((h, (i - hs + 1) // L - 1, k))
+
+
+def _entry_bytes(e, n):
+    raw = b"".join(int(w).to_bytes(4, "little") for w in e[3:8])
+    return raw[:n]
+
+
+def emul_filter(f, buf, offsets=None, stride_bytes=0):
+    """stage 1 bitmap -> anchor table (UNIQUE: direct key compare, MULTI: trie walk)"""
+    L, g, s = f["letter_bytes"], f["gram_bytes"], f["stride"]
+    mul1, mul2 = multipliers(g, 1), multipliers(g, 2)
+    l1, lA = f["log2_bits1"], f["log2_anchor_slots"]
+    anchors = f["anchors"]
+    amask = (1 << lA) - 1
+    total = len(buf)
+    raw = bytes(bytearray(buf))
+    n_hay = (len(offsets) - 1) if offsets is not None else total // stride_bytes
     recs = []
     if f["n_keys"] == 0:
         return recs
@@ -80,22 +101,29 @@ def emul_filter(f, buf, offsets=None, stride_bytes=0):
             continue
         if q + g > total:
             continue
-        if not _bit(f["bitmap2"], hash_bytes(buf, q, g, mul2) >> (32 - l2)):
+        tag = hash_bytes(buf, q, g, mul2) | 1
+        if not _bit(f["bitmap2"], tag >> (32 - f["log2_bits2"])):
             continue
-        h, hs, he = _bounds(q, offsets, stride_bytes, n_hay)
-        for j in range(0, s, L):
-            start = q - j
-            if start < hs:
+        slot = tag >> (32 - lA)
+        bounds = None
+        while True:
+            e = anchors[slot]
+            if int(e[0]) == 0:
                 break
-            st = 0
-            for i in range(start, he):
-                nx = int(gto[cls[buf[i]], st])
-                if nx < 0:
-                    break
-                st = nx
-                k = int(key_of[st])
-                if k >= 0:
-                    recs.append((h, (i - hs + 1) // L - 1, k))
+            if int(e[0]) == tag:
+                if bounds is None:
+                    bounds = _bounds(q, offsets, stride_bytes, n_hay)
+                h, hs, he = bounds
+                kid = int(np.int32(np.uint32(e[1])))
+                j, ln = int(e[2]) & 0xFF, (int(e[2]) >> 8) & 0xFF
+                start = q - j
+                if start >= hs:
+                    if kid >= 0:
+                        if start + ln <= he and raw[start:start + ln] == _entry_bytes(e, ln):
+                            recs.append((h, (start + ln - hs) // L - 1, kid))
+                    elif raw[q:q + ln] == _entry_bytes(e, ln):
+                        _walk(f, buf, start, h, hs, he, recs)
+            slot = (slot + 1) & amask
     return _sorted(recs, f["key_len"])
 
 

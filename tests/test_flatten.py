@@ -106,6 +106,10 @@ def test_filter_choice_for_baseline_configs():
     assert (f["gram_bytes"], f["stride"], f["log2_bits1"]) == (4, 1, 20)
     fill = np.unpackbits(f["bitmap1"].view(np.uint8)).mean()
     assert 0.005 < fill < 0.012
+    a = f["anchors"]
+    used = a[a[:, 0] != 0]
+    assert 9000 < len(used) <= 10000 and len(used) * 4 <= len(a)         # one anchor per distinct 4-byte prefix
+    assert (used[:, 1].astype(np.int32) >= 0).mean() > 0.95               # almost all UNIQUE
 
 
 def test_state_machine_and_removal():
