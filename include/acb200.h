@@ -115,12 +115,12 @@ typedef struct acb_flat_view {
     /* prefilter (see DESIGN.md "filter kernel") */
     int32_t        gram_bytes;    /* g : bytes hashed per probe                               */
     int32_t        stride;        /* s : probe every s-th byte position                       */
-    int32_t        log2_bits1;    /* stage-1 bitmap (shared memory) has 2^log2_bits1 bits     */
-    int32_t        log2_bits2;    /* stage-2 bitmap (global memory) has 2^log2_bits2 bits     */
+    int32_t        log2_bits1;    /* n: the two bitmaps share 2^n bits of shared memory, 7/8 : 1/8 */
+    int32_t        log2_bits2;    /* n - 3: the stage-2 bitmap has 2^(n-3) bits               */
     int32_t        log2_anchor_slots; /* anchor table has 2^n slots of 8 uint32 (32 B)        */
-    const uint32_t *bitmap1;      /* bit index = hash1(gram) >> (32 - log2_bits1)             */
-    const uint32_t *bitmap2;      /* bit index = hash2(gram) >> (32 - log2_bits2)             */
-    const uint32_t *anchors;      /* slot: tag(hash2|1, 0=empty), key_id(-1=MULTI), j|len<<8, 20 bytes */
+    const uint32_t *bitmap1;      /* 7<<(n-8) words: word = umulhi(hash1, 7<<(n-8)), bit = (hash1>>(32-n))&31 */
+    const uint32_t *bitmap2;      /* 1<<(n-8) words: word = hash2>>(40-n),          bit = (hash2>>(35-n))&31 */
+    const uint32_t *anchors;      /* slot: tag(hash2|1, 0=empty), key_id(-1=MULTI), j|len<<8|last<<16, 20 bytes */
 } acb_flat_view;
 
 int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out);

@@ -430,8 +430,8 @@ class Automaton:
             out_idx=arr(fv.out_idx, n_out, np.int32), key_len=arr(fv.key_len, fv.n_keys, np.int32),
             gram_bytes=fv.gram_bytes, stride=fv.stride, log2_bits1=fv.log2_bits1, log2_bits2=fv.log2_bits2,
             log2_anchor_slots=fv.log2_anchor_slots,
-            bitmap1=arr(fv.bitmap1, 1 << (fv.log2_bits1 - 5), np.uint32),
-            bitmap2=arr(fv.bitmap2, 1 << (fv.log2_bits2 - 5), np.uint32),
+            bitmap1=arr(fv.bitmap1, 7 << (fv.log2_bits1 - 8), np.uint32),
+            bitmap2=arr(fv.bitmap2, 1 << (fv.log2_bits1 - 8), np.uint32),
             anchors=arr(fv.anchors, 8 << fv.log2_anchor_slots, np.uint32).reshape(-1, 8))
 
     # ------------------------------------------------------------------ GPU scan plumbing

@@ -3,8 +3,10 @@
  *
  * ACB_ALGO_FILTER (the fast path) is two launches per <= 2 GiB segment of the batch:
  *
- *  acb_filter_kernel<NW,STRIDE> streams the haystack bytes once (stage 1) and appends the
- *  few surviving probe positions to a candidate list; acb_verify_kernel resolves them.
+ *  acb_filter_kernel<NW,STRIDE> streams the haystack bytes once (stage 1); each warp resolves
+ *  its own survivors between work units (stage 2/3) while the other warps keep streaming.
+ *  Only when a warp's queue overflows are candidates spilled to a global list, which
+ *  acb_verify_kernel resolves afterwards (normally that list is empty).
  *      Start-anchored search.  Every probe position is first tested against a gram
  *      bitmap held in shared memory (stage 1).  Survivors look their gram up in the
  *      anchor table in global memory (stage 2, one 32-byte slot): a UNIQUE anchor
@@ -52,7 +54,7 @@ namespace {
 constexpr int kThreads      = 1024;               /* filter kernel: one CTA per SM                 */
 constexpr int kWarps        = kThreads / 32;
 constexpr int kBlockBytes   = 4096;               /* work unit per warp grab (filter kernel)       */
-constexpr int kQueueCap     = 64;                 /* stage-1 survivors queued per warp (smem)      */
+constexpr int kQueueCap     = 128;                /* stage-1 survivors queued per warp (smem)      */
 constexpr int kStageCap     = 32;                 /* match records staged per warp (smem)          */
 constexpr uint32_t kFull    = 0xffffffffu;
 constexpr int32_t  kTermBit = 0x40000000;         /* goto entry flag: child ends a key             */
@@ -102,6 +104,9 @@ struct ScanParams {
     unsigned long long cand_cap;
     unsigned long long *cand_count;
     unsigned int *work_ctr;        /* [0] next work unit, [1] filter CTAs done, [2] verify CTAs done */
+    int stride_shift;              /* log2(stride_bytes) when it is a power of two, else -1 */
+    int letter_shift;              /* log2(L) */
+    int inline_resolve;            /* 1: warps resolve their own candidates between work units; 0: all go to the list */
 };
 
 /* ---------------------------------------------------------------- helpers */
@@ -116,7 +121,9 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t *hay, long long a, l
 
 __device__ __forceinline__ void find_haystack(const ScanParams &p, long long q, long long &h, long long &hs, long long &he) {
     if (p.offsets == nullptr) {
-        h = q / p.stride_bytes;
+        if (p.stride_shift >= 0) h = q >> p.stride_shift;
+        else if (p.total <= 0xffffffffLL) h = (long long)((uint32_t)q / (uint32_t)p.stride_bytes);
+        else h = q / p.stride_bytes;
         hs = h * p.stride_bytes;
         he = hs + p.stride_bytes;
     } else {
@@ -188,8 +195,14 @@ __device__ __forceinline__ bool text_equals(const ScanParams &p, long long x, in
     const long long x0 = x & ~3LL;
     const int sh = (int)(x & 3) * 8;
     uint32_t w[6];
+    if (x0 + 24 <= p.total) {
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(p.hay + x0);
 #pragma unroll
-    for (int i = 0; i < 6; i++) w[i] = load_word(p.hay, x0 + 4 * i, p.total);
+        for (int i = 0; i < 6; i++) w[i] = __ldg(a + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; i++) w[i] = load_word(p.hay, x0 + 4 * i, p.total);
+    }
     uint32_t diff = 0;
 #pragma unroll
     for (int i = 0; i < 5; i++) {
@@ -215,12 +228,64 @@ __device__ __forceinline__ uint32_t lds_word(uint32_t saddr) {
     return v;
 }
 
+__device__ __forceinline__ void resolve(const ScanParams &p, const WarpStage &ws, uint2 c) {
+    const long long q = p.seg_begin + (long long)c.x;
+    const uint32_t tag = c.y;
+    const uint32_t amask = (1u << p.logA) - 1u;
+    uint32_t slot = tag >> (32 - p.logA);
+    long long h = -1, hs = 0, he = 0;
+    for (;;) {
+        const uint4 e0 = __ldg(p.anchors + 2 * (size_t)slot);             /* both halves of the 32-byte slot at once */
+        const uint4 e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
+        if (e0.x == 0u) break;                                 /* empty slot ends the probe sequence */
+        if (e0.x == tag) {
+            const uint32_t kw[5] = {e0.w, e1.x, e1.y, e1.z, e1.w};
+            const int j = (int)(e0.z & 0xffu), len = (int)((e0.z >> 8) & 0xffu);
+            const int32_t kid = (int32_t)e0.y;
+            if (h < 0) find_haystack(p, q, h, hs, he);
+            const long long start = q - j;
+            if (start >= hs) {
+                if (kid >= 0) {                                /* UNIQUE: the only key that can match at start */
+                    if (start + len <= he && text_equals(p, start, len, kw))
+                        emit(p, ws, (int32_t)h, (int32_t)(((start + len - hs) >> p.letter_shift) - 1), kid);
+                } else if (q + len <= he && text_equals(p, q, len, kw)) {   /* MULTI: exact gram, then the trie */
+                    walk_from(p, ws, start, h, hs, he);
+                }
+            }
+            if (e0.z & 0x10000u) break;                        /* no further entry carries this tag */
+        }
+        slot = (slot + 1) & amask;
+    }
+}
+
+/* per-warp state of the in-kernel stage 2/3 (all in shared memory except the ring positions) */
+struct WarpResolve {
+    uint2 *queue;      /* candidates {pos, tag} that passed both bitmaps, ring of kQueueCap */
+    WarpStage ws;
+};
+
+/* Resolve the warp's queued candidates (they passed both bitmaps) through the anchor table, 32 at a
+ * time.  Called between work units, never from the probe loop, so that none of the probe loop's
+ * registers are live across it.  While this warp waits on L2 the other warps keep filtering. */
+__device__ __noinline__ void drain_queue(const ScanParams &p, const WarpResolve &wr, int &qhead, int qtail,
+                                         bool final_flush, int lane) {
+    while (qtail - qhead >= 32 || (final_flush && qtail > qhead)) {
+        __syncwarp();
+        const int n = (qtail - qhead >= 32) ? 32 : (qtail - qhead);
+        if (lane < n) resolve(p, wr.ws, wr.queue[(qhead + lane) & (kQueueCap - 1)]);
+        qhead += n;
+        flush_stage(p, wr.ws, lane);
+    }
+}
+
 struct FilterCtx {
     const uint8_t *seg;        /* hay + seg_begin */
     uint32_t seg_len;          /* bytes of this segment: positions >= seg_len belong to the next launch */
     long long total_rel;       /* total - seg_begin: bytes that exist from seg onwards */
     uint32_t sbm;              /* shared-memory address of the bitmap */
-    uint32_t mul_word;         /* umulhi(h, mul_word) = bitmap word index */
+    uint32_t mul_word;         /* umulhi(h, mul_word) = stage-1 word index (7/8 of the words) */
+    uint32_t sbm2;             /* shared-memory address of the stage-2 bitmap (last 1/8) */
+    int sh_word2, sh_bit2;     /* tag >> sh_word2 = stage-2 word index, tag >> sh_bit2 = its bit index */
     uint32_t four;             /* == 4, opaque to the compiler so the address is one IMAD (FMA pipe) */
     int sh_bit;                /* h >> sh_bit: bit index (low 5 bits, wrap shift) */
     uint32_t lt_mask;
@@ -230,6 +295,20 @@ struct FilterCtx {
     unsigned long long cand_cap;
     unsigned long long *cand_count;
 };
+
+/* move queued candidates to the global list, 32 at a time (all of them when `all` is set) */
+__device__ __forceinline__ void spill_queue(const FilterCtx &c, int &qhead, int qtail, bool all) {
+    while (qtail - qhead >= 32 || (all && qtail > qhead)) {
+        __syncwarp();
+        const int n = (qtail - qhead >= 32) ? 32 : (qtail - qhead);
+        unsigned long long g = 0;
+        if (c.lane == 0) g = atomicAdd(c.cand_count, (unsigned long long)n);
+        g = __shfl_sync(kFull, g, 0);
+        if (c.lane < n && g + c.lane < c.cand_cap) c.cand[g + c.lane] = c.queue[(qhead + c.lane) & (kQueueCap - 1)];
+        qhead += n;
+        __syncwarp();
+    }
+}
 
 template <bool GUARD>
 __device__ __forceinline__ uint4 ld_chunk(const FilterCtx &c, uint32_t rel) {
@@ -250,6 +329,15 @@ __device__ __forceinline__ uint32_t ld_word(const FilterCtx &c, uint32_t rel) { 
 constexpr int kFChunk = 32;                       /* bytes per lane per iteration   */
 constexpr int kFWarpBytes = 32 * kFChunk;         /* 1 KiB per warp iteration       */
 constexpr int kFIters = kBlockBytes / kFWarpBytes;
+
+/* W[off + g] for g in 0..7 without dynamic register indexing: a 3-level select tree */
+template <int N>
+__device__ __forceinline__ uint32_t sel8(const uint32_t (&W)[N], int off, int g) {
+    const uint32_t a0 = (g & 1) ? W[off + 1] : W[off + 0], a1 = (g & 1) ? W[off + 3] : W[off + 2];
+    const uint32_t a2 = (g & 1) ? W[off + 5] : W[off + 4], a3 = (g & 1) ? W[off + 7] : W[off + 6];
+    const uint32_t b0 = (g & 2) ? a1 : a0, b1 = (g & 2) ? a3 : a2;
+    return (g & 4) ? b1 : b0;
+}
 
 template <int NW, int STRIDE, bool GUARD>
 __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (&mul)[NW], const uint32_t (&mul2)[NW],
@@ -306,23 +394,31 @@ __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (
         /* queue the survivors (ballot-ranked append into the warp's ring) with hash2 of their gram */
         unsigned any = __ballot_sync(kFull, hits != 0);
         while (any) {
+            bool keep = false;
+            uint2 cand = make_uint2(0, 0);
             if (hits) {
-                const uint32_t x = pos0 + (__ffs(hits) - 1) * STRIDE;
+                const int t = (__ffs(hits) - 1) * STRIDE;                          /* byte offset inside the lane's 32 */
+                const uint32_t x = pos0 + t;
                 hits &= hits - 1;
-                /* re-read the gram: an L1 hit, this warp loaded the line one iteration ago */
-                const uint32_t xa = x & ~3u;
-                const int sh = (int)(x & 3u) * 8;
-                uint32_t tag = 0, w0 = ld_word<GUARD>(c, xa);
+                /* hash2 of the gram, from the words still in registers (8-way select on t / 4) */
+                const int g = t >> 2, sh = (t & 3) * 8;
+                uint32_t tag = 0, w0 = sel8(W, 0, g);
 #pragma unroll
                 for (int k = 0; k < NW; k++) {
-                    const uint32_t w1 = ld_word<GUARD>(c, xa + 4 * (k + 1));
+                    const uint32_t w1 = sel8(W, k + 1, g);
                     tag += __funnelshift_r(w0, w1, sh) * mul2[k];
                     w0 = w1;
                 }
-                c.queue[(qtail + __popc(any & c.lt_mask)) & (kQueueCap - 1)] = make_uint2(x, tag | 1u);
+                tag |= 1u;
+                /* stage 2: second bitmap (hash2), also in shared memory; only its survivors are queued */
+                const uint32_t word2 = lds_word((tag >> c.sh_word2) * 4u + c.sbm2);
+                keep = (__funnelshift_r(word2, 0u, tag >> c.sh_bit2) & 1u) != 0;
+                cand = make_uint2(x, tag);
             }
-            qtail += __popc(any);
-            if (qtail - qhead >= 32) {                                             /* spill 32 candidates to global */
+            const unsigned km = __ballot_sync(kFull, keep);
+            if (keep) c.queue[(qtail + __popc(km & c.lt_mask)) & (kQueueCap - 1)] = cand;
+            qtail += __popc(km);
+            if (qtail - qhead > kQueueCap - 32) {                                  /* ring nearly full: spill 32 to the global list */
                 __syncwarp();
                 unsigned long long g = 0;
                 if (lane == 0) g = atomicAdd(c.cand_count, 32ULL);
@@ -339,26 +435,38 @@ __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (
 }
 
 template <int NW, int STRIDE>
-__global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int nwords = 1 << (p.log1 - 5);
     uint32_t *s_bm = smem;
     uint2 *s_queue = reinterpret_cast<uint2 *>(s_bm + nwords);           /* kWarps * kQueueCap */
+    acb_match *s_stage = reinterpret_cast<acb_match *>(s_queue + kWarps * kQueueCap);   /* kWarps * kStageCap */
+    int *s_cnt = reinterpret_cast<int *>(s_stage + kWarps * kStageCap);  /* kWarps */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {   /* stage-1 bitmap -> shared memory, 16 B per thread per step */
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.bm1);
+    {   /* both bitmaps -> shared memory (stage 1 in the first 7/8 of the words, stage 2 in the last 1/8) */
+        const int n1 = 7 * (nwords / 8);
+        const uint4 *src1 = reinterpret_cast<const uint4 *>(p.bm1), *src2 = reinterpret_cast<const uint4 *>(p.bm2);
         uint4 *dst = reinterpret_cast<uint4 *>(s_bm);
-        for (int i = tid; i < nwords / 4; i += kThreads) dst[i] = __ldg(src + i);
+        for (int i = tid; i < n1 / 4; i += kThreads) dst[i] = __ldg(src1 + i);
+        for (int i = tid; i < (nwords - n1) / 4; i += kThreads) dst[n1 / 4 + i] = __ldg(src2 + i);
+        if (tid < kWarps) s_cnt[tid] = 0;
     }
     __syncthreads();
+    WarpResolve wr;
+    wr.queue = s_queue + warp * kQueueCap;
+    wr.ws.buf = s_stage + warp * kStageCap;
+    wr.ws.cnt = s_cnt + warp;
 
     FilterCtx c;
     c.seg = p.hay + p.seg_begin;
     c.seg_len = (uint32_t)(p.seg_end - p.seg_begin);                     /* <= 2^31 */
     c.total_rel = p.total - p.seg_begin;
     c.sbm = (uint32_t)__cvta_generic_to_shared(s_bm);
-    c.mul_word = 1u << (p.log1 - 5);
+    c.mul_word = 7u << (p.log1 - 8);
+    c.sbm2 = c.sbm + 4u * (7u << (p.log1 - 8));
+    c.sh_word2 = 40 - p.log1;
+    c.sh_bit2 = 35 - p.log1;
     c.four = 4u + (uint32_t)(p.log1 >> 8);                               /* always 4 */
     c.sh_bit = 32 - p.log1;
     c.lt_mask = (1u << lane) - 1u;
@@ -384,17 +492,13 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const ScanParam
         const uint32_t rel0 = blk * (uint32_t)kBlockBytes;
         if ((long long)blk < n_interior) filter_unit<NW, STRIDE, false>(c, mul, mul2, rel0, qhead, qtail);
         else filter_unit<NW, STRIDE, true>(c, mul, mul2, rel0, qhead, qtail);
-    }
-    {   /* leftovers */
-        __syncwarp();
-        const int n = qtail - qhead;
-        if (n > 0) {
-            unsigned long long g = 0;
-            if (lane == 0) g = atomicAdd(p.cand_count, (unsigned long long)n);
-            g = __shfl_sync(kFull, g, 0);
-            if (lane < n && g + lane < p.cand_cap) p.cand[g + lane] = c.queue[(qhead + lane) & (kQueueCap - 1)];
+        if (qtail - qhead >= 32) {
+            if (p.inline_resolve) drain_queue(p, wr, qhead, qtail, false, lane);
+            else spill_queue(c, qhead, qtail, false);
         }
     }
+    if (p.inline_resolve) drain_queue(p, wr, qhead, qtail, true, lane);  /* leftovers */
+    else spill_queue(c, qhead, qtail, true);
     /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
     __syncthreads();
     if (tid == 0) {
@@ -409,82 +513,28 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const ScanParam
 }
 
 /* ------------------------------------------------------- the verify kernel */
-/* Stage 2/3.  Warps stream the candidate list.  A candidate's tag (hash2 of its gram) is first
- * tested against the stage-2 bitmap; the few that pass are compacted into a per-warp list and
- * resolved 32 at a time through the anchor table (open addressing, 32-byte slots):
+/* Overflow path of stage 3: resolves the candidates that warps had to spill to the global list
+ * (normally none).  Each candidate is resolved through the anchor table (open addressing, 32-byte slots):
  * UNIQUE anchor -> the single key that can match is compared with the text;
  * MULTI anchor  -> exact gram compare, then a trie walk from the root. */
 
-__device__ __forceinline__ void resolve(const ScanParams &p, const WarpStage &ws, uint2 c) {
-    const long long q = p.seg_begin + (long long)c.x;
-    const uint32_t tag = c.y;
-    const uint32_t amask = (1u << p.logA) - 1u;
-    uint32_t slot = tag >> (32 - p.logA);
-    long long h = -1, hs = 0, he = 0;
-    for (;;) {
-        const uint4 e0 = __ldg(p.anchors + 2 * (size_t)slot);
-        if (e0.x == 0u) break;                                 /* empty slot ends the probe sequence */
-        if (e0.x == tag) {
-            const uint4 e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
-            const uint32_t kw[5] = {e0.w, e1.x, e1.y, e1.z, e1.w};
-            const int j = (int)(e0.z & 0xffu), len = (int)((e0.z >> 8) & 0xffu);
-            const int32_t kid = (int32_t)e0.y;
-            if (h < 0) find_haystack(p, q, h, hs, he);
-            const long long start = q - j;
-            if (start >= hs) {
-                if (kid >= 0) {                                /* UNIQUE: the only key that can match at start */
-                    if (start + len <= he && text_equals(p, start, len, kw))
-                        emit(p, ws, (int32_t)h, (int32_t)((start + len - hs) / p.L - 1), kid);
-                } else if (q + len <= he && text_equals(p, q, len, kw)) {   /* MULTI: exact gram, then the trie */
-                    walk_from(p, ws, start, h, hs, he);
-                }
-            }
-        }
-        slot = (slot + 1) & amask;
-    }
-}
-
-__global__ void __launch_bounds__(kVerThreads) acb_verify_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kVerThreads) acb_verify_kernel(const __grid_constant__ ScanParams p) {
     __shared__ acb_match s_stage[kVerWarps * kStageCap];
     __shared__ int s_cnt[kVerWarps];
-    __shared__ uint2 s_list[kVerWarps * 64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < kVerWarps) s_cnt[tid] = 0;
     __syncthreads();
     WarpStage ws;
     ws.buf = s_stage + warp * kStageCap;
     ws.cnt = s_cnt + warp;
-    uint2 *list = s_list + warp * 64;
-    int lhead = 0, ltail = 0;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const int sh2 = 32 - p.log2;
-
     const unsigned long long found = *p.cand_count;
     const unsigned long long n = found < p.cand_cap ? found : p.cand_cap;
     const unsigned long long gwarp = (unsigned long long)blockIdx.x * kVerWarps + warp;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * kVerWarps;
     for (unsigned long long w0 = gwarp * 32; w0 < n; w0 += nwarps * 32) {
-        const unsigned long long i = w0 + lane;
-        uint2 c = make_uint2(0, 0);
-        bool pass = false;
-        if (i < n) {
-            c = p.cand[i];
-            const uint32_t idx = c.y >> sh2;
-            pass = (__ldg(p.bm2 + (idx >> 5)) >> (idx & 31)) & 1u;
-        }
-        const unsigned m = __ballot_sync(kFull, pass);
-        if (pass) list[(ltail + __popc(m & lt_mask)) & 63] = c;
-        ltail += __popc(m);
-        if (ltail - lhead >= 32) {
-            __syncwarp();
-            resolve(p, ws, list[(lhead + lane) & 63]);
-            lhead += 32;
-            flush_stage(p, ws, lane);
-        }
+        if (w0 + lane < n) resolve(p, ws, p.cand[w0 + lane]);
+        flush_stage(p, ws, lane);
     }
-    __syncwarp();
-    if (lane < ltail - lhead) resolve(p, ws, list[(lhead + lane) & 63]);
-    flush_stage(p, ws, lane);
     /* last CTA out: re-arm the candidate counter; flag an overflowed candidate list in *count */
     __syncthreads();
     if (tid == 0) {
@@ -645,8 +695,8 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if ((rc = upload(&tb->d_outptr, f.out_ptr, (size_t)f.n_states + 1, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_outidx, f.out_idx, (size_t)f.out_ptr[f.n_states], tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_keylen, f.key_len, (size_t)f.n_keys, tb->dev_bytes))) break;
-        if ((rc = upload(&tb->d_bm1, f.bitmap1, (size_t)1 << (f.log2_bits1 - 5), tb->dev_bytes))) break;
-        if ((rc = upload(&tb->d_bm2, f.bitmap2, (size_t)1 << (f.log2_bits2 - 5), tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_bm1, f.bitmap1, (size_t)7 << (f.log2_bits1 - 8), tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_bm2, f.bitmap2, (size_t)1 << (f.log2_bits1 - 8), tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_anchors, f.anchors, (size_t)8 << f.log2_anchor_slots, tb->dev_bytes))) break;
         unsigned int zero[4] = {0, 0, 0, 0};   /* work counters, re-armed by the kernels themselves */
         if ((rc = upload(&tb->d_work, zero, 4, tb->dev_bytes))) break;
@@ -671,7 +721,8 @@ extern "C" float acb_last_kernel_ms(void) { return g_last_ms; }
 /* ------------------------------------------------------------- launching */
 
 static size_t filter_smem_bytes(int log1) {
-    return ((size_t)1 << (log1 - 3)) + (size_t)kWarps * kQueueCap * sizeof(uint2);
+    return ((size_t)1 << (log1 - 3)) + (size_t)kWarps * kQueueCap * sizeof(uint2) +
+           (size_t)kWarps * kStageCap * sizeof(acb_match) + (size_t)kWarps * sizeof(int);
 }
 
 template <int NW, int STRIDE>
@@ -751,6 +802,14 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     memcpy(p.mul2, tb->mul2, sizeof(p.mul2));
     p.out = d_out; p.cap = cap; p.count = reinterpret_cast<unsigned long long *>(d_count);
     p.work_ctr = tb->d_work;
+    p.stride_shift = -1;
+    if (!d_offsets) for (int b = 0; b < 62; b++) if ((1LL << b) == stride_bytes) p.stride_shift = b;
+    p.letter_shift = tb->L == 4 ? 2 : (tb->L == 2 ? 1 : 0);
+    {
+        static int inl = -1;
+        if (inl < 0) { const char *e = getenv("ACB_INLINE_RESOLVE"); inl = e ? atoi(e) : 1; }
+        p.inline_resolve = inl;
+    }
 
     if (algo == ACB_ALGO_AUTO) algo = ACB_ALGO_FILTER;
     if (tb->n_keys == 0) return ACB_OK;                     /* empty key set: nothing can match */
@@ -770,7 +829,7 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
             int grid = (int)std::min<long long>(tb->sm_count, p.n_blocks);
             rc = launch_filter(p, tb->stride, grid, s);
             if (rc != ACB_OK) return rc;
-            acb_verify_kernel<<<tb->sm_count * 4, kVerThreads, 0, s>>>(p);
+            acb_verify_kernel<<<p.inline_resolve ? tb->sm_count : tb->sm_count * 6, kVerThreads, 0, s>>>(p);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) { acb_set_error("verify kernel launch failed: %s", cudaGetErrorString(e)); return ACB_ECUDA; }
             g_launches.fetch_add(1);

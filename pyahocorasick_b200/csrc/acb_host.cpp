@@ -315,7 +315,8 @@ static int32_t unique_key_below(const acb_trie *t, int32_t v, std::vector<uint8_
  *     carrying the key itself: the device compares the text at q-j with the key directly;
  *   - otherwise the whole (gram, j) group collapses to one MULTI entry carrying the gram: the
  *     device walks the trie from the root at q-j.
- * Entry = 8 x uint32: tag (hash2|1, 0 = empty), key_id (-1 = MULTI), j | len<<8, 20 key/gram bytes. */
+ * Entry = 8 x uint32: tag (hash2|1, 0 = empty), key_id (-1 = MULTI), j | len<<8 | last<<16 (last = no
+ * further entry with this tag in the probe sequence), 20 key/gram bytes. */
 static void build_filter(acb_trie *t, Flat &f) {
     const int L = t->letter_bytes;
     const int m = f.min_key_bytes;
@@ -365,7 +366,7 @@ static void build_filter(acb_trie *t, Flat &f) {
             if (forced_l1) log1 = forced_l1;
             double space = std::pow(Kb, (double)g);
             double p_true = std::min(1.0, E / space);
-            double fill1 = std::min(1.0, E / std::pow(2.0, log1));
+            double fill1 = std::min(1.0, E / (0.875 * std::pow(2.0, log1)));
             int nw = (g + 3) / 4;
             double pass1 = p_true + (1 - p_true) * fill1;
             /* per byte: probe instructions + anchor lookups for stage-1 survivors + key compares */
@@ -380,11 +381,22 @@ static void build_filter(acb_trie *t, Flat &f) {
     f.gram = g;
     f.stride = s;
     f.log1 = best.log1;
-    f.bm1.assign((size_t)1 << (best.log1 - 5), 0);
+    /* The 2^log1 bits of shared memory are split 7/8 : 1/8 between the stage-1 bitmap (probed at
+     * every position, indexed by hash1) and the stage-2 bitmap (probed only by stage-1 survivors,
+     * indexed by hash2):  word1 = umulhi(hash1, 7 << (log1-8)), bit1 = (hash1 >> (32-log1)) & 31;
+     *                     word2 = hash2 >> (40-log1),           bit2 = (hash2 >> (35-log1)) & 31. */
+    const uint32_t mulw1 = 7u << (best.log1 - 8);
+    f.bm1.assign((size_t)7 << (best.log1 - 8), 0);
+    f.bm2.assign((size_t)1 << (best.log1 - 8), 0);
+    f.log2 = best.log1 - 3;
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     acb_hash_multipliers(g, 1, mul1);
     acb_hash_multipliers(g, 2, mul2);
-    for (const auto &gr : best_grams) set_bit(f.bm1, acb_hash_bytes(gr.data(), g, mul1) >> (32 - best.log1));
+    for (const auto &gr : best_grams) {
+        uint32_t h1 = acb_hash_bytes(gr.data(), g, mul1), h2 = acb_hash_bytes(gr.data(), g, mul2) | 1u;
+        f.bm1[(size_t)(((uint64_t)h1 * mulw1) >> 32)] |= 1u << ((h1 >> (32 - best.log1)) & 31);
+        f.bm2[h2 >> (40 - best.log1)] |= 1u << ((h2 >> (35 - best.log1)) & 31);
+    }
 
     /* ---- anchor table ---- */
     struct Cand { std::vector<uint8_t> gram; int j; int32_t node; };
@@ -439,19 +451,18 @@ static void build_filter(acb_trie *t, Flat &f) {
         }
         a = b;
     }
-    /* stage-2 bitmap over the tags (bit index = high bits of hash2): rejects almost every stage-1
-     * false positive with one load, so that only real anchors reach the table below */
-    int log2 = std::min(30, std::max(15, ceil_log2_u64((uint64_t)entries.size() * 128 + 1)));
-    f.log2 = log2;
-    f.bm2.assign((size_t)1 << (log2 - 5), 0);
-    for (const Entry &e : entries) set_bit(f.bm2, e.w[0] >> (32 - log2));
     int logA = std::max(10, ceil_log2_u64((uint64_t)entries.size() * 4 + 1));     /* load factor <= 1/4 */
     if (logA > 28) logA = 28;
     while (((size_t)1 << logA) < entries.size() + entries.size() / 4 + 1) logA++;
     f.logA = logA;
     const size_t slots = (size_t)1 << logA, mask = slots - 1;
     f.anchors.assign(slots * 8, 0);
-    for (const Entry &e : entries) {
+    /* insert tag by tag; within one tag the chain order is the insertion order, and the last entry of
+     * the tag gets bit 16 of word 2 set so that a lookup can stop there */
+    std::stable_sort(entries.begin(), entries.end(), [](const Entry &a, const Entry &b) { return a.w[0] < b.w[0]; });
+    for (size_t a = 0; a < entries.size(); a++) {
+        Entry e = entries[a];
+        if (a + 1 == entries.size() || entries[a + 1].w[0] != e.w[0]) e.w[2] |= 1u << 16;
         size_t i = e.w[0] >> (32 - logA);                   /* slot from the high bits of hash2 */
         while (f.anchors[i * 8] != 0) i = (i + 1) & mask;
         memcpy(&f.anchors[i * 8], e.w, sizeof(e.w));
@@ -562,9 +573,9 @@ extern "C" int acb_trie_make_automaton(acb_trie *t, int32_t *built) {
 
         if (f.n_keys > 0) build_filter(t, f);
         else {                                               /* nothing can ever match */
-            f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.log2 = 15; f.logA = 10;
-            f.bm1.assign((size_t)1 << (13 - 5), 0);
-            f.bm2.assign((size_t)1 << (15 - 5), 0);
+            f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.log2 = 10; f.logA = 10;
+            f.bm1.assign((size_t)7 << (13 - 8), 0);
+            f.bm2.assign((size_t)1 << (13 - 8), 0);
             f.anchors.assign(((size_t)1 << 10) * 8, 0);
         }
         f.valid = true;

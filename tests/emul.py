@@ -97,12 +97,13 @@ def emul_filter(f, buf, offsets=None, stride_bytes=0):
     if f["n_keys"] == 0:
         return recs
     for q in range(0, total, s):
-        if not _bit(f["bitmap1"], hash_bytes(buf, q, g, mul1) >> (32 - l1)):
+        h1 = hash_bytes(buf, q, g, mul1)
+        if not (int(f["bitmap1"][(h1 * (7 << (l1 - 8))) >> 32]) >> ((h1 >> (32 - l1)) & 31)) & 1:
             continue
         if q + g > total:
             continue
         tag = hash_bytes(buf, q, g, mul2) | 1
-        if not _bit(f["bitmap2"], tag >> (32 - f["log2_bits2"])):
+        if not (int(f["bitmap2"][tag >> (40 - l1)]) >> ((tag >> (35 - l1)) & 31)) & 1:
             continue
         slot = tag >> (32 - lA)
         bounds = None
@@ -123,6 +124,8 @@ def emul_filter(f, buf, offsets=None, stride_bytes=0):
                             recs.append((h, (start + ln - hs) // L - 1, kid))
                     elif raw[q:q + ln] == _entry_bytes(e, ln):
                         _walk(f, buf, start, h, hs, he, recs)
+                if (int(e[2]) >> 16) & 1:
+                    break                      # last entry carrying this tag
             slot = (slot + 1) & amask
     return _sorted(recs, f["key_len"])
 

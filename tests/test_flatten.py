@@ -105,7 +105,8 @@ def test_filter_choice_for_baseline_configs():
     f = synth.build_automaton(w.keys).flat()
     assert (f["gram_bytes"], f["stride"], f["log2_bits1"]) == (4, 1, 20)
     fill = np.unpackbits(f["bitmap1"].view(np.uint8)).mean()
-    assert 0.005 < fill < 0.012
+    assert 0.005 < fill < 0.014
+    assert 0.02 < np.unpackbits(f["bitmap2"].view(np.uint8)).mean() < 0.09
     a = f["anchors"]
     used = a[a[:, 0] != 0]
     assert 9000 < len(used) <= 10000 and len(used) * 4 <= len(a)         # one anchor per distinct 4-byte prefix
