@@ -175,6 +175,12 @@ int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_bytes,
                   const int64_t *offsets, int64_t n_hay, int64_t stride_bytes,
                   acb_match *out, int64_t cap, int64_t *n_found, int algo, int sort);
 
+/* Sort n device-resident records into the reference's order (hay_id, end_index ascending, longest
+ * key first) with a 64-bit radix sort, asynchronously on `stream`.  max_hay_letters bounds end_index.
+ * ACB_ERANGE when hay_id/end_index/length do not fit one 64-bit key (sort on the host then). */
+int acb_sort_matches_device(acb_table *tb, acb_match *d_records, int64_t n, int64_t n_hay,
+                            int64_t max_hay_letters, void *stream);
+
 /* number of kernel launches issued by this library so far (bench.py's gpu_launches) */
 int64_t acb_launch_count(void);
 

@@ -30,6 +30,7 @@
 #include "acb_hash.h"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <atomic>
@@ -622,6 +623,7 @@ struct acb_table {
     unsigned long long *w_count = nullptr;
     unsigned long long *h_count = nullptr;   /* pinned */
     acb_match *h_out = nullptr; size_t h_out_cap = 0;   /* pinned staging for the records */
+    void *d_sort = nullptr; size_t sort_cap = 0;         /* radix-sort scratch */
 };
 
 extern "C" int acb_device_count(int32_t *n) {
@@ -648,7 +650,7 @@ extern "C" void acb_table_free(acb_table *tb) {
     cudaSetDevice(tb->device);
     cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
     cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_bm2); cudaFree(tb->d_anchors);
-    cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->d_cand_count); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
+    cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->d_cand_count); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
     if (tb->h_count) cudaFreeHost(tb->h_count);
     if (tb->h_out) cudaFreeHost(tb->h_out);
     if (tb->ev0) cudaEventDestroy(tb->ev0);
@@ -856,6 +858,55 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     return ACB_OK;
 }
 
+/* ------------------------------------------------------------ record sort */
+/* Reference order: haystack, then end_index ascending, then longest key first.  One
+ * 64-bit radix key per record: hay_id | end_index | (max_len - len), packed into the fewest bits. */
+namespace {
+__global__ void acb_sortkey_kernel(const acb_match *rec, long long n, const int32_t *key_len, int be, int bl,
+                                   int max_len, unsigned long long *keys) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const acb_match m = rec[i];
+    const unsigned long long inv = (unsigned long long)(max_len - __ldg(key_len + m.key_id));
+    keys[i] = ((unsigned long long)(uint32_t)m.hay_id << (be + bl)) | ((unsigned long long)(uint32_t)m.end_index << bl) | inv;
+}
+int bits_for(unsigned long long v) { int b = 1; while (b < 64 && (v >> b)) b++; return b; }
+} // namespace
+
+extern "C" int acb_sort_matches_device(acb_table *tb, acb_match *d_records, int64_t n, int64_t n_hay,
+                                       int64_t max_hay_letters, void *stream) {
+    if (!tb || n < 0 || (n && !d_records)) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    if (n <= 1) return ACB_OK;
+    CUDA_TRY(cudaSetDevice(tb->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int max_len = tb->max_key_bytes / tb->L;
+    const int bh = bits_for((unsigned long long)std::max<int64_t>(n_hay - 1, 1));
+    const int be = bits_for((unsigned long long)std::max<int64_t>(max_hay_letters, 1));
+    const int bl = bits_for((unsigned long long)max_len);
+    if (bh + be + bl > 64) { acb_set_error("sort key does not fit 64 bits (%d+%d+%d)", bh, be, bl); return ACB_ERANGE; }
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const acb_match *)nullptr, (acb_match *)nullptr, (int)n, 0, bh + be + bl, s);
+    const size_t need = (size_t)n * (2 * sizeof(unsigned long long) + sizeof(acb_match)) + temp + 1024;
+    if (tb->sort_cap < need) {
+        if (tb->d_sort) { cudaFree(tb->d_sort); tb->d_sort = nullptr; tb->sort_cap = 0; }
+        CUDA_TRY(cudaMalloc(&tb->d_sort, need + need / 4));
+        tb->sort_cap = need + need / 4;
+    }
+    if (n > 0x7fffffffLL) { acb_set_error("too many records to sort on the device"); return ACB_ERANGE; }
+    char *base = reinterpret_cast<char *>(tb->d_sort);
+    unsigned long long *k0 = reinterpret_cast<unsigned long long *>(base);
+    unsigned long long *k1 = k0 + n;
+    acb_match *r1 = reinterpret_cast<acb_match *>(k1 + n);
+    void *tmp = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(r1 + n) + 255) & ~(uintptr_t)255);
+    acb_sortkey_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_records, n, tb->d_keylen, be, bl, max_len, k0);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, temp, k0, k1, d_records, r1, (int)n, 0, bh + be + bl, s));
+    CUDA_TRY(cudaMemcpyAsync(d_records, r1, (size_t)n * sizeof(acb_match), cudaMemcpyDeviceToDevice, s));
+    return ACB_OK;
+}
+
 /* ------------------------------------------------------- host-buffer scan */
 
 template <typename T>
@@ -909,9 +960,14 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
             CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&tb->h_out), want * sizeof(acb_match)));
             tb->h_out_cap = want;
         }
+        bool host_sort = sort != 0;
+        if (sort) {                                            /* radix sort on the device when the key fits 64 bits */
+            const int64_t max_letters = (offsets ? total_bytes : stride_bytes) / tb->L;
+            if (acb_sort_matches_device(tb, tb->w_out, (int64_t)n, n_hay, max_letters, s) == ACB_OK) host_sort = false;
+        }
         CUDA_TRY(cudaMemcpyAsync(tb->h_out, tb->w_out, (size_t)n * sizeof(acb_match), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
-        if (sort) {
+        if (host_sort) {
             const int32_t *kl = tb->key_len.data();
             std::sort(tb->h_out, tb->h_out + n, [kl](const acb_match &a, const acb_match &b) {
                 if (a.hay_id != b.hay_id) return a.hay_id < b.hay_id;
