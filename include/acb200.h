@@ -170,10 +170,15 @@ int acb_table_reserve_candidates(acb_table *tb, int worst_case);
  * the count and the records, all inside the call (this is what `e2e` times).
  * Returns ACB_EOVERFLOW (and the needed size in *n_found) when cap is too small.
  * If sort != 0 the records come back in the reference's order:
- * hay_id, then end_index ascending, then longest key first. */
+ * hay_id, then end_index ascending, then longest key first.
+ * `out` may be NULL (then `cap` only bounds the device buffer): the records stay in the
+ * table's pinned staging area and acb_copy_records() copies them out once the count is known. */
 int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_bytes,
                   const int64_t *offsets, int64_t n_hay, int64_t stride_bytes,
                   acb_match *out, int64_t cap, int64_t *n_found, int algo, int sort);
+
+/* copy the first n records of the last acb_scan_host(out = NULL) call into `out` */
+int acb_copy_records(acb_table *tb, acb_match *out, int64_t n);
 
 /* Sort n device-resident records into the reference's order (hay_id, end_index ascending, longest
  * key first) with a 64-bit radix sort, asynchronously on `stream`.  max_hay_letters bounds end_index.

@@ -73,6 +73,7 @@ def lib() -> ctypes.CDLL:
         "acb_table_reserve_candidates": (ctypes.c_int, [vp, ctypes.c_int]),
         "acb_scan_device": (ctypes.c_int, [vp, vp, i64, vp, i64, i64, vp, i64, vp, vp, ctypes.c_int]),
         "acb_scan_host": (ctypes.c_int, [vp, vp, i64, vp, i64, i64, vp, i64, pi64, ctypes.c_int, ctypes.c_int]),
+        "acb_copy_records": (ctypes.c_int, [vp, vp, i64]),
         "acb_sort_matches_device": (ctypes.c_int, [vp, vp, i64, i64, i64, vp]),
         "acb_launch_count": (i64, []),
         "acb_set_kernel_timing": (ctypes.c_int, [ctypes.c_int]),
@@ -93,7 +94,7 @@ EXPORTED_SYMBOLS = [
     "acb_trie_find", "acb_trie_longest_prefix", "acb_trie_make_automaton", "acb_trie_kind",
     "acb_trie_count", "acb_trie_longest_word", "acb_trie_nodes", "acb_trie_links", "acb_trie_flat_view",
     "acb_device_count", "acb_table_upload", "acb_table_free", "acb_table_device_bytes", "acb_table_reserve_candidates",
-    "acb_scan_device", "acb_scan_host", "acb_sort_matches_device", "acb_launch_count", "acb_set_kernel_timing",
+    "acb_scan_device", "acb_scan_host", "acb_copy_records", "acb_sort_matches_device", "acb_launch_count", "acb_set_kernel_timing",
     "acb_last_kernel_ms", "acb_last_error", "acb_abi_version",
 ]
 

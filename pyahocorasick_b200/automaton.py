@@ -123,7 +123,7 @@ class Automaton:
         self._version = 0
         self._table = None                # acb_table* (device), created lazily
         self._table_device = None
-        self._out_buf = None
+        self._match_cap = 0
 
     @staticmethod
     def _check_store(store):
@@ -440,20 +440,21 @@ class Automaton:
         """flat uint8 buffer (+ int64 byte offsets or a fixed stride) -> sorted match records."""
         tb = self._ensure_table(device)
         total = int(flat.size)
-        cap = max(1 << 12, 2 * n_hay)
+        cap = max(self._match_cap, 1 << 12, 2 * n_hay)        # device-side capacity; grown on overflow
         found = ctypes.c_int64(0)
         while True:
-            if self._out_buf is None or len(self._out_buf) < cap:
-                self._out_buf = np.empty(cap, dtype=N.MATCH_DTYPE)
-            out = self._out_buf
             rc = self._lib.acb_scan_host(tb, N.ptr(flat) if total else None, total,
                                          N.ptr(offsets) if offsets is not None else None, n_hay, stride_bytes,
-                                         N.ptr(out), len(out), ctypes.byref(found), N.ALGOS[algo], 1 if sort else 0)
+                                         None, cap, ctypes.byref(found), N.ALGOS[algo], 1 if sort else 0)
             if rc == N.ACB_EOVERFLOW:
                 cap = int(found.value) + 1024
+                self._match_cap = cap
                 continue
             N.check(rc)
-            return out[:found.value].copy()
+            out = np.empty(found.value, dtype=N.MATCH_DTYPE)   # exact size, one copy out of the pinned staging
+            if found.value:
+                N.check(self._lib.acb_copy_records(tb, N.ptr(out), found.value))
+            return out
 
     def _scan_one(self, letters: np.ndarray, algo: str = "auto") -> np.ndarray:
         flat = np.ascontiguousarray(letters).view(np.uint8)

@@ -34,6 +34,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -623,6 +624,7 @@ struct acb_table {
     unsigned long long *w_count = nullptr;
     unsigned long long *h_count = nullptr;   /* pinned */
     acb_match *h_out = nullptr; size_t h_out_cap = 0;   /* pinned staging for the records */
+    unsigned long long h_out_n = 0;                      /* records of the last scan held in h_out */
     void *d_sort = nullptr; size_t sort_cap = 0;         /* radix-sort scratch */
 };
 
@@ -858,6 +860,12 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     return ACB_OK;
 }
 
+extern "C" int acb_copy_records(acb_table *tb, acb_match *out, int64_t n) {
+    if (!tb || n < 0 || (n && !out) || (unsigned long long)n > tb->h_out_n) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    if (n) memcpy(out, tb->h_out, (size_t)n * sizeof(acb_match));
+    return ACB_OK;
+}
+
 /* ------------------------------------------------------------ record sort */
 /* Reference order: haystack, then end_index ascending, then longest key first.  One
  * 64-bit radix key per record: hay_id | end_index | (max_len - len), packed into the fewest bits. */
@@ -924,6 +932,7 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
                              acb_match *out, int64_t cap, int64_t *n_found, int algo, int sort) {
     if (!tb || !n_found || total_bytes < 0 || n_hay < 0 || cap < 0) { acb_set_error("bad argument"); return ACB_EINVAL; }
     *n_found = 0;
+    tb->h_out_n = 0;
     if (total_bytes == 0 || n_hay == 0) return ACB_OK;
     CUDA_TRY(cudaSetDevice(tb->device));
     if (!tb->stream) CUDA_TRY(cudaStreamCreateWithFlags(&tb->stream, cudaStreamNonBlocking));
@@ -934,14 +943,19 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
     if (offsets && (rc = ensure(&tb->w_off, &tb->w_off_cap, (size_t)n_hay + 1))) return rc;
     if ((rc = ensure(&tb->w_out, &tb->w_out_cap, (size_t)std::max<int64_t>(cap, 1)))) return rc;
     cudaStream_t s = tb->stream;
+    static const bool trace = getenv("ACB_TRACE") != nullptr;          /* phase timing to stderr (adds syncs) */
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = trace ? now() : 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
     CUDA_TRY(cudaMemcpyAsync(tb->w_hay, hay, (size_t)total_bytes, cudaMemcpyHostToDevice, s));
     if (offsets) CUDA_TRY(cudaMemcpyAsync(tb->w_off, offsets, (size_t)(n_hay + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(tb->w_count, 0, sizeof(unsigned long long), s));
+    if (trace) { cudaStreamSynchronize(s); t1 = now(); }
     rc = acb_scan_device(tb, tb->w_hay, total_bytes, offsets ? reinterpret_cast<const int64_t *>(tb->w_off) : nullptr,
                          n_hay, stride_bytes, tb->w_out, cap, reinterpret_cast<int64_t *>(tb->w_count), s, algo);
     if (rc != ACB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(tb->h_count, tb->w_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    if (trace) t2 = now();
     unsigned long long n = *tb->h_count;
     if (n == ~0ULL) {                                           /* candidate list overflowed: redo with room for every probe */
         if (tb->cand_worst_case) { acb_set_error("candidate list overflow even at worst-case capacity"); return ACB_ECUDA; }
@@ -965,6 +979,7 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
             const int64_t max_letters = (offsets ? total_bytes : stride_bytes) / tb->L;
             if (acb_sort_matches_device(tb, tb->w_out, (int64_t)n, n_hay, max_letters, s) == ACB_OK) host_sort = false;
         }
+        if (trace) { cudaStreamSynchronize(s); t3 = now(); }
         CUDA_TRY(cudaMemcpyAsync(tb->h_out, tb->w_out, (size_t)n * sizeof(acb_match), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (host_sort) {
@@ -975,7 +990,13 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
                 return kl[a.key_id] > kl[b.key_id];            /* longest first: fail-chain order */
             });
         }
-        memcpy(out, tb->h_out, (size_t)n * sizeof(acb_match));
+        if (out) memcpy(out, tb->h_out, (size_t)n * sizeof(acb_match));   /* out == NULL: fetch with acb_copy_records */
+    }
+    tb->h_out_n = n;
+    if (trace) {
+        t4 = now();
+        fprintf(stderr, "[acb_scan_host] %lld B: h2d %.3f ms, scan %.3f ms, sort %.3f ms, d2h+copy %.3f ms (%llu records)\n",
+                (long long)total_bytes, t1 - t0, t2 - t1, t3 ? t3 - t2 : 0.0, t3 ? t4 - t3 : t4 - t2, n);
     }
     return ACB_OK;
 }
