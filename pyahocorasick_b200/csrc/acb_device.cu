@@ -55,7 +55,10 @@ namespace {
 
 constexpr int kThreads      = 1024;               /* filter kernel: one CTA per SM                 */
 constexpr int kWarps        = kThreads / 32;
-constexpr int kBlockBytes   = 4096;               /* work unit per warp grab (filter kernel)       */
+#ifndef ACB_BLOCK_BYTES
+#define ACB_BLOCK_BYTES 4096
+#endif
+constexpr int kBlockBytes   = ACB_BLOCK_BYTES;    /* work unit per warp grab (filter kernel)       */
 constexpr int kQueueCap     = 128;                /* stage-1 survivors queued per warp (smem)      */
 constexpr int kStageCap     = 32;                 /* match records staged per warp (smem)          */
 constexpr uint32_t kFull    = 0xffffffffu;
