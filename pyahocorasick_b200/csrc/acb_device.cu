@@ -95,8 +95,9 @@ struct ScanParams {
     int32_t max_key_bytes;
     const uint32_t *bm1;
     const uint32_t *bm2;
+    const uint32_t *bm3;           /* stage 3, global memory; log3 == 0: unused */
     const uint4 *anchors;          /* 2 x uint4 per slot */
-    int32_t log1, log2, logA;
+    int32_t log1, log2, log3, logA;
     uint32_t mul1[ACB_MAX_WINDOWS];
     uint32_t mul2[ACB_MAX_WINDOWS];
     acb_match *out;
@@ -289,6 +290,8 @@ struct FilterCtx {
     long long total_rel;       /* total - seg_begin: bytes that exist from seg onwards */
     uint32_t sbm;              /* shared-memory address of the bitmap */
     uint32_t mul_word;         /* umulhi(h, mul_word) = stage-1 word index (7/8 of the words) */
+    const uint32_t *bm3;       /* stage-3 bitmap in global memory (large key sets), log3 == 0: unused */
+    int log3;
     uint32_t sbm2;             /* shared-memory address of the stage-2 bitmap (last 1/8) */
     int sh_word2, sh_bit2;     /* tag >> sh_word2 = stage-2 word index, tag >> sh_bit2 = its bit index */
     uint32_t four;             /* == 4, opaque to the compiler so the address is one IMAD (FMA pipe) */
@@ -418,6 +421,10 @@ __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (
                 /* stage 2: second bitmap (hash2), also in shared memory; only its survivors are queued */
                 const uint32_t word2 = lds_word((tag >> c.sh_word2) * 4u + c.sbm2);
                 keep = (__funnelshift_r(word2, 0u, tag >> c.sh_bit2) & 1u) != 0;
+                if (keep && c.log3) {                                              /* stage 3 (large key sets only): bitmap in L2 */
+                    const uint32_t i3 = (tag * ACB_S3_MIX) >> (32 - c.log3);
+                    keep = ((__ldg(c.bm3 + (i3 >> 5)) >> (i3 & 31)) & 1u) != 0;
+                }
                 cand = make_uint2(x, tag);
             }
             const unsigned km = __ballot_sync(kFull, keep);
@@ -469,6 +476,8 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
     c.total_rel = p.total - p.seg_begin;
     c.sbm = (uint32_t)__cvta_generic_to_shared(s_bm);
     c.mul_word = 7u << (p.log1 - 8);
+    c.bm3 = p.bm3;
+    c.log3 = p.log3;
     c.sbm2 = c.sbm + 4u * (7u << (p.log1 - 8));
     c.sh_word2 = 40 - p.log1;
     c.sh_bit2 = 35 - p.log1;
@@ -605,12 +614,12 @@ __global__ void __launch_bounds__(kDfaThreads) acb_dfa_kernel(const ScanParams p
 struct acb_table {
     int device = 0;
     int sm_count = 0;
-    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log2 = 15, logA = 10;
+    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log2 = 15, log3 = 0, logA = 10;
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     uint8_t *d_cls = nullptr;
     int32_t *d_goto = nullptr, *d_fail = nullptr, *d_keyof = nullptr, *d_outptr = nullptr, *d_outidx = nullptr, *d_keylen = nullptr;
-    uint32_t *d_bm1 = nullptr, *d_bm2 = nullptr, *d_anchors = nullptr;
+    uint32_t *d_bm1 = nullptr, *d_bm2 = nullptr, *d_bm3 = nullptr, *d_anchors = nullptr;
     unsigned int *d_work = nullptr;
     uint2 *d_cand = nullptr;                 /* candidate list (filter -> verify) */
     unsigned long long cand_cap = 0;
@@ -654,7 +663,7 @@ extern "C" void acb_table_free(acb_table *tb) {
     if (!tb) return;
     cudaSetDevice(tb->device);
     cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
-    cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_bm2); cudaFree(tb->d_anchors);
+    cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_bm2); cudaFree(tb->d_bm3); cudaFree(tb->d_anchors);
     cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->d_cand_count); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
     if (tb->h_count) cudaFreeHost(tb->h_count);
     if (tb->h_out) cudaFreeHost(tb->h_out);
@@ -684,7 +693,7 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { acb_set_error("cudaGetDeviceProperties failed"); rc = ACB_ECUDA; break; }
         tb->sm_count = prop.multiProcessorCount;
         tb->S = f.n_states; tb->K = f.n_classes; tb->L = f.letter_bytes; tb->n_keys = f.n_keys;
-        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log2 = f.log2_bits2; tb->logA = f.log2_anchor_slots;
+        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log2 = f.log2_bits2; tb->log3 = f.log2_bits3; tb->logA = f.log2_anchor_slots;
         tb->min_key_bytes = f.min_key_bytes; tb->max_key_bytes = f.max_key_bytes;
         acb_hash_multipliers(tb->gram, 1, tb->mul1);
         acb_hash_multipliers(tb->gram, 2, tb->mul2);
@@ -704,6 +713,7 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if ((rc = upload(&tb->d_keylen, f.key_len, (size_t)f.n_keys, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_bm1, f.bitmap1, (size_t)7 << (f.log2_bits1 - 8), tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_bm2, f.bitmap2, (size_t)1 << (f.log2_bits1 - 8), tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_bm3, f.bitmap3, f.log2_bits3 ? ((size_t)1 << (f.log2_bits3 - 5)) : 1, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_anchors, f.anchors, (size_t)8 << f.log2_anchor_slots, tb->dev_bytes))) break;
         unsigned int zero[4] = {0, 0, 0, 0};   /* work counters, re-armed by the kernels themselves */
         if ((rc = upload(&tb->d_work, zero, 4, tb->dev_bytes))) break;
@@ -803,8 +813,8 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     p.cls = tb->d_cls; p.gto = tb->d_goto; p.fail = tb->d_fail; p.key_of = tb->d_keyof;
     p.out_ptr = tb->d_outptr; p.out_idx = tb->d_outidx; p.key_len = tb->d_keylen;
     p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.max_key_bytes = tb->max_key_bytes;
-    p.bm1 = tb->d_bm1; p.bm2 = tb->d_bm2; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
-    p.log1 = tb->log1; p.log2 = tb->log2; p.logA = tb->logA;
+    p.bm1 = tb->d_bm1; p.bm2 = tb->d_bm2; p.bm3 = tb->d_bm3; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
+    p.log1 = tb->log1; p.log2 = tb->log2; p.log3 = tb->log3; p.logA = tb->logA;
     memcpy(p.mul1, tb->mul1, sizeof(p.mul1));
     memcpy(p.mul2, tb->mul2, sizeof(p.mul2));
     p.out = d_out; p.cap = cap; p.count = reinterpret_cast<unsigned long long *>(d_count);
@@ -836,6 +846,14 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
             int grid = (int)std::min<long long>(tb->sm_count, p.n_blocks);
             rc = launch_filter(p, tb->stride, grid, s);
             if (rc != ACB_OK) return rc;
+            if (getenv("ACB_DEBUG")) {                          /* diagnostic: size of the spilled candidate list */
+                unsigned long long cc = 0, mc = 0;
+                cudaStreamSynchronize(s);
+                cudaMemcpy(&cc, tb->d_cand_count, sizeof(cc), cudaMemcpyDeviceToHost);
+                cudaMemcpy(&mc, p.count, sizeof(mc), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[acb_scan_device] segment %lld..%lld: %llu candidates spilled (cap %llu), %llu matches so far, gram %d stride %d log3 %d\n",
+                        p.seg_begin, p.seg_end, cc, (unsigned long long)p.cand_cap, mc, p.gram, tb->stride, p.log3);
+            }
             acb_verify_kernel<<<p.inline_resolve ? tb->sm_count : tb->sm_count * 6, kVerThreads, 0, s>>>(p);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) { acb_set_error("verify kernel launch failed: %s", cudaGetErrorString(e)); return ACB_ECUDA; }

@@ -37,6 +37,7 @@
 #define ACB_S2_M1 0xD3A2646Du
 #define ACB_S2_M2 0xFD7046C5u
 #define ACB_S2_M3 0xB55A4F09u
+#define ACB_S3_MIX 0x9E3779B1u   /* stage 3 (global bitmap): bit index = (tag * ACB_S3_MIX) >> (32 - log2_bits3) */
 
 /* fill mul[0..3] for a gram of g bytes; stage = 1 or 2 */
 ACB_HD void acb_hash_multipliers(int g, int stage, uint32_t mul[ACB_MAX_WINDOWS]) {

@@ -102,8 +102,8 @@ struct Flat {
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint8_t byte_class[256];
     std::vector<int32_t> goto_cm, fail, key_of, out_ptr, out_idx, key_len;
-    int32_t gram = 0, stride = 0, log1 = 0, log2 = 0, logA = 0;
-    std::vector<uint32_t> bm1, bm2, anchors;
+    int32_t gram = 0, stride = 0, log1 = 0, log2 = 0, log3 = 0, logA = 0;
+    std::vector<uint32_t> bm1, bm2, bm3, anchors;
 };
 
 } // namespace
@@ -451,6 +451,20 @@ static void build_filter(acb_trie *t, Flat &f) {
         }
         a = b;
     }
+    /* stage 3: a bitmap in global memory over a re-mix of the tag, 64 bits per distinct tag.  Only used
+     * when the shared-memory bitmaps are too full to reject much (large key sets): it keeps the flood of
+     * survivors away from the anchor table at the price of one L2 access each. */
+    {
+        const double fill2 = (double)best_grams.size() / std::pow(2.0, best.log1 - 3);
+        f.log3 = 0;
+        f.bm3.assign(1, 0);
+        if (fill2 > 0.25) {
+            int log3 = std::min(30, std::max(16, ceil_log2_u64((uint64_t)entries.size() * 64 + 1)));
+            f.log3 = log3;
+            f.bm3.assign((size_t)1 << (log3 - 5), 0);
+            for (const Entry &e : entries) set_bit(f.bm3, (e.w[0] * ACB_S3_MIX) >> (32 - log3));
+        }
+    }
     int logA = std::max(10, ceil_log2_u64((uint64_t)entries.size() * 4 + 1));     /* load factor <= 1/4 */
     if (logA > 28) logA = 28;
     while (((size_t)1 << logA) < entries.size() + entries.size() / 4 + 1) logA++;
@@ -576,6 +590,8 @@ extern "C" int acb_trie_make_automaton(acb_trie *t, int32_t *built) {
             f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.log2 = 10; f.logA = 10;
             f.bm1.assign((size_t)7 << (13 - 8), 0);
             f.bm2.assign((size_t)1 << (13 - 8), 0);
+            f.log3 = 0;
+            f.bm3.assign(1, 0);
             f.anchors.assign(((size_t)1 << 10) * 8, 0);
         }
         f.valid = true;
@@ -611,7 +627,9 @@ extern "C" int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out) {
     out->stride = f.stride;
     out->log2_bits1 = f.log1;
     out->log2_bits2 = f.log2;
+    out->log2_bits3 = f.log3;
     out->log2_anchor_slots = f.logA;
+    out->bitmap3 = f.bm3.data();
     out->bitmap1 = f.bm1.data();
     out->bitmap2 = f.bm2.data();
     out->anchors = f.anchors.data();

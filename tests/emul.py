@@ -105,6 +105,9 @@ def emul_filter(f, buf, offsets=None, stride_bytes=0):
         tag = hash_bytes(buf, q, g, mul2) | 1
         if not (int(f["bitmap2"][tag >> (40 - l1)]) >> ((tag >> (35 - l1)) & 31)) & 1:
             continue
+        l3 = f["log2_bits3"]
+        if l3 and not _bit(f["bitmap3"], ((tag * 0x9E3779B1) & M32) >> (32 - l3)):
+            continue
         slot = tag >> (32 - lA)
         bounds = None
         while True:
