@@ -307,8 +307,8 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": world * total / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": total,
-               "d2h_bytes_per_step": 8 + 12 * len(m), "ms_per_step": dt * 1e3, "steps": e2e_steps,
+        e2e = {"value": world * total / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": world * total,
+               "d2h_bytes_per_step": world * (8 + 12 * len(m)), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "includes": "H2D of the batch from pinned host memory, kernel, D2H of count+records, reference-order sort"}
         assert len(m) == n_matches, (len(m), n_matches)
 

@@ -391,8 +391,9 @@ __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (
                 h += w * mul[k];
             }
             const uint32_t word = lds_word(__umulhi(h, c.mul_word) * c.four + c.sbm);
-            const uint32_t bit0 = __funnelshift_r(word, 0u, h >> c.sh_bit);        /* word >> (idx & 31) */
-            acc = __funnelshift_r(acc, bit0, 1);                                   /* (acc >> 1) | (bit0 << 31) */
+            /* blocked Bloom, k = 2: both bits of the gram must be set in this word (wrap shifts use 5 bits) */
+            const uint32_t both = __funnelshift_r(word, 0u, h >> c.sh_bit) & __funnelshift_r(word, 0u, h);
+            acc = __funnelshift_r(acc, both, 1);                                   /* (acc >> 1) | (bit 0 of both << 31) */
         }
         uint32_t hits = (kProbes == 32) ? acc : (acc >> (32 - kProbes));           /* bit i = probe i */
         if (GUARD && pos0 + kFChunk > c.seg_len) {                                 /* probes that start past the segment */

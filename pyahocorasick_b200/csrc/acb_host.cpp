@@ -383,7 +383,7 @@ static void build_filter(acb_trie *t, Flat &f) {
     f.log1 = best.log1;
     /* The 2^log1 bits of shared memory are split 7/8 : 1/8 between the stage-1 bitmap (probed at
      * every position, indexed by hash1) and the stage-2 bitmap (probed only by stage-1 survivors,
-     * indexed by hash2):  word1 = umulhi(hash1, 7 << (log1-8)), bit1 = (hash1 >> (32-log1)) & 31;
+     * indexed by hash2):  word1 = umulhi(hash1, 7 << (log1-8)), bits (hash1 >> (32-log1)) & 31 AND hash1 & 31;
      *                     word2 = hash2 >> (40-log1),           bit2 = (hash2 >> (35-log1)) & 31. */
     const uint32_t mulw1 = 7u << (best.log1 - 8);
     f.bm1.assign((size_t)7 << (best.log1 - 8), 0);
@@ -394,7 +394,9 @@ static void build_filter(acb_trie *t, Flat &f) {
     acb_hash_multipliers(g, 2, mul2);
     for (const auto &gr : best_grams) {
         uint32_t h1 = acb_hash_bytes(gr.data(), g, mul1), h2 = acb_hash_bytes(gr.data(), g, mul2) | 1u;
-        f.bm1[(size_t)(((uint64_t)h1 * mulw1) >> 32)] |= 1u << ((h1 >> (32 - best.log1)) & 31);
+        /* two bits per gram inside one word (a blocked Bloom filter with k = 2): the probe costs one
+           shared-memory load either way, and a random gram now has to find BOTH bits set */
+        f.bm1[(size_t)(((uint64_t)h1 * mulw1) >> 32)] |= (1u << ((h1 >> (32 - best.log1)) & 31)) | (1u << (h1 & 31));
         f.bm2[h2 >> (40 - best.log1)] |= 1u << ((h2 >> (35 - best.log1)) & 31);
     }
 

@@ -98,7 +98,8 @@ def emul_filter(f, buf, offsets=None, stride_bytes=0):
         return recs
     for q in range(0, total, s):
         h1 = hash_bytes(buf, q, g, mul1)
-        if not (int(f["bitmap1"][(h1 * (7 << (l1 - 8))) >> 32]) >> ((h1 >> (32 - l1)) & 31)) & 1:
+        w1 = int(f["bitmap1"][(h1 * (7 << (l1 - 8))) >> 32])
+        if not ((w1 >> ((h1 >> (32 - l1)) & 31)) & (w1 >> (h1 & 31)) & 1):
             continue
         if q + g > total:
             continue
