@@ -457,13 +457,18 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
     int *s_cnt = reinterpret_cast<int *>(s_stage + kWarps * kStageCap);  /* kWarps */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {   /* both bitmaps -> shared memory (stage 1 in the first 7/8 of the words, stage 2 in the last 1/8) */
+    {   /* both bitmaps -> shared memory (stage 1 in the first 7/8 of the words, stage 2 in the last 1/8), with
+           cp.async so that all of a thread's 16-byte pieces are in flight at once instead of one L2 round trip each */
         const int n1 = 7 * (nwords / 8);
         const uint4 *src1 = reinterpret_cast<const uint4 *>(p.bm1), *src2 = reinterpret_cast<const uint4 *>(p.bm2);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_bm);
-        for (int i = tid; i < n1 / 4; i += kThreads) dst[i] = __ldg(src1 + i);
-        for (int i = tid; i < (nwords - n1) / 4; i += kThreads) dst[n1 / 4 + i] = __ldg(src2 + i);
+        const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(s_bm);
+        for (int i = tid; i < n1 / 4; i += kThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sdst + 16u * i), "l"(src1 + i));
+        for (int i = tid; i < (nwords - n1) / 4; i += kThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sdst + 16u * (n1 / 4 + i)), "l"(src2 + i));
+        asm volatile("cp.async.commit_group;");
         if (tid < kWarps) s_cnt[tid] = 0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     WarpResolve wr;
