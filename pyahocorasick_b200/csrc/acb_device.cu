@@ -112,6 +112,7 @@ struct ScanParams {
     unsigned int *work_ctr;        /* [0] next work unit, [1] filter CTAs done, [2] verify CTAs done */
     int stride_shift;              /* log2(stride_bytes) when it is a power of two, else -1 */
     int letter_shift;              /* log2(L) */
+    unsigned long long *timeline;  /* debug (ACB_TIMELINE=1): 6 globaltimer stamps per warp, else nullptr */
     int inline_resolve;            /* 1: warps resolve their own candidates between work units; 0: all go to the list */
 };
 
@@ -227,6 +228,13 @@ __device__ __forceinline__ bool text_equals(const ScanParams &p, long long x, in
  * per warp in shared memory together with hash2 of their gram (re-read through L1) and written,
  * 32 at a time, to the global candidate list.  Work units that lie completely inside the buffer
  * run a variant without any bounds check (GUARD = false). */
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define ACB_STAMP(i) do { if (p.timeline && lane == 0) p.timeline[((size_t)blockIdx.x * kWarps + warp) * 6 + (i)] = gtime(); } while (0)
 
 __device__ __forceinline__ uint32_t lds_word(uint32_t saddr) {
     uint32_t v;
@@ -457,6 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
     int *s_cnt = reinterpret_cast<int *>(s_stage + kWarps * kStageCap);  /* kWarps */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    ACB_STAMP(0);
     {   /* both bitmaps -> shared memory (stage 1 in the first 7/8 of the words, stage 2 in the last 1/8), with
            cp.async so that all of a thread's 16-byte pieces are in flight at once instead of one L2 round trip each */
         const int n1 = 7 * (nwords / 8);
@@ -471,6 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    ACB_STAMP(1);
     WarpResolve wr;
     wr.queue = s_queue + warp * kQueueCap;
     wr.ws.buf = s_stage + warp * kStageCap;
@@ -504,11 +514,13 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
     long long interior_end = c.total_rel - 64 < (long long)c.seg_len ? c.total_rel - 64 : (long long)c.seg_len;
     const long long n_interior = interior_end < kBlockBytes ? 0 : interior_end / kBlockBytes;
 
+    bool first_unit = true;
     for (;;) {
         unsigned int blk = 0;
         if (lane == 0) blk = atomicAdd(p.work_ctr, 1u);
         blk = __shfl_sync(kFull, blk, 0);
         if ((long long)blk >= p.n_blocks) break;
+        if (first_unit) { ACB_STAMP(2); first_unit = false; }
         const uint32_t rel0 = blk * (uint32_t)kBlockBytes;
         if ((long long)blk < n_interior) filter_unit<NW, STRIDE, false>(c, mul, mul2, rel0, qhead, qtail);
         else filter_unit<NW, STRIDE, true>(c, mul, mul2, rel0, qhead, qtail);
@@ -517,8 +529,10 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
             else spill_queue(c, qhead, qtail, false);
         }
     }
+    ACB_STAMP(3);
     if (p.inline_resolve) drain_queue(p, wr, qhead, qtail, true, lane);  /* leftovers */
     else spill_queue(c, qhead, qtail, true);
+    ACB_STAMP(4);
     /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
     __syncthreads();
     if (tid == 0) {
@@ -530,6 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
             __threadfence();
         }
     }
+    ACB_STAMP(5);
 }
 
 /* ------------------------------------------------------- the verify kernel */
@@ -850,8 +865,33 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
             p.seg_end = std::min<long long>(seg + kSegBytes, total_bytes);
             p.n_blocks = (p.seg_end - p.seg_begin + kBlockBytes - 1) / kBlockBytes;
             int grid = (int)std::min<long long>(tb->sm_count, p.n_blocks);
+            unsigned long long *d_tl = nullptr;
+            const size_t n_tl = (size_t)grid * kWarps * 6;
+            if (getenv("ACB_TIMELINE")) {                       /* diagnostic: per-warp phase timestamps */
+                cudaMalloc(reinterpret_cast<void **>(&d_tl), n_tl * 8);
+                cudaMemset(d_tl, 0, n_tl * 8);
+                p.timeline = d_tl;
+            }
             rc = launch_filter(p, tb->stride, grid, s);
             if (rc != ACB_OK) return rc;
+            if (d_tl) {
+                std::vector<unsigned long long> tl(n_tl);
+                cudaStreamSynchronize(s);
+                cudaMemcpy(tl.data(), d_tl, n_tl * 8, cudaMemcpyDeviceToHost);
+                cudaFree(d_tl);
+                p.timeline = nullptr;
+                unsigned long long t0 = ~0ULL;
+                for (size_t w = 0; w < n_tl / 6; w++) if (tl[w * 6]) t0 = std::min(t0, tl[w * 6]);
+                const char *nm[6] = {"start", "bitmap ready", "first unit claimed", "stream done", "drained", "exit"};
+                for (int k = 0; k < 6; k++) {
+                    std::vector<double> v;
+                    for (size_t w = 0; w < n_tl / 6; w++) if (tl[w * 6 + k]) v.push_back((double)(tl[w * 6 + k] - t0) / 1000.0);
+                    if (v.empty()) continue;
+                    std::sort(v.begin(), v.end());
+                    fprintf(stderr, "[timeline] %-20s n=%6zu  min %8.2f  p50 %8.2f  p90 %8.2f  max %8.2f us\n", nm[k], v.size(),
+                            v.front(), v[v.size() / 2], v[v.size() * 9 / 10], v.back());
+                }
+            }
             if (getenv("ACB_DEBUG")) {                          /* diagnostic: size of the spilled candidate list */
                 unsigned long long cc = 0, mc = 0;
                 cudaStreamSynchronize(s);
