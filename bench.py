@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--scale", type=float, default=None, help="shrink the batch (debug only; invalidates the number)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", default="auto", choices=["auto", "filter", "dfa"])
-    ap.add_argument("--cpu-sample", type=int, default=200_000, help="haystacks in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="haystacks in the cpu_baseline sample (~10 s of CPU for C2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--variant", default="planted", choices=["planted", "sparse"], help="sparse = pure random haystacks (diagnostic)")
@@ -330,7 +330,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "acb_filter_kernel" if args.algo != "dfa" else "acb_dfa_kernel",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "acb_filter_kernel (+ acb_verify_kernel over the spill list, 4 us when empty)" if args.algo != "dfa" else "acb_dfa_kernel",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes}
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------
