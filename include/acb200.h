@@ -108,6 +108,7 @@ typedef struct acb_flat_view {
     const uint8_t *byte_class;    /* [256]  byte -> class                                     */
     const int32_t *goto_cm;       /* [K*S]  column-major: goto_cm[c*S+s] = child or -1        */
     const int32_t *fail;          /* [S]    failure link, fail[0] = -1 (root has none, A12)   */
+    const int32_t *letter_fail;   /* [S]    fail link between letter-aligned states (== fail for 1-byte letters), root -1 */
     const int32_t *key_of;        /* [S]    key_id ending exactly at this state, or -1        */
     const int32_t *out_ptr;       /* [S+1]  CSR over out_idx                                  */
     const int32_t *out_idx;       /* key ids on the chain s, fail(s), ... (longest first)     */
@@ -141,7 +142,9 @@ int64_t acb_table_device_bytes(const acb_table *tb);
 enum {
     ACB_ALGO_AUTO   = 0,
     ACB_ALGO_FILTER = 1,  /* gram-filter + trie walk (start-anchored), the fast path          */
-    ACB_ALGO_DFA    = 2   /* goto/fail automaton walk with CSR outputs, one lane per chunk     */
+    ACB_ALGO_DFA    = 2,  /* goto/fail automaton walk with CSR outputs, one lane per chunk     */
+    ACB_ALGO_LONG   = 3   /* iter_long semantics (src/AutomatonSearchIterLong.c:89-153): longest,
+                             non-overlapping matches; one lane per haystack                       */
 };
 
 /* Batch scan, DEVICE buffers, asynchronous on `stream` (a cudaStream_t / CUstream).

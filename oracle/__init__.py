@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
     L.orc_make_automaton.restype = ctypes.c_int
     L.orc_find_all.argtypes = [vp, u32p, i64, i64, i64p, i64p, i64]
     L.orc_find_all.restype = i64
+    L.orc_iter_long.argtypes = [vp, u32p, i64, i64, i64p, i64p, i64]
+    L.orc_iter_long.restype = i64
     L.orc_iter_new.argtypes = [vp, u32p, i64, i64, ctypes.c_int]
     L.orc_iter_new.restype = vp
     L.orc_iter_free.argtypes = [vp]
@@ -159,6 +161,23 @@ class OracleAutomaton:
 
     def iter(self, text, start=0, end=None, ignore_white_space=False):
         return OracleIter(self, text, start, end, ignore_white_space)
+
+    def iter_long(self, text, start=0, end=None):
+        """[(end_index, value)] of the longest-match variant (src/AutomatonSearchIterLong.c)."""
+        w = _letters(text)
+        if end is None:
+            end = len(w)
+        cap = 1024
+        while True:
+            idx = np.empty(cap, dtype=np.int64)
+            val = np.empty(cap, dtype=np.int64)
+            n = self._L.orc_iter_long(self._h, _p(w, ctypes.c_uint32), start, end,
+                                      _p(idx, ctypes.c_int64), _p(val, ctypes.c_int64), cap)
+            if n < 0:
+                raise AttributeError("not an automaton yet")
+            if n <= cap:
+                return list(zip(idx[:n].tolist(), val[:n].tolist()))
+            cap = int(n)
 
     def scan_batch_bytes(self, flat: np.ndarray, offsets: np.ndarray) -> np.ndarray:
         """(n,3) int32 records (hay_id, end_index, value) in scan order."""

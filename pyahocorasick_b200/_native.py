@@ -11,8 +11,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ACB_LIB") or os.path.join(_PKG, "_native", "libacb200.so")   # ACB_LIB: experimental builds
 
 ACB_OK, ACB_ENOMEM, ACB_EINVAL, ACB_ESTATE, ACB_ECUDA, ACB_EOVERFLOW, ACB_ERANGE = 0, -1, -2, -3, -4, -5, -6
-ALGO_AUTO, ALGO_FILTER, ALGO_DFA = 0, 1, 2
-ALGOS = {"auto": ALGO_AUTO, "filter": ALGO_FILTER, "dfa": ALGO_DFA}
+ALGO_AUTO, ALGO_FILTER, ALGO_DFA, ALGO_LONG = 0, 1, 2, 3
+ALGOS = {"auto": ALGO_AUTO, "filter": ALGO_FILTER, "dfa": ALGO_DFA, "long": ALGO_LONG}
 
 MATCH_DTYPE = np.dtype([("hay_id", "<i4"), ("end_index", "<i4"), ("key_id", "<i4")])
 
@@ -23,6 +23,7 @@ class FlatView(ctypes.Structure):
         ("letter_bytes", ctypes.c_int32), ("min_key_bytes", ctypes.c_int32), ("max_key_bytes", ctypes.c_int32),
         ("byte_class", ctypes.POINTER(ctypes.c_uint8)),
         ("goto_cm", ctypes.POINTER(ctypes.c_int32)), ("fail", ctypes.POINTER(ctypes.c_int32)),
+        ("letter_fail", ctypes.POINTER(ctypes.c_int32)),
         ("key_of", ctypes.POINTER(ctypes.c_int32)), ("out_ptr", ctypes.POINTER(ctypes.c_int32)),
         ("out_idx", ctypes.POINTER(ctypes.c_int32)), ("key_len", ctypes.POINTER(ctypes.c_int32)),
         ("gram_bytes", ctypes.c_int32), ("stride", ctypes.c_int32),

@@ -426,7 +426,7 @@ class Automaton:
             n_states=S, n_classes=K, n_keys=fv.n_keys, letter_bytes=fv.letter_bytes,
             min_key_bytes=fv.min_key_bytes, max_key_bytes=fv.max_key_bytes,
             byte_class=arr(fv.byte_class, 256, np.uint8), goto_cm=arr(fv.goto_cm, K * S, np.int32).reshape(K, S),
-            fail=arr(fv.fail, S, np.int32), key_of=arr(fv.key_of, S, np.int32), out_ptr=arr(fv.out_ptr, S + 1, np.int32),
+            fail=arr(fv.fail, S, np.int32), letter_fail=arr(fv.letter_fail, S, np.int32), key_of=arr(fv.key_of, S, np.int32), out_ptr=arr(fv.out_ptr, S + 1, np.int32),
             out_idx=arr(fv.out_idx, n_out, np.int32), key_len=arr(fv.key_len, fv.n_keys, np.int32),
             gram_bytes=fv.gram_bytes, stride=fv.stride, log2_bits1=fv.log2_bits1, log2_bits2=fv.log2_bits2,
             log2_bits3=fv.log2_bits3, log2_anchor_slots=fv.log2_anchor_slots,
@@ -520,7 +520,19 @@ class Automaton:
         return None
 
     def iter_long(self, *args):
-        raise NotImplementedError("iter_long is outside the B200 hot path in this round (SURVEY.md section 8(f) #1)")
+        """src/Automaton.c:968-1040 + src/AutomatonSearchIterLong.c:89-153: iter_long(string, [start, [end]]) --
+        longest, non-overlapping matches.  One GPU lane replays the reference's state machine per haystack."""
+        if self.kind != AHOCORASICK:
+            raise AttributeError("not an automaton yet; add some words and call make_automaton")
+        if len(args) < 1:
+            raise IndexError("tuple index out of range")
+        letters = self._letters(args[0], required=True)
+        start, end = _parse_start_end(args, 1, 2, 0, len(letters))
+        return AutomatonSearchIterLong(self, letters, start, end)
+
+    def find_long_batch(self, haystacks, *, sort: bool = True, device: Optional[int] = None) -> "Matches":
+        """iter_long() over a whole batch (same input forms and result type as find_all_batch)."""
+        return self.find_all_batch(haystacks, algo="long", sort=sort, device=device)
 
     def dump(self):
         """(nodes, edges, fail) in the spirit of src/Automaton.c:1100-1180, with int state ids."""
@@ -660,6 +672,33 @@ class AutomatonSearchIter:
         self._install(letters, 0, len(letters))
         self._index = -1                                            # :354
         return None
+
+
+class AutomatonSearchIterLong:
+    """Result of `Automaton.iter_long()`; matches are produced by one GPU scan at construction."""
+
+    def __init__(self, A: Automaton, letters: np.ndarray, start: int, end: int):
+        self._A = A
+        self._version = A._version
+        seg = letters[start:end] if end > start else letters[:0]
+        rec = A._scan_one(seg, algo="long") if len(seg) else np.empty(0, dtype=N.MATCH_DTYPE)
+        self._matches = list(zip((rec["end_index"] + start).tolist(), rec["key_id"].tolist()))
+        self._cursor = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._version != self._A._version:
+            raise ValueError("underlaying automaton has changed, iterator is not valid anymore")
+        if self._cursor >= len(self._matches):
+            raise StopIteration
+        i, k = self._matches[self._cursor]
+        self._cursor += 1
+        return (i, self._A._values[k])
+
+    def set(self, *args):
+        raise NotImplementedError("AutomatonSearchIterLong.set() is not part of this round (SURVEY.md section 8(f) #1)")
 
 
 # ---------------------------------------------------------------------- helpers

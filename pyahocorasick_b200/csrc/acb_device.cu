@@ -85,6 +85,7 @@ struct ScanParams {
     const uint8_t *cls;
     const int32_t *gto;            /* flagged goto (kTermBit) */
     const int32_t *fail;
+    const int32_t *letter_fail;
     const int32_t *key_of;
     const int32_t *out_ptr;
     const int32_t *out_idx;
@@ -628,6 +629,72 @@ __global__ void __launch_bounds__(kDfaThreads) acb_dfa_kernel(const ScanParams p
     }
 }
 
+/* ------------------------------------------------------- the iter_long kernel */
+/* ACB_ALGO_LONG: the reference's longest-match iterator (src/AutomatonSearchIterLong.c:89-153) is a
+ * sequential state machine per haystack (after every reported match it restarts from the root at the
+ * match's last letter), so one lane replays it per haystack: trie edges only (`goto`, letter by letter),
+ * letter-level fail links, and the reference's early return when a non-terminal state's fail state ends
+ * a key (:122-126).  Records of one haystack come out in increasing end_index. */
+__device__ __forceinline__ int32_t letter_step(const ScanParams &p, int32_t st, const uint8_t *letter) {
+    for (int b = 0; b < p.L; b++) {
+        const int32_t nx = __ldg(p.gto + (long long)__ldg(p.cls + letter[b]) * p.S + st);
+        if (nx < 0) return -1;
+        st = nx & kIdMask;
+    }
+    return st;
+}
+
+__global__ void __launch_bounds__(kDfaThreads) acb_long_kernel(const __grid_constant__ ScanParams p) {
+    const long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= p.n_hay) return;
+    const long long hs = p.offsets ? __ldg(p.offsets + h) : h * p.stride_bytes;
+    const long long he = p.offsets ? __ldg(p.offsets + h + 1) : hs + p.stride_bytes;
+    const long long n = (he - hs) / p.L;                       /* letters */
+    const uint8_t *text = p.hay + hs;
+    int32_t state = 0, last_node = -1;
+    long long index = -1, last_index = -1;
+    for (;;) {
+        if (last_node >= 0) {                                   /* return_output */
+            unsigned long long g = atomicAdd(p.count, 1ULL);
+            if (g < (unsigned long long)p.cap) {
+                acb_match m;
+                m.hay_id = (int32_t)h;
+                m.end_index = (int32_t)last_index;
+                m.key_id = __ldg(p.key_of + last_node);
+                p.out[g] = m;
+            }
+            state = 0;                                          /* start over: no overlapped results */
+            index = last_index;
+            last_node = -1;
+            last_index = -1;
+        }
+        index += 1;
+        bool emit = false;
+        while (index < n) {
+            const int32_t nx = letter_step(p, state, text + index * p.L);
+            if (nx >= 0) {
+                if (__ldg(p.key_of + nx) >= 0) {
+                    last_node = nx;
+                    last_index = index;
+                } else {
+                    const int32_t fl = __ldg(p.letter_fail + nx);
+                    if (fl > 0 && __ldg(p.key_of + fl) >= 0) { last_node = fl; last_index = index; emit = true; break; }
+                }
+                state = nx;
+                index += 1;
+            } else {
+                if (last_node >= 0) { emit = true; break; }
+                for (;;) {
+                    state = __ldg(p.letter_fail + state);
+                    if (state < 0) { state = 0; index += 1; break; }
+                    if (letter_step(p, state, text + index * p.L) >= 0) break;
+                }
+            }
+        }
+        if (!emit && last_node < 0) break;                      /* StopIteration */
+    }
+}
+
 } // namespace
 
 /* ------------------------------------------------------------- the table */
@@ -639,6 +706,7 @@ struct acb_table {
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     uint8_t *d_cls = nullptr;
+    int32_t *d_lfail = nullptr;
     int32_t *d_goto = nullptr, *d_fail = nullptr, *d_keyof = nullptr, *d_outptr = nullptr, *d_outidx = nullptr, *d_keylen = nullptr;
     uint32_t *d_bm1 = nullptr, *d_bm2 = nullptr, *d_bm3 = nullptr, *d_anchors = nullptr;
     unsigned int *d_work = nullptr;
@@ -683,7 +751,7 @@ static int upload(T **dst, const T *src, size_t n, long long &acc) {
 extern "C" void acb_table_free(acb_table *tb) {
     if (!tb) return;
     cudaSetDevice(tb->device);
-    cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
+    cudaFree(tb->d_lfail); cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
     cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_bm2); cudaFree(tb->d_bm3); cudaFree(tb->d_anchors);
     cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->d_cand_count); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
     if (tb->h_count) cudaFreeHost(tb->h_count);
@@ -728,6 +796,7 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if ((rc = upload(&tb->d_cls, f.byte_class, 256, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_goto, flagged.data(), flagged.size(), tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_fail, f.fail, (size_t)f.n_states, tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_lfail, f.letter_fail, (size_t)f.n_states, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_keyof, f.key_of, (size_t)f.n_states, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_outptr, f.out_ptr, (size_t)f.n_states + 1, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_outidx, f.out_idx, (size_t)f.out_ptr[f.n_states], tb->dev_bytes))) break;
@@ -831,7 +900,7 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     memset(&p, 0, sizeof(p));
     p.hay = d_hay; p.total = total_bytes; p.offsets = reinterpret_cast<const long long *>(d_offsets);
     p.n_hay = n_hay; p.stride_bytes = stride_bytes;
-    p.cls = tb->d_cls; p.gto = tb->d_goto; p.fail = tb->d_fail; p.key_of = tb->d_keyof;
+    p.cls = tb->d_cls; p.gto = tb->d_goto; p.fail = tb->d_fail; p.letter_fail = tb->d_lfail; p.key_of = tb->d_keyof;
     p.out_ptr = tb->d_outptr; p.out_idx = tb->d_outidx; p.key_len = tb->d_keylen;
     p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.max_key_bytes = tb->max_key_bytes;
     p.bm1 = tb->d_bm1; p.bm2 = tb->d_bm2; p.bm3 = tb->d_bm3; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
@@ -912,6 +981,12 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
         acb_dfa_kernel<<<(unsigned)grid, kDfaThreads, 0, s>>>(p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { acb_set_error("DFA kernel launch failed: %s", cudaGetErrorString(e)); return ACB_ECUDA; }
+        g_launches.fetch_add(1);
+    } else if (algo == ACB_ALGO_LONG) {
+        long long grid = (n_hay + kDfaThreads - 1) / kDfaThreads;
+        acb_long_kernel<<<(unsigned)grid, kDfaThreads, 0, s>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { acb_set_error("iter_long kernel launch failed: %s", cudaGetErrorString(e)); return ACB_ECUDA; }
         g_launches.fetch_add(1);
     } else {
         acb_set_error("unknown algo %d", algo);

@@ -101,7 +101,7 @@ struct Flat {
     int32_t S = 0, K = 0, n_keys = 0;
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint8_t byte_class[256];
-    std::vector<int32_t> goto_cm, fail, key_of, out_ptr, out_idx, key_len;
+    std::vector<int32_t> goto_cm, fail, letter_fail, key_of, out_ptr, out_idx, key_len;
     int32_t gram = 0, stride = 0, log1 = 0, log2 = 0, log3 = 0, logA = 0;
     std::vector<uint32_t> bm1, bm2, bm3, anchors;
 };
@@ -569,6 +569,16 @@ extern "C" int acb_trie_make_automaton(acb_trie *t, int32_t *built) {
             f.fail[s] = (g >= 0) ? g : 0;                                 /* :631-633 */
         }
 
+        /* letter-level failure link (iter_long walks the trie letter by letter): the first state on the
+         * byte-level fail chain that sits on a letter boundary; equal to fail[] for 1-byte letters */
+        f.letter_fail.assign(S, -1);
+        for (int32_t s = 1; s < S; s++) {
+            if (depth[s] % t->letter_bytes) continue;
+            int32_t x = f.fail[s];
+            while (x > 0 && depth[x] % t->letter_bytes) x = f.fail[x];
+            f.letter_fail[s] = x < 0 ? 0 : x;
+        }
+
         /* CSR output lists: keys on s, fail(s), fail(fail(s)).. (longest first) */
         std::vector<int32_t> osuf(S, -1), cnt(S, 0);
         int64_t total = 0;
@@ -621,6 +631,7 @@ extern "C" int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out) {
     out->byte_class = f.byte_class;
     out->goto_cm = f.goto_cm.data();
     out->fail = f.fail.data();
+    out->letter_fail = f.letter_fail.data();
     out->key_of = f.key_of.data();
     out->out_ptr = f.out_ptr.data();
     out->out_idx = f.out_idx.data();

@@ -167,14 +167,75 @@ def emul_dfa(f, buf, offsets=None, stride_bytes=0, span=64):
     return _sorted(recs, key_len)
 
 
+def emul_long(f, buf, offsets=None, stride_bytes=0):
+    """acb_long_kernel: the reference's iter_long state machine (src/AutomatonSearchIterLong.c:89-153) on the
+    flattened tables, one haystack at a time, letter by letter."""
+    L = f["letter_bytes"]
+    total = len(buf)
+    n_hay = (len(offsets) - 1) if offsets is not None else total // stride_bytes
+    cls, gto, lfail, key_of = f["byte_class"], f["goto_cm"], f["letter_fail"], f["key_of"]
+    recs = []
+
+    for h in range(n_hay):
+        hs = int(offsets[h]) if offsets is not None else h * stride_bytes
+        he = int(offsets[h + 1]) if offsets is not None else hs + stride_bytes
+        n = (he - hs) // L
+
+        def step(st, i):
+            for b in range(L):
+                st = int(gto[cls[buf[hs + i * L + b]], st])
+                if st < 0:
+                    return -1
+            return st
+
+        state, index, last_node, last_index = 0, -1, -1, -1
+        while True:
+            if last_node >= 0:
+                recs.append((h, last_index, int(key_of[last_node])))
+                state, index, last_node, last_index = 0, last_index, -1, -1
+            index += 1
+            emit = False
+            while index < n:
+                nx = step(state, index)
+                if nx >= 0:
+                    if key_of[nx] >= 0:
+                        last_node, last_index = nx, index
+                    else:
+                        fl = int(lfail[nx])
+                        if fl > 0 and key_of[fl] >= 0:
+                            last_node, last_index, emit = fl, index, True
+                            break
+                    state = nx
+                    index += 1
+                else:
+                    if last_node >= 0:
+                        emit = True
+                        break
+                    while True:
+                        state = int(lfail[state])
+                        if state < 0:
+                            state = 0
+                            index += 1
+                            break
+                        if step(state, index) >= 0:
+                            break
+            if not emit and last_node < 0:
+                break
+    return _sorted(recs, f["key_len"])
+
+
 def install(monkeypatch_or_none, algo="filter"):
     """Route Automaton._scan_flat through the emulation (CPU tests of the host logic only)."""
     from pyahocorasick_b200 import _native as N
     from pyahocorasick_b200 import automaton as am
 
-    def fake_scan_flat(self, flat, offsets, n_hay, stride_bytes, algo=algo, sort=True, device=None):
+    default_algo = algo
+
+    def fake_scan_flat(self, flat, offsets, n_hay, stride_bytes, algo="auto", sort=True, device=None):
         f = self.flat()
-        fn = emul_dfa if algo == "dfa" else emul_filter
+        if algo == "auto":
+            algo = default_algo
+        fn = {"dfa": emul_dfa, "long": emul_long}.get(algo, emul_filter)
         recs = fn(f, np.asarray(flat, dtype=np.uint8), offsets, stride_bytes)
         out = np.empty(len(recs), dtype=N.MATCH_DTYPE)
         for i, r in enumerate(recs):

@@ -121,6 +121,8 @@ def _exec(A, op):
         r = A.find_all(dec(op["hay"]), lambda i, v: res.append([int(i), v]), *op.get("args", []))
         assert r is None
         return res
+    if kind == "iter_long":
+        return _pairs(A.iter_long(dec(op["hay"]), *op.get("args", [])))
     if kind == "find_all_notbuilt":
         return A.find_all(dec(op["hay"]), lambda i, v: None)
     if kind == "iter_set":
@@ -259,6 +261,29 @@ def hotpath_scenarios():
                       words=[[c(w), i] for i, w in enumerate(["GT-C3303", "SAMSUNG-GT-C3303K/"])], ops=[
             dict(op="iter", hay=c("SAMSUNG-GT-C3303i/1.0 NetFront/3.5 Profile/MIDP-2.0")),
             dict(op="iter", hay=c("SAMSUNG-GT-C3303K/1.0 SAMSUNG-GT-C330 GT-C3303"))]))
+    # iter_long: tests/test_unit.py:1491-1520, tests/test_issue_133.py, docs/automaton_iter_long.rst:41-44
+    for fl in ("bytes", "unicode"):
+        c = lambda s, fl=fl: enc(conv(fl, s))  # noqa: E731
+        S.append(dict(name=f"iter_long_{fl}", flavour=fl, store=STORE_ANY,
+                      words=[[c(w), i] for i, w in enumerate("he here her".split())], ops=[
+            dict(op="iter_long", hay=c("he here her")), dict(op="iter_long", hay=c("he here her"), args=[2]),
+            dict(op="iter_long", hay=c("he here her"), args=[3, 9]), dict(op="iter_long", hay=c("")),
+            dict(op="iter_long", hay=c("hehehere herehe h")), dict(op="iter", hay=c("he here her"))]))
+        S.append(dict(name=f"iter_long_133a_{fl}", flavour=fl, store=STORE_ANY,
+                      words=[[c("b"), 0], [c("abc"), 1]], ops=[dict(op="iter_long", hay=c("abb")), dict(op="iter_long", hay=c("ababcabb"))]))
+        S.append(dict(name=f"iter_long_133b_{fl}", flavour=fl, store=STORE_ANY,
+                      words=[[c(w), i] for i, w in enumerate(["b", "c", "abd"])], ops=[dict(op="iter_long", hay=c("abc")), dict(op="iter_long", hay=c("abdabcab"))]))
+        S.append(dict(name=f"iter_long_133c_{fl}", flavour=fl, store=STORE_ANY,
+                      words=[[c(w), i] for i, w in enumerate(["知识产权", "国家知识产权局"])], ops=[dict(op="iter_long", hay=c("国家知识产权")), dict(op="iter_long", hay=c("国家知识产权局知识产权"))]))
+        S.append(dict(name=f"iter_long_overlap_{fl}", flavour=fl, store=STORE_ANY,
+                      words=[[c(w), i] for i, w in enumerate(["a", "ab", "abc", "bcd", "cde", "abcdef", "f", "ef"])], ops=[
+            dict(op="iter_long", hay=c("abcdefabcdeabcdabcabaf")), dict(op="iter_long", hay=c("xxabcdexefab")),
+            dict(op="iter_long", hay=c("aaaaabababcabcdabcdeabcdef"))]))
+    S.append(dict(name="iter_long_sequence", flavour="unicode", store=STORE_ANY, key_type=KEY_SEQUENCE,
+                  words=[[enc((1, 2)), 0], [enc((1, 2, 3)), 1], [enc((1, 2, 3, 4)), 2]], ops=[
+        dict(op="iter_long", hay=enc((0, 1, 2, 3, 4, 0, 0, 1, 2, 0, 1, 3, 1, 2, 3, 0)))]))
+    S.append(dict(name="iter_long_notbuilt", flavour="bytes", store=STORE_ANY, make=False,
+                  words=[[enc(b"he"), 0]], ops=[dict(op="iter_long", hay=enc(b"he"))]))
     # bytes >= 0x80 (src/utils.c:199-202 sign extension) -- bytes flavour only
     S.append(dict(name="high_bytes", flavour="bytes", store=STORE_ANY,
                   words=[[enc(b"\xff\x80"), 0], [enc(b"\x80"), 1], [enc(b"\x00\x00"), 2], [enc(b"\x7f\x80\xff"), 3]], ops=[
@@ -324,6 +349,7 @@ def random_scenarios():
                 p = int(rng.integers(0, max(1, hl - len(w))))
                 hay = hay[:p] + w + hay[p + len(w):]
             ops.append(dict(op="iter", hay=enc(hay)))
+            ops.append(dict(op="iter_long", hay=enc(hay)))
             if h % 3 == 0:
                 a = int(rng.integers(0, hl // 2))
                 b = int(rng.integers(hl // 2, hl + 1))

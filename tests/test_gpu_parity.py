@@ -28,8 +28,8 @@ SC = all_scenarios()
 def test_golden_on_gpu(sc, algo, monkeypatch):
     real = am.Automaton._scan_flat
 
-    def forced(self, flat, offsets, n_hay, stride_bytes, algo=algo, sort=True, device=None, _a=algo):
-        return real(self, flat, offsets, n_hay, stride_bytes, algo=_a, sort=sort, device=device)
+    def forced(self, flat, offsets, n_hay, stride_bytes, algo="auto", sort=True, device=None, _a=algo):
+        return real(self, flat, offsets, n_hay, stride_bytes, algo=_a if algo == "auto" else algo, sort=sort, device=device)
     monkeypatch.setattr(am.Automaton, "_scan_flat", forced)
     bad = run_ops(ac.flavour(sc["flavour"]), sc, record=False)
     assert not bad, bad[:3]
@@ -111,6 +111,21 @@ def test_reference_extension_agrees_on_c2_sample():
     for algo in ("filter", "dfa"):
         m = A.find_all_batch(w.haystacks, algo=algo)
         assert list(zip(m.hay_id.tolist(), m.end_index.tolist(), m.values())) == want
+
+
+def test_iter_long_batch_matches_oracle():
+    """find_long_batch == looping the oracle's iter_long (pinned to the reference by tests/golden) per haystack."""
+    rng = np.random.Generator(np.random.PCG64(2024))
+    for alpha, nk, lo, hi in ((np.frombuffer(b"ab", dtype=np.uint8), 30, 1, 6), (synth.ALNUM, 3000, 2, 8), (synth.DNA, 500, 3, 10)):
+        keys = synth.draw_keys(rng, alpha, nk, lo, hi)
+        hay = synth.random_haystacks(rng, alpha, 400, 200)
+        synth.plant(rng, hay, keys, np.arange(400))
+        A = synth.build_automaton(keys)
+        O = _oracle_for(keys)
+        want = [(h, e, v) for h in range(400) for e, v in O.iter_long(hay[h].tobytes())]
+        m = A.find_long_batch(hay)
+        assert list(zip(m.hay_id.tolist(), m.end_index.tolist(), m.values())) == want
+        assert list(A.iter_long(hay[7].tobytes(), 3, 150)) == O.iter_long(hay[7].tobytes(), 3, 150)
 
 
 def test_pathological_overlaps():

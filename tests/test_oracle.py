@@ -62,6 +62,16 @@ def test_oracle_matches_golden(sc):
             got = [[i, v] for i, v in A.iter(hay, s, e, iws)]
             assert got == op["expect"], (sc["name"], op)
             checked += 1
+        elif kind == "iter_long":
+            hay = dec(op["hay"])
+            a = op.get("args", [])
+            if any(x < 0 for x in a):
+                continue
+            s = a[0] if len(a) > 0 else 0
+            e = a[1] if len(a) > 1 else len(hay)
+            got = [[i, v] for i, v in A.iter_long(hay, s, e)]
+            assert got == op["expect"], (sc["name"], op)
+            checked += 1
         elif kind == "find_all":
             hay = dec(op["hay"])
             a = op.get("args", [])
