@@ -198,11 +198,9 @@ __device__ __forceinline__ void walk_from(const ScanParams &p, const WarpStage &
     }
 }
 
-/* do the n (<= 20) text bytes at x equal the packed bytes kw?  (zero fill past the end of the buffer) */
-__device__ __forceinline__ bool text_equals(const ScanParams &p, long long x, int n, const uint32_t kw[5]) {
+/* six aligned words covering the 20 text bytes from x on (zero fill past the end of the buffer) */
+__device__ __forceinline__ void load_text(const ScanParams &p, long long x, uint32_t (&w)[6]) {
     const long long x0 = x & ~3LL;
-    const int sh = (int)(x & 3) * 8;
-    uint32_t w[6];
     if (x0 + 24 <= p.total) {
         const uint32_t *a = reinterpret_cast<const uint32_t *>(p.hay + x0);
 #pragma unroll
@@ -211,6 +209,11 @@ __device__ __forceinline__ bool text_equals(const ScanParams &p, long long x, in
 #pragma unroll
         for (int i = 0; i < 6; i++) w[i] = load_word(p.hay, x0 + 4 * i, p.total);
     }
+}
+
+/* do the n (<= 20) text bytes at x (words w = load_text(x)) equal the packed bytes kw? */
+__device__ __forceinline__ bool text_equals(const uint32_t (&w)[6], long long x, int n, const uint32_t kw[5]) {
+    const int sh = (int)(x & 3) * 8;
     uint32_t diff = 0;
 #pragma unroll
     for (int i = 0; i < 5; i++) {
@@ -249,6 +252,10 @@ __device__ __forceinline__ void resolve(const ScanParams &p, const WarpStage &ws
     const uint32_t amask = (1u << p.logA) - 1u;
     uint32_t slot = tag >> (32 - p.logA);
     long long h = -1, hs = 0, he = 0;
+    /* the text at the probe position is fetched together with the anchor slot, not after it: for stride-1
+       filters (j == 0) that is the text every entry compares with, so the two L2 round trips overlap */
+    uint32_t tq[6];
+    load_text(p, q, tq);
     for (;;) {
         const uint4 e0 = __ldg(p.anchors + 2 * (size_t)slot);             /* both halves of the 32-byte slot at once */
         const uint4 e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
@@ -261,9 +268,13 @@ __device__ __forceinline__ void resolve(const ScanParams &p, const WarpStage &ws
             const long long start = q - j;
             if (start >= hs) {
                 if (kid >= 0) {                                /* UNIQUE: the only key that can match at start */
-                    if (start + len <= he && text_equals(p, start, len, kw))
-                        emit(p, ws, (int32_t)h, (int32_t)(((start + len - hs) >> p.letter_shift) - 1), kid);
-                } else if (q + len <= he && text_equals(p, q, len, kw)) {   /* MULTI: exact gram, then the trie */
+                    bool eq = false;
+                    if (start + len <= he) {
+                        if (j == 0) eq = text_equals(tq, q, len, kw);
+                        else { uint32_t ts[6]; load_text(p, start, ts); eq = text_equals(ts, start, len, kw); }
+                    }
+                    if (eq) emit(p, ws, (int32_t)h, (int32_t)(((start + len - hs) >> p.letter_shift) - 1), kid);
+                } else if (q + len <= he && text_equals(tq, q, len, kw)) {   /* MULTI: exact gram, then the trie */
                     walk_from(p, ws, start, h, hs, he);
                 }
             }
