@@ -457,6 +457,51 @@ class Automaton:
                 N.check(self._lib.acb_copy_records(tb, N.ptr(out), found.value))
             return out
 
+    def _scan_device_tensor(self, t, algo: str, sort: bool) -> np.ndarray:
+        """Batch already resident in HBM: a C-contiguous uint8 torch CUDA tensor [n, stride].  No host copy of
+        the haystacks; the scan runs on torch's current stream, only the records come back."""
+        import torch
+        if t.dtype != torch.uint8 or t.dim() != 2 or not t.is_contiguous():
+            raise TypeError("device batches must be 2-D contiguous uint8 tensors [n_haystacks, stride_bytes]")
+        n, stride = int(t.shape[0]), int(t.shape[1])
+        if stride % self._L:
+            raise ValueError("row length must be a multiple of the letter width")
+        if n == 0 or stride == 0:
+            return np.empty(0, dtype=N.MATCH_DTYPE)
+        dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+        tb = self._ensure_table(dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            cnt = torch.zeros(1, dtype=torch.int64, device=t.device)
+            cap = max(self._match_cap, 1 << 12, 2 * n)
+            while True:
+                out = torch.empty((cap, 3), dtype=torch.int32, device=t.device)
+                cnt.zero_()
+                N.check(self._lib.acb_scan_device(tb, t.data_ptr(), n * stride, None, n, stride, out.data_ptr(), cap,
+                                                  cnt.data_ptr(), stream, N.ALGOS[algo]))
+                found = int(cnt.item())
+                if found == -1:                                   # internal candidate list overflowed: worst-case size, again
+                    N.check(self._lib.acb_table_reserve_candidates(tb, 1))
+                    continue
+                if found > cap:
+                    cap = self._match_cap = found + 1024
+                    continue
+                break
+            if sort and found > 1:
+                rc = self._lib.acb_sort_matches_device(tb, out.data_ptr(), found, n, stride // self._L, stream)
+                if rc == N.ACB_ERANGE:
+                    sort_on_host = True
+                else:
+                    N.check(rc)
+                    sort_on_host = False
+            else:
+                sort_on_host = False
+            rec = out[:found].cpu().numpy().view(N.MATCH_DTYPE).reshape(-1)
+        if sort_on_host:
+            kl = np.asarray(self.flat()["key_len"])
+            rec = rec[np.lexsort((-kl[rec["key_id"]], rec["end_index"], rec["hay_id"]))]
+        return rec
+
     def _scan_one(self, letters: np.ndarray, algo: str = "auto") -> np.ndarray:
         flat = np.ascontiguousarray(letters).view(np.uint8)
         if flat.size == 0:
@@ -554,13 +599,16 @@ class Automaton:
 
         haystacks: a sequence of bytes / str / tuple objects (as `iter` accepts), or a 2-D
         C-contiguous uint8 array [n, stride] (bytes flavour: one haystack per row), or a pair
-        (flat uint8 array, int64 byte offsets of length n+1).
+        (flat uint8 array, int64 byte offsets of length n+1), or a 2-D contiguous uint8 torch CUDA
+        tensor [n, stride] that already lives in HBM (no host copy of the batch).
 
         Equivalent to ``[(h, e, v) for h, hay in enumerate(haystacks) for e, v in A.iter(hay)]``
         of the reference, returned as arrays.
         """
         self._require_automaton()
         L = self._L
+        if type(haystacks).__module__.startswith("torch") and getattr(haystacks, "is_cuda", False):
+            return Matches(self._scan_device_tensor(haystacks, algo, sort), self._values)
         if isinstance(haystacks, np.ndarray):
             if haystacks.dtype != np.uint8 or haystacks.ndim != 2 or not haystacks.flags.c_contiguous:
                 raise TypeError("array batches must be 2-D C-contiguous uint8 [n_haystacks, stride_bytes]")

@@ -220,6 +220,34 @@ def test_c5_100k_keys_properties():
     _check_full(w, A)
 
 
+def test_dense_matches_grow_the_buffers():
+    """a key set that matches at every position: the match buffer overflows and is regrown, the internal
+    candidate list falls back to its worst-case size; results still equal the oracle's."""
+    keys = [b"a", b"aa", b"ab"]
+    A = synth.build_automaton(keys)
+    O = _oracle_for(keys)
+    hay = np.full((64, 4096), ord("a"), dtype=np.uint8)
+    hay[:, ::97] = ord("b")
+    off = np.arange(65, dtype=np.int64) * 4096
+    want = _want_sorted(O, keys, hay.reshape(-1), off)
+    assert len(want) > 2 * hay.size * 0.9
+    for algo in ("filter", "dfa"):
+        assert _records(A.find_all_batch(hay, algo=algo)) == want
+    import torch
+    assert _records(A.find_all_batch(torch.from_numpy(hay).cuda())) == want       # device-resident entry, same growth path
+
+
+def test_torch_cuda_tensor_batches():
+    import torch
+    w = synth.make("C2", scale=0.01)
+    A = synth.build_automaton(w.keys)
+    want = _records(A.find_all_batch(w.haystacks))
+    d = torch.from_numpy(w.haystacks).cuda()
+    for algo in ("filter", "dfa"):
+        assert _records(A.find_all_batch(d, algo=algo)) == want
+    assert sorted(_records(A.find_all_batch(d, sort=False))) == sorted(want)
+
+
 def test_device_resident_entry_and_overflow_retry():
     import ctypes
     import torch
