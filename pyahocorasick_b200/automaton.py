@@ -123,6 +123,12 @@ class Automaton:
         self._version = 0
         self._table = None                # acb_table* (device), created lazily
         self._table_device = None
+        # unicode flavour only: a second, 1-byte-per-letter automaton over the keys that are pure latin-1,
+        # built lazily and used whenever a haystack is latin-1 too (4x fewer bytes to move and scan)
+        self._narrow_trie = None
+        self._narrow_table = None
+        self._narrow_device = None
+        self._narrow_empty = False
         self._match_cap = 0
 
     @staticmethod
@@ -150,6 +156,15 @@ class Automaton:
             pass
 
     # ------------------------------------------------------------------ marshalling (src/utils.c:145-289)
+    def _hay_letters(self, obj, required: bool = False) -> np.ndarray:
+        """haystack -> letters; latin-1 `str` haystacks of the unicode flavour come back as uint8 (narrow path)."""
+        if self._uses_narrow() and isinstance(obj, str):
+            try:
+                return np.frombuffer(obj.encode("latin-1"), dtype=np.uint8)
+            except UnicodeEncodeError:
+                pass
+        return self._letters(obj, required)
+
     def _letters(self, obj, required: bool = False) -> np.ndarray:
         """key / haystack object -> array of letters (dtype by letter width)."""
         if self._key_type == KEY_SEQUENCE:
@@ -400,6 +415,59 @@ class Automaton:
         if self._table is not None:
             self._lib.acb_table_free(self._table)
             self._table = None
+        if self._narrow_table is not None:
+            self._lib.acb_table_free(self._narrow_table)
+            self._narrow_table = None
+        if self._narrow_trie is not None:
+            self._lib.acb_trie_free(self._narrow_trie)
+            self._narrow_trie = None
+        self._narrow_empty = False
+
+    def _uses_narrow(self) -> bool:
+        return self._UNICODE and self._key_type == KEY_STRING
+
+    def _narrow_host(self):
+        """host trie of the latin-1 automaton (built lazily), or None when no key is pure latin-1."""
+        if self._narrow_empty:
+            return None
+        if self._narrow_trie is None:
+            t = self._lib.acb_trie_new(1)
+            if not t:
+                raise MemoryError(N.last_error())
+            n = 0
+            for kid, key in enumerate(self._key_objs):
+                if key is None:
+                    continue
+                try:
+                    raw = key.encode("latin-1")
+                except UnicodeEncodeError:
+                    continue                                    # cannot occur in a latin-1 haystack
+                N.check(self._lib.acb_trie_add_word(t, raw, len(raw), kid, None))
+                n += 1
+            if n == 0:
+                self._lib.acb_trie_free(t)
+                self._narrow_empty = True
+                return None
+            built = ctypes.c_int32(0)
+            N.check(self._lib.acb_trie_make_automaton(t, ctypes.byref(built)))
+            self._narrow_trie = t
+        return self._narrow_trie
+
+    def _ensure_narrow(self, device: Optional[int]):
+        """(trie, table) of the latin-1 automaton, or None when no key is pure latin-1."""
+        if self._narrow_host() is None:
+            return None
+        if device is None:
+            device = _default_device()
+        if self._narrow_table is None or self._narrow_device != device:
+            if self._narrow_table is not None:
+                self._lib.acb_table_free(self._narrow_table)
+                self._narrow_table = None
+            tb = ctypes.c_void_p()
+            N.check(self._lib.acb_table_upload(self._narrow_trie, device, ctypes.byref(tb)))
+            self._narrow_table = tb
+            self._narrow_device = device
+        return self._narrow_trie, self._narrow_table
 
     def _ensure_table(self, device: Optional[int] = None):
         if device is None:
@@ -413,10 +481,16 @@ class Automaton:
         self._table_device = device
         return tb
 
-    def flat(self) -> dict:
-        """White-box view of the flattened automaton (numpy copies) -- used by tests and docs."""
+    def flat(self, narrow: bool = False) -> dict:
+        """White-box view of the flattened automaton (numpy copies) -- used by tests and docs.
+        narrow=True: the latin-1 automaton of a unicode-flavour Automaton (None if it has no latin-1 key)."""
         fv = N.FlatView()
-        N.check(self._lib.acb_trie_flat_view(self._trie, ctypes.byref(fv)))
+        trie = self._trie
+        if narrow:
+            trie = self._narrow_host()
+            if trie is None:
+                return None
+        N.check(self._lib.acb_trie_flat_view(trie, ctypes.byref(fv)))
         S, K = fv.n_states, fv.n_classes
 
         def arr(p, n, dt):
@@ -437,9 +511,16 @@ class Automaton:
 
     # ------------------------------------------------------------------ GPU scan plumbing
     def _scan_flat(self, flat: np.ndarray, offsets: Optional[np.ndarray], n_hay: int, stride_bytes: int,
-                   algo: str = "auto", sort: bool = True, device: Optional[int] = None) -> np.ndarray:
-        """flat uint8 buffer (+ int64 byte offsets or a fixed stride) -> sorted match records."""
-        tb = self._ensure_table(device)
+                   algo: str = "auto", sort: bool = True, device: Optional[int] = None, narrow: bool = False) -> np.ndarray:
+        """flat uint8 buffer (+ int64 byte offsets or a fixed stride) -> sorted match records.
+        narrow=True: the buffer holds 1-byte letters of a unicode-flavour automaton (latin-1 path)."""
+        if narrow:
+            core = self._ensure_narrow(device)
+            if core is None:
+                return np.empty(0, dtype=N.MATCH_DTYPE)
+            tb = core[1]
+        else:
+            tb = self._ensure_table(device)
         total = int(flat.size)
         cap = max(self._match_cap, 1 << 12, 2 * n_hay)        # device-side capacity; grown on overflow
         found = ctypes.c_int64(0)
@@ -503,9 +584,12 @@ class Automaton:
         return rec
 
     def _scan_one(self, letters: np.ndarray, algo: str = "auto") -> np.ndarray:
+        narrow = self._uses_narrow() and letters.dtype == np.uint8
         flat = np.ascontiguousarray(letters).view(np.uint8)
         if flat.size == 0:
             return np.empty(0, dtype=N.MATCH_DTYPE)
+        if narrow:
+            return self._scan_flat(flat, None, 1, int(flat.size), algo=algo, narrow=True)
         return self._scan_flat(flat, None, 1, int(flat.size), algo=algo)
 
     def _require_automaton(self):
@@ -532,7 +616,7 @@ class Automaton:
         start = _parse_c_int(vals.get("start", -1))
         end = _parse_c_int(vals.get("end", -1))
         iws = _parse_c_int(vals.get("ignore_white_space", -1)) == 1          # :897-899 (A6)
-        letters = self._letters(vals["string"], required=True)
+        letters = self._hay_letters(vals["string"], required=True)
         n = len(letters)
         if start == -1:
             start = 0                                                         # -1 = "not given" (A2)
@@ -550,7 +634,7 @@ class Automaton:
             return None                                                        # :666-667 (A4)
         if len(args) < 1:
             raise IndexError("tuple index out of range")
-        letters = self._letters(args[0])
+        letters = self._hay_letters(args[0])
         if len(args) < 2:
             raise IndexError("tuple index out of range")
         callback = args[1]
@@ -571,7 +655,7 @@ class Automaton:
             raise AttributeError("not an automaton yet; add some words and call make_automaton")
         if len(args) < 1:
             raise IndexError("tuple index out of range")
-        letters = self._letters(args[0], required=True)
+        letters = self._hay_letters(args[0], required=True)
         start, end = _parse_start_end(args, 1, 2, 0, len(letters))
         return AutomatonSearchIterLong(self, letters, start, end)
 
@@ -625,14 +709,21 @@ class Automaton:
             n = len(offs) - 1
             rec = self._scan_flat(flat, offs, n, 0, algo=algo, sort=sort, device=device) if n and flat.size else np.empty(0, dtype=N.MATCH_DTYPE)
             return Matches(rec, self._values)
-        parts = [np.ascontiguousarray(self._letters(h, required=True)).view(np.uint8) for h in haystacks]
+        letters = [self._hay_letters(h, required=True) for h in haystacks]
+        narrow = self._uses_narrow() and len(letters) > 0 and all(a.dtype == np.uint8 for a in letters)
+        if self._uses_narrow() and not narrow:                   # mixed batch: everything at 4 bytes per letter
+            letters = [a.astype("<u4") if a.dtype == np.uint8 else a for a in letters]
+        parts = [np.ascontiguousarray(a).view(np.uint8) for a in letters]
         n = len(parts)
         lens = np.fromiter((p.size for p in parts), dtype=np.int64, count=n)
         offs = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(lens, out=offs[1:])
         flat = np.concatenate(parts) if n else np.empty(0, dtype=np.uint8)
-        rec = self._scan_flat(flat, offs, n, 0, algo=algo, sort=sort, device=device) if n and flat.size else np.empty(0, dtype=N.MATCH_DTYPE)
-        return Matches(rec, self._values)
+        if not (n and flat.size):
+            return Matches(np.empty(0, dtype=N.MATCH_DTYPE), self._values)
+        if narrow:
+            return Matches(self._scan_flat(flat, offs, n, 0, algo=algo, sort=sort, device=device, narrow=True), self._values)
+        return Matches(self._scan_flat(flat, offs, n, 0, algo=algo, sort=sort, device=device), self._values)
 
 
 class AutomatonSearchIter:
@@ -660,6 +751,10 @@ class AutomatonSearchIter:
         else:
             pos = None
         nh = len(self._hist)
+        if nh and self._hist.dtype != seg.dtype:                    # a narrow (latin-1) chunk after a wide one or vice versa
+            wide = np.dtype("<u4")
+            self._hist = self._hist.astype(wide)
+            seg = seg.astype(wide)
         data = np.concatenate([self._hist, seg]) if nh else seg
         rec = A._scan_one(data) if len(data) else np.empty(0, dtype=N.MATCH_DTYPE)
         ends = rec["end_index"]
@@ -697,7 +792,7 @@ class AutomatonSearchIter:
         if not args:
             raise IndexError("tuple index out of range")
         A = self._A
-        letters = A._letters(args[0])
+        letters = A._hay_letters(args[0])
         reset = bool(args[1]) if len(args) > 1 else False
         if reset:
             self._hist = letters[:0]
@@ -711,7 +806,12 @@ class AutomatonSearchIter:
             else:
                 ncons = min(max(consumed_upto - self._start + 1, 0), len(self._seg))
             keep = max(int(A._lib.acb_trie_longest_word(A._trie)) - 1, 0)
-            hist = np.concatenate([self._hist, self._seg[:ncons]])
+            old = self._seg[:ncons]
+            if len(self._hist) and self._hist.dtype != old.dtype:
+                old = old.astype(self._hist.dtype) if self._hist.dtype.itemsize > old.dtype.itemsize else old
+                if self._hist.dtype != old.dtype:
+                    self._hist = self._hist.astype(old.dtype)
+            hist = np.concatenate([self._hist, old])
             self._hist = hist[len(hist) - keep:] if keep else hist[:0]
             # outputs of the current position not yet returned stay pending (iter->output survives set())
             if not self._pending:

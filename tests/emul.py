@@ -231,8 +231,10 @@ def install(monkeypatch_or_none, algo="filter"):
 
     default_algo = algo
 
-    def fake_scan_flat(self, flat, offsets, n_hay, stride_bytes, algo="auto", sort=True, device=None):
-        f = self.flat()
+    def fake_scan_flat(self, flat, offsets, n_hay, stride_bytes, algo="auto", sort=True, device=None, narrow=False):
+        f = self.flat(narrow=narrow)
+        if f is None:
+            return np.empty(0, dtype=N.MATCH_DTYPE)
         if algo == "auto":
             algo = default_algo
         fn = {"dfa": emul_dfa, "long": emul_long}.get(algo, emul_filter)

@@ -20,3 +20,40 @@ def test_golden_via_emulated_device(sc, algo, monkeypatch):
     emul.install(monkeypatch, algo)
     bad = run_ops(ac.flavour(sc["flavour"]), sc, record=False)
     assert not bad, bad[:3]
+
+
+def test_unicode_narrow_and_wide_paths_agree_with_oracle(monkeypatch):
+    """unicode flavour: latin-1 haystacks take the 1-byte-per-letter automaton, others the 4-byte one;
+    streams may switch between the two from chunk to chunk."""
+    import oracle
+    emul.install(monkeypatch, "filter")
+    U = ac.flavour("unicode")
+    words = ["he", "hers", "é", "éa", "中文", "a中", "he\U0001F629"]
+    A = U.Automaton()
+    O = oracle.OracleAutomaton()
+    for i, w in enumerate(words):
+        A.add_word(w, i)
+        O.add_word(w, i)
+    A.make_automaton()
+    O.make_automaton()
+    texts = ["hers é éa he", "xx中文a中 hers", "he\U0001F629é", "", "plain ascii hers"]
+    for t in texts:
+        assert list(A.iter(t)) == O.find_all(t)
+        assert list(A.iter_long(t)) == O.iter_long(t)
+    m = A.find_all_batch(texts)                       # mixed batch -> all wide
+    assert m.per_haystack(len(texts)) == [O.find_all(t) for t in texts]
+    m = A.find_all_batch([texts[0], texts[4]])        # all latin-1 -> narrow
+    assert m.per_haystack(2) == [O.find_all(texts[0]), O.find_all(texts[4])]
+    # a stream that alternates narrow and wide chunks, with keys straddling the boundaries
+    chunks = ["..h", "ers a", "中", "文 é", "a h", "e\U0001F629"]
+    it = A.iter("")
+    got = []
+    for c in chunks:
+        it.set(c)
+        got += list(it)
+    assert got == O.find_all("".join(chunks))
+    # only non-latin keys: the narrow automaton does not exist
+    B = U.Automaton()
+    B.add_word("中文", 1)
+    B.make_automaton()
+    assert list(B.iter("latin only")) == [] and list(B.iter("x中文")) == [(2, 1)]
