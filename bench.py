@@ -74,7 +74,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -312,6 +312,13 @@ def main():
                "includes": "H2D of the batch from pinned host memory, kernel, D2H of count+records, reference-order sort"}
         assert len(m) == n_matches, (len(m), n_matches)
 
+    # clocks under load: the timed region is only a few ms long, so keep the same step running for another
+    # ~0.5 s (untimed) while nvidia-smi samples SM clock and throttle reasons every 50 ms
+    t_end = time.perf_counter() + 0.5
+    while time.perf_counter() < t_end:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel ------------------------------------------------------

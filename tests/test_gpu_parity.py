@@ -248,6 +248,35 @@ def test_torch_cuda_tensor_batches():
     assert sorted(_records(A.find_all_batch(d, sort=False))) == sorted(want)
 
 
+def test_batch_larger_than_one_segment():
+    """> 2 GiB in one call: the filter path scans it in 2 GiB segments (32-bit candidate offsets); a key planted
+    across the segment boundary (inside one haystack) must be found, and both kernels must agree."""
+    rng = np.random.Generator(np.random.PCG64(31))
+    keys = synth.draw_keys(rng, synth.ALNUM, 2000, 4, 16)
+    stride, n = 250, 9_000_000                                   # 2.25e9 bytes > 2^31
+    hay = synth.random_haystacks(rng, synth.ALNUM, n, stride)
+    rows = np.arange(0, n, 7)
+    ph, pe, pk = synth.plant(rng, hay, keys, rows)
+    flat = hay.reshape(-1)
+    b = 1 << 31                                                  # straddle the segment boundary
+    k = np.frombuffer(keys[5], dtype=np.uint8)
+    st = b - len(k) // 2
+    assert st // stride == (st + len(k) - 1) // stride           # stays inside one haystack
+    flat[st:st + len(k)] = k
+    w = synth.Workload("seg", keys, hay, np.append(ph, st // stride), np.append(pe, st % stride + len(k) - 1), np.append(pk, 5))
+    # earlier plants in that haystack may have been overwritten: keep only plants whose bytes survived
+    klen = np.fromiter((len(x) for x in keys), dtype=np.int64, count=len(keys))
+    starts = w.planted_hay * stride + w.planted_end - klen[w.planted_key] + 1
+    ok = np.ones(len(starts), dtype=bool)
+    hit = np.nonzero(w.planted_hay == st // stride)[0]
+    for i in hit.tolist():
+        kk = np.frombuffer(keys[int(w.planted_key[i])], dtype=np.uint8)
+        ok[i] = np.array_equal(flat[starts[i]:starts[i] + len(kk)], kk)
+    w.planted_hay, w.planted_end, w.planted_key = w.planted_hay[ok], w.planted_end[ok], w.planted_key[ok]
+    A = synth.build_automaton(keys)
+    _check_full(w, A, sample=5000)
+
+
 def test_device_resident_entry_and_overflow_retry():
     import ctypes
     import torch
