@@ -135,3 +135,20 @@ def test_state_machine_and_removal():
         B.Automaton(-42)
     with pytest.raises(ValueError):
         B.Automaton(ac.STORE_ANY, -42)
+
+
+def test_pickle_round_trip_keeps_keys_values_and_kind():
+    import pickle
+    for mod, conv in ((B, lambda s: s.encode()), (ac.flavour("unicode"), lambda s: s)):
+        A = mod.Automaton()
+        for i, w in enumerate(["he", "her", "hers", "she"]):
+            A.add_word(conv(w), (i, w))
+        A.make_automaton()
+        C = pickle.loads(pickle.dumps(A))
+        assert type(C) is type(A) and C.kind == ac.AHOCORASICK and len(C) == 4
+        assert sorted(C.items(), key=repr) == sorted(A.items(), key=repr)
+        assert C.flat()["fail"].tolist() == A.flat()["fail"].tolist()
+        T = mod.Automaton(ac.STORE_LENGTH)
+        T.add_word(conv("abc"))
+        D = pickle.loads(pickle.dumps(T))
+        assert D.kind == ac.TRIE and D.get(conv("abc")) == 3 and D.store == ac.STORE_LENGTH
