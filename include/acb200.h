@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ACB_ABI_VERSION 1
+#define ACB_ABI_VERSION 2
 
 enum {
     ACB_OK        =  0,
@@ -120,11 +120,17 @@ typedef struct acb_flat_view {
     int32_t        log2_bits2;    /* n - 3: the stage-2 bitmap has 2^(n-3) bits               */
     int32_t        log2_bits3;    /* stage-3 bitmap (global memory) has 2^k bits; 0 = stage 3 unused */
     int32_t        log2_anchor_slots; /* anchor table has 2^n slots of 8 uint32 (32 B)        */
-    const uint32_t *bitmap1;      /* 7<<(n-8) words: word = umulhi(hash1, 7<<(n-8)); a gram sets bits (hash1>>(32-n))&31 and hash1&31 */
+    const uint32_t *bitmap1;      /* 7<<(n-8) words: word = umulhi(hash1, 7<<(n-8)); a gram sets two bits of it (csrc/acb_hash.h) */
     const uint32_t *bitmap2;      /* 1<<(n-8) words: word = hash2>>(40-n),          bit = (hash2>>(35-n))&31 */
     const uint32_t *bitmap3;      /* 1<<(k-5) words: bit = (hash2|1) * 0x9E3779B1 >> (32-k); large key sets only */
     const uint32_t *anchors;      /* slot: tag(hash2|1, 0=empty), key_id(-1=MULTI), j|len<<8|last<<16, 20 bytes */
+    int32_t        filter_flags;  /* ACB_FILTER_* : how stage 1 places a gram (csrc/acb_hash.h)            */
 } acb_flat_view;
+
+/* filter_flags */
+#define ACB_FILTER_WIDE 1   /* g % 4 == 0: the first stage-1 bit comes from the high half of the 64-bit hash sum  */
+#define ACB_FILTER_PAIR 2   /* g = 4, s = 1: probes x (even) and x+1 share ONE word, chosen by the three bytes they
+                               have in common; every gram is entered twice, once for each role                   */
 
 int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out);
 

@@ -31,6 +31,7 @@ class FlatView(ctypes.Structure):
         ("log2_anchor_slots", ctypes.c_int32),
         ("bitmap1", ctypes.POINTER(ctypes.c_uint32)), ("bitmap2", ctypes.POINTER(ctypes.c_uint32)),
         ("bitmap3", ctypes.POINTER(ctypes.c_uint32)), ("anchors", ctypes.POINTER(ctypes.c_uint32)),
+        ("filter_flags", ctypes.c_int32),
     ]
 
 

@@ -115,6 +115,7 @@ struct ScanParams {
     int letter_shift;              /* log2(L) */
     unsigned long long *timeline;  /* debug (ACB_TIMELINE=1): 6 globaltimer stamps per warp, else nullptr */
     int inline_resolve;            /* 1: warps resolve their own candidates between work units; 0: all go to the list */
+    int filter_flags;              /* ACB_FILTER_* of the table */
 };
 
 /* ---------------------------------------------------------------- helpers */
@@ -240,6 +241,12 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define ACB_STAMP(i) do { if (p.timeline && lane == 0) p.timeline[((size_t)blockIdx.x * kWarps + warp) * 6 + (i)] = gtime(); } while (0)
 
+__device__ __forceinline__ unsigned long long mad_wide(uint32_t a, uint32_t b, unsigned long long c) {
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t lds_word(uint32_t saddr) {
     uint32_t v;
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
@@ -315,6 +322,7 @@ struct FilterCtx {
     uint32_t sbm2;             /* shared-memory address of the stage-2 bitmap (last 1/8) */
     int sh_word2, sh_bit2;     /* tag >> sh_word2 = stage-2 word index, tag >> sh_bit2 = its bit index */
     uint32_t four;             /* == 4, opaque to the compiler so the address is one IMAD (FMA pipe) */
+    uint32_t two;              /* == 2, same trick for the hit accumulator */
     int sh_bit;                /* h >> sh_bit: bit index (low 5 bits, wrap shift) */
     uint32_t lt_mask;
     int lane;
@@ -367,7 +375,7 @@ __device__ __forceinline__ uint32_t sel8(const uint32_t (&W)[N], int off, int g)
     return (g & 4) ? b1 : b0;
 }
 
-template <int NW, int STRIDE, bool GUARD>
+template <int NW, int STRIDE, bool WIDE, bool PAIR, bool GUARD>
 __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (&mul)[NW], const uint32_t (&mul2)[NW],
                                             uint32_t rel0, int &qhead, int &qtail) {
     constexpr int kProbes = kFChunk / STRIDE;
@@ -399,23 +407,52 @@ __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (
                 W[8 + k] = (lane == 31) ? b : a;
             }
         }
-        /* one bitmap probe per position; hit bits are shifted into `acc` from the top */
+        /* One bitmap probe per position.  The hit bit is shifted into `acc` with a multiply-add (FMA pipe, which
+           has room; c.two == 2 is opaque to the compiler), so probe i ends up in bit kProbes-1-i.  Blocked Bloom,
+           k = 2: both bits of the gram must be set in its word (wrap shifts use the low 5 bits of the hash). */
         uint32_t acc = 0;
+        if (PAIR) {                                  /* NW == 1, STRIDE == 1, WIDE: probes t, t+1 share one word */
 #pragma unroll
-        for (int t = 0; t < kFChunk; t += STRIDE) {
-            uint32_t h = 0;
-#pragma unroll
-            for (int k = 0; k < NW; k++) {
-                const int wi = (t >> 2) + k;
-                uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
-                h += w * mul[k];
+            for (int t = 0; t < kFChunk; t += 2) {
+                const uint32_t w0 = ((t & 3) == 0) ? W[t >> 2] : __funnelshift_r(W[t >> 2], W[(t >> 2) + 1], (t & 3) * 8);
+                const uint32_t w1 = __funnelshift_r(W[(t + 1) >> 2], W[((t + 1) >> 2) + 1], ((t + 1) & 3) * 8);
+                const unsigned long long h0 = mad_wide(w0, mul[0], 0ULL), h1 = mad_wide(w1, mul[0], 0ULL);
+                /* the word is chosen by the three bytes the two grams share (acb_hash.h) */
+                const uint32_t word = lds_word(__umulhi(w1 * ACB_PAIR_MUL, c.mul_word) * c.four + c.sbm);
+                const uint32_t b0 = __funnelshift_r(word, 0u, (uint32_t)(h0 >> 32)) & __funnelshift_r(word, 0u, (uint32_t)h0) & 1u;
+                acc = acc * c.two + b0;
+                const uint32_t b1 = __funnelshift_r(word, 0u, (uint32_t)(h1 >> 32)) & __funnelshift_r(word, 0u, (uint32_t)h1) & 1u;
+                acc = acc * c.two + b1;
             }
-            const uint32_t word = lds_word(__umulhi(h, c.mul_word) * c.four + c.sbm);
-            /* blocked Bloom, k = 2: both bits of the gram must be set in this word (wrap shifts use 5 bits) */
-            const uint32_t both = __funnelshift_r(word, 0u, h >> c.sh_bit) & __funnelshift_r(word, 0u, h);
-            acc = __funnelshift_r(acc, both, 1);                                   /* (acc >> 1) | (bit 0 of both << 31) */
+        } else {
+#pragma unroll
+            for (int t = 0; t < kFChunk; t += STRIDE) {
+                uint32_t h = 0, ha;
+                if (WIDE) {                          /* 64-bit products: low half = hash1, high half -> first bit */
+                    unsigned long long hw = 0;
+#pragma unroll
+                    for (int k = 0; k < NW; k++) {
+                        const int wi = (t >> 2) + k;
+                        const uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
+                        hw = mad_wide(w, mul[k], hw);
+                    }
+                    h = (uint32_t)hw;
+                    ha = (uint32_t)(hw >> 32);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NW; k++) {
+                        const int wi = (t >> 2) + k;
+                        const uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
+                        h += w * mul[k];
+                    }
+                    ha = h >> c.sh_bit;
+                }
+                const uint32_t word = lds_word(__umulhi(h, c.mul_word) * c.four + c.sbm);
+                const uint32_t both = __funnelshift_r(word, 0u, ha) & __funnelshift_r(word, 0u, h) & 1u;
+                acc = acc * c.two + both;
+            }
         }
-        uint32_t hits = (kProbes == 32) ? acc : (acc >> (32 - kProbes));           /* bit i = probe i */
+        uint32_t hits = __brev(acc) >> (32 - kProbes);                             /* bit i = probe i */
         if (GUARD && pos0 + kFChunk > c.seg_len) {                                 /* probes that start past the segment */
             const int valid = (pos0 >= c.seg_len) ? 0 : ((int)(c.seg_len - pos0) + STRIDE - 1) / STRIDE;
             hits = (valid <= 0) ? 0u : ((valid >= 32) ? hits : (hits & ((1u << valid) - 1u)));
@@ -467,7 +504,7 @@ __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (
     }
 }
 
-template <int NW, int STRIDE>
+template <int NW, int STRIDE, bool WIDE, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int nwords = 1 << (p.log1 - 5);
@@ -510,6 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
     c.sh_word2 = 40 - p.log1;
     c.sh_bit2 = 35 - p.log1;
     c.four = 4u + (uint32_t)(p.log1 >> 8);                               /* always 4 */
+    c.two = 2u + (uint32_t)(p.log1 >> 8);                                /* always 2 */
     c.sh_bit = 32 - p.log1;
     c.lt_mask = (1u << lane) - 1u;
     c.lane = lane;
@@ -534,8 +572,8 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
         if ((long long)blk >= p.n_blocks) break;
         if (first_unit) { ACB_STAMP(2); first_unit = false; }
         const uint32_t rel0 = blk * (uint32_t)kBlockBytes;
-        if ((long long)blk < n_interior) filter_unit<NW, STRIDE, false>(c, mul, mul2, rel0, qhead, qtail);
-        else filter_unit<NW, STRIDE, true>(c, mul, mul2, rel0, qhead, qtail);
+        if ((long long)blk < n_interior) filter_unit<NW, STRIDE, WIDE, PAIR, false>(c, mul, mul2, rel0, qhead, qtail);
+        else filter_unit<NW, STRIDE, WIDE, PAIR, true>(c, mul, mul2, rel0, qhead, qtail);
         if (qtail - qhead >= 32) {
             if (p.inline_resolve) drain_queue(p, wr, qhead, qtail, false, lane);
             else spill_queue(c, qhead, qtail, false);
@@ -713,7 +751,7 @@ __global__ void __launch_bounds__(kDfaThreads) acb_long_kernel(const __grid_cons
 struct acb_table {
     int device = 0;
     int sm_count = 0;
-    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log2 = 15, log3 = 0, logA = 10;
+    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log2 = 15, log3 = 0, logA = 10, filter_flags = 0;
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     uint8_t *d_cls = nullptr;
@@ -793,7 +831,7 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { acb_set_error("cudaGetDeviceProperties failed"); rc = ACB_ECUDA; break; }
         tb->sm_count = prop.multiProcessorCount;
         tb->S = f.n_states; tb->K = f.n_classes; tb->L = f.letter_bytes; tb->n_keys = f.n_keys;
-        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log2 = f.log2_bits2; tb->log3 = f.log2_bits3; tb->logA = f.log2_anchor_slots;
+        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log2 = f.log2_bits2; tb->log3 = f.log2_bits3; tb->logA = f.log2_anchor_slots; tb->filter_flags = f.filter_flags;
         tb->min_key_bytes = f.min_key_bytes; tb->max_key_bytes = f.max_key_bytes;
         acb_hash_multipliers(tb->gram, 1, tb->mul1);
         acb_hash_multipliers(tb->gram, 2, tb->mul2);
@@ -843,15 +881,27 @@ static size_t filter_smem_bytes(int log1) {
            (size_t)kWarps * kStageCap * sizeof(acb_match) + (size_t)kWarps * sizeof(int);
 }
 
-template <int NW, int STRIDE>
-static int launch_filter_t(const ScanParams &p, int grid, cudaStream_t s) {
-    auto kern = acb_filter_kernel<NW, STRIDE>;
+template <int NW, int STRIDE, bool WIDE, bool PAIR>
+static int launch_filter_w(const ScanParams &p, int grid, cudaStream_t s) {
+    auto kern = acb_filter_kernel<NW, STRIDE, WIDE, PAIR>;
     const size_t smem = filter_smem_bytes(p.log1);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     return ACB_OK;
+}
+
+/* WIDE follows from the gram length (acb_hash_is_wide); PAIR exists for one shape only: g = 4, s = 1 */
+template <int NW, int STRIDE>
+static int launch_filter_t(const ScanParams &p, int grid, cudaStream_t s) {
+    if (p.filter_flags & ACB_FILTER_PAIR) {
+        if (NW == 1 && STRIDE == 1 && p.gram == 4) return launch_filter_w<1, 1, true, true>(p, grid, s);
+        acb_set_error("PAIR filter needs gram 4, stride 1 (got gram %d)", p.gram);
+        return ACB_EINVAL;
+    }
+    if (p.gram == 4 * NW) return launch_filter_w<NW, STRIDE, true, false>(p, grid, s);
+    return launch_filter_w<NW, STRIDE, false, false>(p, grid, s);
 }
 
 template <int NW>
@@ -913,7 +963,7 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     p.n_hay = n_hay; p.stride_bytes = stride_bytes;
     p.cls = tb->d_cls; p.gto = tb->d_goto; p.fail = tb->d_fail; p.letter_fail = tb->d_lfail; p.key_of = tb->d_keyof;
     p.out_ptr = tb->d_outptr; p.out_idx = tb->d_outidx; p.key_len = tb->d_keylen;
-    p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.max_key_bytes = tb->max_key_bytes;
+    p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.filter_flags = tb->filter_flags; p.max_key_bytes = tb->max_key_bytes;
     p.bm1 = tb->d_bm1; p.bm2 = tb->d_bm2; p.bm3 = tb->d_bm3; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
     p.log1 = tb->log1; p.log2 = tb->log2; p.log3 = tb->log3; p.logA = tb->logA;
     memcpy(p.mul1, tb->mul1, sizeof(p.mul1));

@@ -77,4 +77,39 @@ ACB_HD uint32_t acb_hash_bytes(const uint8_t *p, int g, const uint32_t mul[ACB_M
     return h;
 }
 
+/* The same sum with 64-bit products (its low half IS acb_hash_bytes): when the gram fills its windows exactly
+ * (g % 4 == 0, no byte is cancelled through a shifted multiplier) the high half is a second, well mixed hash that
+ * costs the probe loop nothing -- mad.wide.u32 instead of mad.lo.u32 -- and supplies the first Bloom bit. */
+ACB_HD uint64_t acb_hash_bytes_wide(const uint8_t *p, int g, const uint32_t mul[ACB_MAX_WINDOWS]) {
+    uint64_t h = 0;
+    int nw = (g + 3) / 4;
+    for (int k = 0; k < nw; k++) {
+        uint32_t w = 0;
+        for (int b = 0; b < 4; b++) {
+            int i = 4 * k + b;
+            if (i < g) w |= (uint32_t)p[i] << (8 * b);
+        }
+        h += (uint64_t)w * mul[k];
+    }
+    return h;
+}
+
+/* does the stage-1 filter of a gram of g bytes take its first Bloom bit from the high half? */
+ACB_HD int acb_hash_is_wide(int g) { return (g % 4) == 0; }
+
+/* the two bit positions (0..31) of a gram inside its stage-1 word; hw = acb_hash_bytes_wide() */
+ACB_HD uint32_t acb_stage1_bit_a(uint64_t hw, int g, int log2_bits) {
+    return acb_hash_is_wide(g) ? ((uint32_t)(hw >> 32) & 31u) : (((uint32_t)hw >> (32 - log2_bits)) & 31u);
+}
+ACB_HD uint32_t acb_stage1_bit_b(uint64_t hw) { return (uint32_t)hw & 31u; }
+
+/* PAIR placement (g = 4, s = 1): the probes at x (x even) and x + 1 read ONE stage-1 word, selected by the
+ * three bytes the two grams share, text[x+1 .. x+4): hash3 = (the window at x+1) * ACB_PAIR_MUL, whose low
+ * byte is zero so the window's fourth byte cancels.  A gram G is therefore entered under hash3(G[1..4)) for
+ * the even role and under hash3(G[0..3)) for the odd role; its two bits are the same in both words. */
+#define ACB_PAIR_MUL (ACB_S1_M1 << 8)
+ACB_HD uint32_t acb_pair_hash3(const uint8_t *three) {
+    return ((uint32_t)three[0] | ((uint32_t)three[1] << 8) | ((uint32_t)three[2] << 16)) * ACB_PAIR_MUL;
+}
+
 #endif

@@ -47,6 +47,35 @@ def hash_bytes(buf, q, g, mul):
     return h
 
 
+def hash_bytes_wide(buf, q, g, mul):
+    """acb_hash_bytes_wide: the same sum with 64-bit products (low half == hash_bytes)"""
+    h = 0
+    nw = (g + 3) // 4
+    n = len(buf)
+    for k in range(nw):
+        w = 0
+        for b in range(4):
+            i = 4 * k + b
+            if i < g and q + i < n:
+                w |= int(buf[q + i]) << (8 * b)
+        h = (h + w * mul[k]) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+FILTER_WIDE, FILTER_PAIR = 1, 2
+PAIR_MUL = (S1[1] << 8) & M32
+
+
+def _pair_hash3(buf, q):
+    """acb_pair_hash3 of buf[q:q+3] (zero filled past the end)"""
+    n = len(buf)
+    w = 0
+    for b in range(3):
+        if q + b < n:
+            w |= int(buf[q + b]) << (8 * b)
+    return (w * PAIR_MUL) & M32
+
+
 def _bit(bm, idx):
     return (int(bm[idx >> 5]) >> (idx & 31)) & 1
 
@@ -97,9 +126,18 @@ def emul_filter(f, buf, offsets=None, stride_bytes=0):
     if f["n_keys"] == 0:
         return recs
     for q in range(0, total, s):
-        h1 = hash_bytes(buf, q, g, mul1)
-        w1 = int(f["bitmap1"][(h1 * (7 << (l1 - 8))) >> 32])
-        if not ((w1 >> ((h1 >> (32 - l1)) & 31)) & (w1 >> (h1 & 31)) & 1):
+        hw = hash_bytes_wide(buf, q, g, mul1)
+        h1 = hw & M32
+        flags = f["filter_flags"]
+        assert bool(flags & FILTER_WIDE) == (g % 4 == 0)
+        bit_a = ((hw >> 32) & 31) if flags & FILTER_WIDE else ((h1 >> (32 - l1)) & 31)
+        if flags & FILTER_PAIR:                  # probes q (even) and q+1 share the word of the bytes they share
+            assert g == 4 and s == 1
+            hsel = _pair_hash3(buf, q + 1) if q % 2 == 0 else _pair_hash3(buf, q)
+        else:
+            hsel = h1
+        w1 = int(f["bitmap1"][(hsel * (7 << (l1 - 8))) >> 32])
+        if not ((w1 >> bit_a) & (w1 >> (h1 & 31)) & 1):
             continue
         if q + g > total:
             continue
