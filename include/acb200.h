@@ -134,6 +134,44 @@ typedef struct acb_flat_view {
 
 int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out);
 
+/* ---- the reference's on-disk node records -------------------------------
+ * Both of the reference's serialisations write one record per trie node, in pre-order (`trie_traverse`,
+ * src/trie.c:196-225), children in table order:
+ *     { u64 output; u64 fail; u32 n; u8 eow; 3 pad }  =  PICKLE_TRIENODE_SIZE, src/pickle/pickle.h:7
+ *     n x { letter (2 bytes in the bytes build, 4 in the unicode build); u64 child }   (packed `Pair`, src/trienode.h:19-25)
+ * `__reduce__` (src/Automaton_pickle.c:128-188) numbers the nodes 1..N and stores those numbers in `fail`/`child`;
+ * `save` (src/custompickle/save/automaton_save.c:85-138) stores node addresses instead, each record preceded by its own
+ * address, and -- for STORE_ANY -- followed by the serialised value whose size is written into `output`.
+ *
+ * acb_trie_export_nodes writes the records with ids 1..N (which double as the "addresses" of a save file).
+ * Call it with out == NULL first: *need_bytes and *n_nodes are always set.  value_of_key (nullable) supplies
+ * `output` of end-of-word nodes (STORE_INTS / STORE_LENGTH); rec_off[N+1] (nullable) receives the byte offset
+ * of every record, eow_key[N] (nullable) the key id ending at the node or -1.  `fail` is written only for a
+ * built automaton (ACB_AHOCORASICK), else 0.  Letters: letter_width 2 sign-extends 1-byte letters exactly
+ * like the bytes build does (src/utils.c:199-202). */
+int acb_trie_export_nodes(const acb_trie *t, int letter_width, const int64_t *value_of_key, int64_t n_values,
+                          uint8_t *out, int64_t cap, int64_t *need_bytes, int64_t *n_nodes,
+                          int64_t *rec_off, int32_t *eow_key, int64_t cap_nodes);
+
+/* The inverse: parse n_nodes records and enter every key into the (empty) trie t, key ids 0.. in pre-order.
+ * mode ACB_NODES_PICKLE: records back to back, node i has id i+1 (src/Automaton_pickle.c:330-456);
+ * mode ACB_NODES_SAVE: `u64 address` before each record, and `output` bytes of serialised value after each
+ * end-of-word record when store_any != 0 (src/custompickle/load/module_automaton_load.c:108-180).
+ * out_value[k] = `output` of key k's node, out_blob_off[k] = offset of its serialised value in buf (SAVE + store_any)
+ * or -1.  Fail links in the file are ignored: acb_trie_make_automaton recomputes them.
+ * Returns ACB_EINVAL for truncated / malformed input (dangling child, node reachable twice, letter out of range). */
+enum { ACB_NODES_PICKLE = 0, ACB_NODES_SAVE = 1 };
+int acb_trie_import_nodes(acb_trie *t, const uint8_t *buf, int64_t len, int64_t n_nodes, int letter_width, int mode,
+                          int store_any, int64_t *out_value, int64_t *out_blob_off, int64_t cap_keys, int64_t *n_keys,
+                          int64_t *consumed,
+                          uint8_t *key_bytes, int64_t key_cap, int64_t *key_off /* cap_keys + 1 */, int64_t *key_need);
+/* key_bytes / key_off (nullable) receive the keys themselves, key k = key_bytes[key_off[k] .. key_off[k+1]);
+ * *key_need (nullable) is always set to the total.  Sizes are not known in advance: import into a scratch trie
+ * first (all outputs NULL except n_keys / key_need), then for real. */
+
+/* bytes taken by n_nodes back-to-back records (the used part of one pickle chunk, src/Automaton_pickle.c:362-419) */
+int acb_node_records_span(const uint8_t *buf, int64_t len, int64_t n_nodes, int letter_width, int64_t *span);
+
 /* ---------------------------------------------------------------- device --- */
 
 /* The flattened automaton resident in HBM of one GPU (uploaded once). */

@@ -18,6 +18,7 @@ import os
 import types
 
 from . import automaton as _a
+from . import serialize as _serialize
 from .automaton import (AHOCORASICK, EMPTY, KEY_SEQUENCE, KEY_STRING, MATCH_AT_LEAST_PREFIX,  # noqa: F401
                         MATCH_AT_MOST_PREFIX, MATCH_EXACT_LENGTH, STORE_ANY, STORE_INTS, STORE_LENGTH,
                         TRIE, AutomatonSearchIter, Matches, load)
@@ -53,6 +54,7 @@ def flavour(name: str):
         m = types.SimpleNamespace(**_CONSTS)
         m.unicode = 1 if name == "unicode" else 0
         m.Automaton = _UnicodeAutomaton if name == "unicode" else _BytesAutomaton
+        m.load = (lambda cls: lambda *args: _serialize.load(cls, *args))(m.Automaton)
         _flavours[name] = m
     return _flavours[name]
 

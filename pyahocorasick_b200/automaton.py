@@ -110,10 +110,25 @@ class Automaton:
         elif len(args) == 1 and isinstance(args[0], int):
             store = args[0]
             self._check_store(store)
+        self._lib = N.lib()
+        self._trie = None
+        self._table = None
+        self._narrow_trie = None
+        self._narrow_table = None
+        self._configure(store, key_type)
+        if len(args) == 7:                # what __reduce__ of the reference produces, src/Automaton.c:106-147
+            from . import serialize
+            serialize.from_reduce_args(self, args)
+
+    def _configure(self, store, key_type):
+        """(re)start as an empty automaton of the given store / key type"""
+        self._drop_table()
+        if self._trie:
+            self._lib.acb_trie_free(self._trie)
+            self._trie = None
         self._store = store
         self._key_type = key_type
         self._L = self._letter_bytes()
-        self._lib = N.lib()
         self._trie = self._lib.acb_trie_new(self._L)
         if not self._trie:
             raise MemoryError(N.last_error())
@@ -397,8 +412,22 @@ class Automaton:
         return object.__sizeof__(self) + self.get_stats()["total_size"]
 
     def __reduce__(self):
-        items = [(k, self._values[i]) for i, k in enumerate(self._key_objs) if k is not None]
-        return (_rebuild, (type(self)._UNICODE, self._store, self._key_type, items, self.kind == AHOCORASICK))
+        """src/Automaton_pickle.c:199-262: (Automaton, (bytes_list, kind, store, key_type, count, longest_word,
+        values)), or (Automaton, ()) without keys.  The argument tuple is the reference's own format -- the
+        reference's constructor accepts it and this constructor accepts the reference's (serialize.py).  An
+        instance of the flavour that is not the package default is rebuilt through _rebuild, because both flavour
+        classes answer to the name `Automaton`."""
+        from . import serialize
+        import pyahocorasick_b200 as pkg
+        args = serialize.reduce_args(self)
+        if type(self) is getattr(pkg, "Automaton", None):
+            return (type(self), args)
+        return (_rebuild, (type(self)._UNICODE, args))
+
+    def save(self, *args):
+        """save(path[, serializer]) in the reference's file format (src/custompickle/save/automaton_save.c)."""
+        from . import serialize
+        serialize.save(self, *args)
 
     # ------------------------------------------------------------------ automaton
     def make_automaton(self):
@@ -880,19 +909,13 @@ def _default_device() -> int:
     return 0
 
 
-def _rebuild(unicode_flavour, store, key_type, items, built):
+def _rebuild(unicode_flavour, args):
     from . import flavour
-    mod = flavour("unicode" if unicode_flavour else "bytes")
-    A = mod.Automaton(store, key_type)
-    for k, v in items:
-        if store == STORE_LENGTH:
-            A.add_word(k)
-        else:
-            A.add_word(k, v)
-    if built:
-        A.make_automaton()
-    return A
+    return flavour("unicode" if unicode_flavour else "bytes").Automaton(*args)
 
 
-def load(path, deserializer=pickle.loads):
-    raise NotImplementedError("save/load are outside the B200 hot path in this round (SURVEY.md section 8(f) #2)")
+def load(*args):
+    """ahocorasick.load(path, deserializer) for the package's default flavour (src/custompickle/load/)."""
+    import pyahocorasick_b200 as pkg
+    from . import serialize
+    return serialize.load(pkg.Automaton, *args)

@@ -667,3 +667,253 @@ extern "C" int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out) {
     out->filter_flags = f.filter_flags;
     return ACB_OK;
 }
+
+/* ------------------------------------------------ the reference's node records (include/acb200.h) */
+namespace {
+
+constexpr int kNodeRecBytes = 24;        /* PICKLE_TRIENODE_SIZE on LP64: output 8, fail 8, n 4, eow 1, pad 3 */
+
+static inline void put_u64(uint8_t *p, uint64_t v) { memcpy(p, &v, 8); }
+static inline void put_u32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
+static inline uint64_t get_u64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static inline uint32_t get_u32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+struct LetterEdge { uint32_t letter; int32_t node; };
+
+/* live letter-children of arena node a: every live node L bytes below it, in sibling (insertion) order */
+static void letter_children(const acb_trie *t, int32_t a, std::vector<LetterEdge> &out, std::vector<LetterEdge> &tmp) {
+    const int L = t->letter_bytes;
+    out.clear();
+    out.push_back({0u, a});
+    for (int d = 0; d < L; d++) {
+        tmp.clear();
+        for (const LetterEdge &e : out)
+            for (int32_t c = t->nodes[e.node].first_child; c >= 0; c = t->nodes[c].next_sibling)
+                if (t->nodes[c].live_below > 0) tmp.push_back({e.letter | ((uint32_t)t->nodes[c].byte << (8 * d)), c});
+        out.swap(tmp);
+    }
+}
+
+} // namespace
+
+extern "C" int acb_trie_export_nodes(const acb_trie *t, int letter_width, const int64_t *value_of_key, int64_t n_values,
+                                     uint8_t *out, int64_t cap, int64_t *need_bytes, int64_t *n_nodes,
+                                     int64_t *rec_off, int32_t *eow_key, int64_t cap_nodes) {
+    if (!t || !need_bytes || !n_nodes) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    if (letter_width != (t->letter_bytes == 4 ? 4 : 2)) {          /* TRIE_LETTER_TYPE: u16 (bytes build) or u32, src/common.h:51-67 */
+        acb_set_error("letter_width %d does not go with %d-byte letters", letter_width, t->letter_bytes);
+        return ACB_EINVAL;
+    }
+    *need_bytes = 0;
+    *n_nodes = 0;
+    if (t->nodes.empty() || t->kind == ACB_EMPTY) return ACB_OK;
+    try {
+        const int L = t->letter_bytes;
+        const bool built = (t->kind == ACB_AHOCORASICK) && t->flat.valid;
+        /* state numbering of make_automaton (BFS, live nodes, insertion order), to read flat.letter_fail */
+        std::vector<int32_t> order, newid;
+        if (built) {
+            newid.assign(t->nodes.size(), -1);
+            order.push_back(0);
+            newid[0] = 0;
+            for (size_t h = 0; h < order.size(); h++)
+                for (int32_t c = t->nodes[order[h]].first_child; c >= 0; c = t->nodes[c].next_sibling)
+                    if (t->nodes[c].live_below > 0) { newid[c] = (int32_t)order.size(); order.push_back(c); }
+        }
+        /* pass 1: pre-order ids (1..N) of the letter nodes */
+        std::vector<int32_t> pre;                       /* id-1 -> arena node */
+        std::vector<int64_t> id_of(t->nodes.size(), 0); /* arena node -> id, 0 = not a letter node */
+        std::vector<LetterEdge> kids, tmp;
+        {
+            std::vector<int32_t> stack;
+            stack.push_back(0);
+            while (!stack.empty()) {
+                int32_t a = stack.back();
+                stack.pop_back();
+                pre.push_back(a);
+                id_of[a] = (int64_t)pre.size();
+                letter_children(t, a, kids, tmp);
+                for (size_t i = kids.size(); i-- > 0;) stack.push_back(kids[i].node);   /* first child on top */
+            }
+        }
+        const int64_t N = (int64_t)pre.size();
+        const int pair_bytes = letter_width + 8;
+        int64_t pos = 0;
+        for (int64_t i = 0; i < N; i++) {
+            const int32_t a = pre[i];
+            letter_children(t, a, kids, tmp);
+            const int64_t rec = kNodeRecBytes + (int64_t)kids.size() * pair_bytes;
+            if (rec_off && i < cap_nodes) rec_off[i] = pos;
+            const int32_t kid = t->nodes[a].key_id;
+            if (eow_key && i < cap_nodes) eow_key[i] = kid;
+            if (out && pos + rec <= cap) {
+                uint8_t *p = out + pos;
+                memset(p, 0, (size_t)rec);
+                uint64_t output = 0;
+                if (kid >= 0 && value_of_key && kid < n_values) output = (uint64_t)value_of_key[kid];
+                uint64_t fail = 0;
+                if (built && a != 0) {
+                    const int32_t lf = t->flat.letter_fail[newid[a]];
+                    if (lf >= 0) fail = (uint64_t)id_of[order[lf]];
+                }
+                put_u64(p, output);
+                put_u64(p + 8, fail);
+                put_u32(p + 16, (uint32_t)kids.size());
+                p[20] = kid >= 0 ? 1 : 0;
+                p += kNodeRecBytes;
+                for (const LetterEdge &e : kids) {
+                    uint32_t letter = e.letter;
+                    if (L == 1 && letter_width == 2) letter = (uint32_t)(uint16_t)(int16_t)(int8_t)(uint8_t)letter;   /* src/utils.c:199-202 */
+                    memcpy(p, &letter, (size_t)letter_width);
+                    put_u64(p + letter_width, (uint64_t)id_of[e.node]);
+                    p += pair_bytes;
+                }
+            }
+            pos += rec;
+        }
+        if (rec_off && N <= cap_nodes) rec_off[N] = pos;            /* rec_off has cap_nodes + 1 slots */
+        *need_bytes = pos;
+        *n_nodes = N;
+        if (out && pos > cap) { acb_set_error("export buffer too small: %lld > %lld", (long long)pos, (long long)cap); return ACB_EOVERFLOW; }
+        if ((rec_off || eow_key) && N > cap_nodes) { acb_set_error("node arrays too small"); return ACB_EOVERFLOW; }
+        return ACB_OK;
+    } catch (const std::bad_alloc &) {
+        acb_set_error("out of memory");
+        return ACB_ENOMEM;
+    }
+}
+
+extern "C" int acb_trie_import_nodes(acb_trie *t, const uint8_t *buf, int64_t len, int64_t n_nodes, int letter_width, int mode,
+                                     int store_any, int64_t *out_value, int64_t *out_blob_off, int64_t cap_keys, int64_t *n_keys,
+                                     int64_t *consumed, uint8_t *key_bytes, int64_t key_cap, int64_t *key_off, int64_t *key_need) {
+    if (!t || !n_keys || len < 0 || n_nodes < 0 || (len && !buf)) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    if (letter_width != (t->letter_bytes == 4 ? 4 : 2)) { acb_set_error("letter_width %d does not go with %d-byte letters", letter_width, t->letter_bytes); return ACB_EINVAL; }
+    if (mode != ACB_NODES_PICKLE && mode != ACB_NODES_SAVE) { acb_set_error("unknown record mode %d", mode); return ACB_EINVAL; }
+    if (!t->nodes.empty()) { acb_set_error("import needs an empty trie"); return ACB_EINVAL; }
+    *n_keys = 0;
+    if (consumed) *consumed = 0;
+    if (key_need) *key_need = 0;
+    if (key_off && cap_keys >= 0) key_off[0] = 0;
+    if (n_nodes == 0) return ACB_OK;
+    try {
+        const int L = t->letter_bytes;
+        const int pair_bytes = letter_width + 8;
+        /* pass 1: locate the records */
+        std::vector<int64_t> rec(n_nodes), blob(n_nodes, -1);
+        std::vector<std::pair<uint64_t, int64_t>> by_addr;          /* SAVE: address -> node index */
+        if (mode == ACB_NODES_SAVE) by_addr.reserve(n_nodes);
+        int64_t pos = 0;
+        for (int64_t i = 0; i < n_nodes; i++) {
+            if (mode == ACB_NODES_SAVE) {
+                if (pos + 8 > len) { acb_set_error("truncated: address of node %lld", (long long)i); return ACB_EINVAL; }
+                by_addr.emplace_back(get_u64(buf + pos), i);
+                pos += 8;
+            }
+            if (pos + kNodeRecBytes > len) { acb_set_error("truncated: header of node %lld", (long long)i); return ACB_EINVAL; }
+            rec[i] = pos;
+            const uint64_t n = get_u32(buf + pos + 16);
+            const bool eow = buf[pos + 20] != 0;
+            const uint64_t output = get_u64(buf + pos);
+            pos += kNodeRecBytes;
+            if (n > (uint64_t)(len - pos) / (uint64_t)pair_bytes) { acb_set_error("truncated: children of node %lld", (long long)i); return ACB_EINVAL; }
+            pos += (int64_t)n * pair_bytes;
+            if (mode == ACB_NODES_SAVE && store_any && eow) {
+                if (output > (uint64_t)(len - pos)) { acb_set_error("truncated: value of node %lld", (long long)i); return ACB_EINVAL; }
+                blob[i] = pos;
+                pos += (int64_t)output;
+            }
+        }
+        if (consumed) *consumed = pos;
+        if (mode == ACB_NODES_SAVE) {
+            std::sort(by_addr.begin(), by_addr.end());
+            for (size_t i = 1; i < by_addr.size(); i++)
+                if (by_addr[i].first == by_addr[i - 1].first) { acb_set_error("two nodes share one address"); return ACB_EINVAL; }
+        }
+        auto resolve = [&](uint64_t ref) -> int64_t {
+            if (mode == ACB_NODES_PICKLE) return (ref >= 1 && ref <= (uint64_t)n_nodes) ? (int64_t)ref - 1 : -1;
+            auto it = std::lower_bound(by_addr.begin(), by_addr.end(), std::make_pair(ref, (int64_t)-1));
+            return (it != by_addr.end() && it->first == ref) ? it->second : -1;
+        };
+        /* pass 2: pre-order walk from the first record (the root), entering the keys */
+        struct Frame { int64_t node; uint32_t next_child; };
+        std::vector<Frame> stack;
+        std::vector<uint8_t> path;
+        std::vector<uint8_t> seen(n_nodes, 0);
+        stack.push_back({0, 0});
+        seen[0] = 1;
+        int64_t keys = 0, kbytes = 0;
+        auto visit = [&](int64_t i) -> int {
+            const uint8_t *p = buf + rec[i];
+            if (p[20]) {                                   /* eow */
+                if (path.empty()) { acb_set_error("the root is marked as the end of a key"); return ACB_EINVAL; }
+                if (keys >= 0x7fffffff) { acb_set_error("too many keys"); return ACB_ERANGE; }
+                if (keys < cap_keys) {
+                    if (out_value) out_value[keys] = (int64_t)get_u64(p);
+                    if (out_blob_off) out_blob_off[keys] = blob[i];
+                    if (key_bytes && key_off && kbytes + (int64_t)path.size() <= key_cap) {
+                        memcpy(key_bytes + kbytes, path.data(), path.size());
+                        key_off[keys + 1] = kbytes + (int64_t)path.size();
+                    }
+                }
+                kbytes += (int64_t)path.size();
+                int rc = acb_trie_add_word(t, path.data(), (int64_t)path.size(), (int32_t)keys, nullptr);
+                if (rc != ACB_OK) return rc;
+                keys++;
+            }
+            return ACB_OK;
+        };
+        while (!stack.empty()) {
+            Frame &f = stack.back();
+            const uint8_t *p = buf + rec[f.node];
+            const uint32_t n = get_u32(p + 16);
+            if (f.next_child == n) {
+                stack.pop_back();
+                if (!stack.empty()) path.resize(path.size() - L);
+                continue;
+            }
+            const uint8_t *pr = p + kNodeRecBytes + (size_t)f.next_child * pair_bytes;
+            f.next_child++;
+            uint32_t letter = 0;
+            memcpy(&letter, pr, (size_t)letter_width);
+            const int64_t child = resolve(get_u64(pr + letter_width));
+            if (child < 0) { acb_set_error("node %lld: child link does not point to a node", (long long)f.node); return ACB_EINVAL; }
+            if (seen[child]) { acb_set_error("node %lld is reachable twice", (long long)child); return ACB_EINVAL; }
+            seen[child] = 1;
+            if (L == 1) {
+                if (letter > 0xffu && letter < 0xff80u) { acb_set_error("letter %u does not fit a byte", letter); return ACB_EINVAL; }
+                path.push_back((uint8_t)(letter & 0xffu));           /* undo the sign extension */
+            } else if (L == 2) {
+                if (letter > 0xffffu) { acb_set_error("letter %u does not fit 16 bits", letter); return ACB_EINVAL; }
+                path.push_back((uint8_t)(letter & 0xff)); path.push_back((uint8_t)(letter >> 8));
+            } else {
+                for (int b = 0; b < 4; b++) path.push_back((uint8_t)(letter >> (8 * b)));
+            }
+            stack.push_back({child, 0});                 /* invalidates f */
+            int rc = visit(child);
+            if (rc != ACB_OK) return rc;
+        }
+        *n_keys = keys;
+        if (key_need) *key_need = kbytes;
+        if (keys > cap_keys && (out_value || out_blob_off || key_off)) { acb_set_error("key arrays too small"); return ACB_EOVERFLOW; }
+        if (key_bytes && kbytes > key_cap) { acb_set_error("key byte buffer too small"); return ACB_EOVERFLOW; }
+        return ACB_OK;
+    } catch (const std::bad_alloc &) {
+        acb_set_error("out of memory");
+        return ACB_ENOMEM;
+    }
+}
+
+extern "C" int acb_node_records_span(const uint8_t *buf, int64_t len, int64_t n_nodes, int letter_width, int64_t *span) {
+    if (!span || len < 0 || n_nodes < 0 || (len && !buf) || (letter_width != 2 && letter_width != 4)) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    const int pair_bytes = letter_width + 8;
+    int64_t pos = 0;
+    for (int64_t i = 0; i < n_nodes; i++) {
+        if (pos + kNodeRecBytes > len) { acb_set_error("Data truncated [parsing header of node #%lld]", (long long)i); return ACB_EINVAL; }
+        const uint64_t n = get_u32(buf + pos + 16);
+        pos += kNodeRecBytes;
+        if (n > (uint64_t)(len - pos) / (uint64_t)pair_bytes) { acb_set_error("Data truncated [parsing children of node #%lld]", (long long)i); return ACB_EINVAL; }
+        pos += (int64_t)n * pair_bytes;
+    }
+    *span = pos;
+    return ACB_OK;
+}
