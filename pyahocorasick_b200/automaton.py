@@ -852,15 +852,41 @@ class AutomatonSearchIter:
 
 
 class AutomatonSearchIterLong:
-    """Result of `Automaton.iter_long()`; matches are produced by one GPU scan at construction."""
+    """Result of `Automaton.iter_long()` (src/AutomatonSearchIterLong.c).  The reference walks lazily; here every
+    chunk is scanned once on the GPU (ACB_ALGO_LONG replays the reference's state machine) when it is handed
+    over, and `__next__` pays the matches out.  What `set()` must carry over is reconstructed from how far the
+    caller had iterated:
+
+    * the walk restarts from the root after every match it returns (:104-112), so once a match of the current
+      chunk has been returned and the chunk is not exhausted, the carried state is the root;
+    * after exhaustion the state is the node reached from the last restart point, i.e. a function of the
+      letters since that point -- `_carry` keeps exactly those letters, and the next chunk is scanned as
+      `carry + chunk` (the replay is deterministic, so it reports nothing inside the carry and reaches the same
+      state at the seam).  A stream without any match therefore keeps growing the carry; that is the price of
+      having no CPU search path.
+    """
 
     def __init__(self, A: Automaton, letters: np.ndarray, start: int, end: int):
         self._A = A
         self._version = A._version
+        self._shift = 0
+        self._carry = letters[:0]
+        self._load(letters, start, end)
+
+    def _load(self, letters: np.ndarray, start: int, end: int) -> None:
         seg = letters[start:end] if end > start else letters[:0]
-        rec = A._scan_one(seg, algo="long") if len(seg) else np.empty(0, dtype=N.MATCH_DTYPE)
-        self._matches = list(zip((rec["end_index"] + start).tolist(), rec["key_id"].tolist()))
+        carry = self._carry
+        if len(carry) and carry.dtype != seg.dtype:           # latin-1 (narrow) next to UCS-4 letters: widen both
+            carry, seg = carry.astype("<u4"), seg.astype("<u4")
+        text = np.concatenate([carry, seg]) if len(carry) else seg
+        rec = self._A._scan_one(text, algo="long") if len(text) else np.empty(0, dtype=N.MATCH_DTYPE)
+        ends = (rec["end_index"].astype(np.int64) - len(carry) + start).tolist()
+        self._matches = list(zip(ends, rec["key_id"].tolist()))
         self._cursor = 0
+        self._carry, self._seg = carry, seg
+        self._start, self._end = start, end
+        self._index = start - 1                               # :34
+        self._exhausted = False
 
     def __iter__(self):
         return self
@@ -869,13 +895,41 @@ class AutomatonSearchIterLong:
         if self._version != self._A._version:
             raise ValueError("underlaying automaton has changed, iterator is not valid anymore")
         if self._cursor >= len(self._matches):
+            self._index += 1                                  # :115, executed on every call
+            if self._index < self._end:
+                self._index = self._end
+            self._exhausted = True
             raise StopIteration
         i, k = self._matches[self._cursor]
         self._cursor += 1
-        return (i, self._A._values[k])
+        self._index = i                                       # :108
+        return (i + self._shift, self._A._values[k])
 
     def set(self, *args):
-        raise NotImplementedError("AutomatonSearchIterLong.set() is not part of this round (SURVEY.md section 8(f) #1)")
+        """set(string, reset=False), :156-212: continue with the next chunk, keeping the walk's state and adding
+        the current index to the offset of the reported positions -- unless `reset`."""
+        if len(args) < 1:
+            raise IndexError("tuple index out of range")
+        letters = self._A._hay_letters(args[0], required=True)
+        reset = bool(args[1]) if len(args) >= 2 else False
+        if reset:
+            self._shift = 0
+            self._carry = letters[:0]
+        else:
+            if self._index >= 0:
+                self._shift += self._index                    # :195-196
+            if self._exhausted:
+                if self._cursor:                              # restart point: just after the last match of this chunk
+                    self._carry = self._seg[self._matches[self._cursor - 1][0] + 1 - self._start:]
+                elif len(self._carry):
+                    self._carry = np.concatenate([self._carry, self._seg])
+                else:
+                    self._carry = self._seg
+            elif self._cursor:
+                self._carry = letters[:0]                     # a match was just returned: the walk is at the root
+            # else: nothing of the old chunk was consumed, state and carry are what they were
+        self._load(letters, 0, len(letters))
+        self._index = -1                                      # :198
 
 
 # ---------------------------------------------------------------------- helpers
