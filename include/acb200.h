@@ -129,8 +129,6 @@ typedef struct acb_flat_view {
 
 /* filter_flags */
 #define ACB_FILTER_WIDE 1   /* g % 4 == 0: the first stage-1 bit comes from the high half of the 64-bit hash sum  */
-#define ACB_FILTER_PAIR 2   /* g = 4, s = 1: probes x (even) and x+1 share ONE word, chosen by the three bytes they
-                               have in common; every gram is entered twice, once for each role                   */
 
 int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out);
 

@@ -375,7 +375,7 @@ __device__ __forceinline__ uint32_t sel8(const uint32_t (&W)[N], int off, int g)
     return (g & 4) ? b1 : b0;
 }
 
-template <int NW, int STRIDE, bool WIDE, bool PAIR, bool GUARD>
+template <int NW, int STRIDE, bool WIDE, bool GUARD>
 __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (&mul)[NW], const uint32_t (&mul2)[NW],
                                             uint32_t rel0, int &qhead, int &qtail) {
     constexpr int kProbes = kFChunk / STRIDE;
@@ -411,20 +411,7 @@ __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (
            has room; c.two == 2 is opaque to the compiler), so probe i ends up in bit kProbes-1-i.  Blocked Bloom,
            k = 2: both bits of the gram must be set in its word (wrap shifts use the low 5 bits of the hash). */
         uint32_t acc = 0;
-        if (PAIR) {                                  /* NW == 1, STRIDE == 1, WIDE: probes t, t+1 share one word */
-#pragma unroll
-            for (int t = 0; t < kFChunk; t += 2) {
-                const uint32_t w0 = ((t & 3) == 0) ? W[t >> 2] : __funnelshift_r(W[t >> 2], W[(t >> 2) + 1], (t & 3) * 8);
-                const uint32_t w1 = __funnelshift_r(W[(t + 1) >> 2], W[((t + 1) >> 2) + 1], ((t + 1) & 3) * 8);
-                const unsigned long long h0 = mad_wide(w0, mul[0], 0ULL), h1 = mad_wide(w1, mul[0], 0ULL);
-                /* the word is chosen by the three bytes the two grams share (acb_hash.h) */
-                const uint32_t word = lds_word(__umulhi(w1 * ACB_PAIR_MUL, c.mul_word) * c.four + c.sbm);
-                const uint32_t b0 = __funnelshift_r(word, 0u, (uint32_t)(h0 >> 32)) & __funnelshift_r(word, 0u, (uint32_t)h0) & 1u;
-                acc = acc * c.two + b0;
-                const uint32_t b1 = __funnelshift_r(word, 0u, (uint32_t)(h1 >> 32)) & __funnelshift_r(word, 0u, (uint32_t)h1) & 1u;
-                acc = acc * c.two + b1;
-            }
-        } else {
+        {
 #pragma unroll
             for (int t = 0; t < kFChunk; t += STRIDE) {
                 uint32_t h = 0, ha;
@@ -504,7 +491,7 @@ __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (
     }
 }
 
-template <int NW, int STRIDE, bool WIDE, bool PAIR>
+template <int NW, int STRIDE, bool WIDE>
 __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int nwords = 1 << (p.log1 - 5);
@@ -572,8 +559,8 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
         if ((long long)blk >= p.n_blocks) break;
         if (first_unit) { ACB_STAMP(2); first_unit = false; }
         const uint32_t rel0 = blk * (uint32_t)kBlockBytes;
-        if ((long long)blk < n_interior) filter_unit<NW, STRIDE, WIDE, PAIR, false>(c, mul, mul2, rel0, qhead, qtail);
-        else filter_unit<NW, STRIDE, WIDE, PAIR, true>(c, mul, mul2, rel0, qhead, qtail);
+        if ((long long)blk < n_interior) filter_unit<NW, STRIDE, WIDE, false>(c, mul, mul2, rel0, qhead, qtail);
+        else filter_unit<NW, STRIDE, WIDE, true>(c, mul, mul2, rel0, qhead, qtail);
         if (qtail - qhead >= 32) {
             if (p.inline_resolve) drain_queue(p, wr, qhead, qtail, false, lane);
             else spill_queue(c, qhead, qtail, false);
@@ -881,9 +868,9 @@ static size_t filter_smem_bytes(int log1) {
            (size_t)kWarps * kStageCap * sizeof(acb_match) + (size_t)kWarps * sizeof(int);
 }
 
-template <int NW, int STRIDE, bool WIDE, bool PAIR>
+template <int NW, int STRIDE, bool WIDE>
 static int launch_filter_w(const ScanParams &p, int grid, cudaStream_t s) {
-    auto kern = acb_filter_kernel<NW, STRIDE, WIDE, PAIR>;
+    auto kern = acb_filter_kernel<NW, STRIDE, WIDE>;
     const size_t smem = filter_smem_bytes(p.log1);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, s>>>(p);
@@ -892,16 +879,14 @@ static int launch_filter_w(const ScanParams &p, int grid, cudaStream_t s) {
     return ACB_OK;
 }
 
-/* WIDE follows from the gram length (acb_hash_is_wide); PAIR exists for one shape only: g = 4, s = 1 */
+/* WIDE follows from the gram length (acb_hash_is_wide) */
 template <int NW, int STRIDE>
 static int launch_filter_t(const ScanParams &p, int grid, cudaStream_t s) {
-    if (p.filter_flags & ACB_FILTER_PAIR) {
-        if (NW == 1 && STRIDE == 1 && p.gram == 4) return launch_filter_w<1, 1, true, true>(p, grid, s);
-        acb_set_error("PAIR filter needs gram 4, stride 1 (got gram %d)", p.gram);
-        return ACB_EINVAL;
+    if (p.filter_flags & ACB_FILTER_WIDE) {
+        if (p.gram != 4 * NW) { acb_set_error("WIDE filter with gram %d", p.gram); return ACB_EINVAL; }
+        return launch_filter_w<NW, STRIDE, true>(p, grid, s);
     }
-    if (p.gram == 4 * NW) return launch_filter_w<NW, STRIDE, true, false>(p, grid, s);
-    return launch_filter_w<NW, STRIDE, false, false>(p, grid, s);
+    return launch_filter_w<NW, STRIDE, false>(p, grid, s);
 }
 
 template <int NW>

@@ -103,13 +103,4 @@ ACB_HD uint32_t acb_stage1_bit_a(uint64_t hw, int g, int log2_bits) {
 }
 ACB_HD uint32_t acb_stage1_bit_b(uint64_t hw) { return (uint32_t)hw & 31u; }
 
-/* PAIR placement (g = 4, s = 1): the probes at x (x even) and x + 1 read ONE stage-1 word, selected by the
- * three bytes the two grams share, text[x+1 .. x+4): hash3 = (the window at x+1) * ACB_PAIR_MUL, whose low
- * byte is zero so the window's fourth byte cancels.  A gram G is therefore entered under hash3(G[1..4)) for
- * the even role and under hash3(G[0..3)) for the odd role; its two bits are the same in both words. */
-#define ACB_PAIR_MUL (ACB_S1_M1 << 8)
-ACB_HD uint32_t acb_pair_hash3(const uint8_t *three) {
-    return ((uint32_t)three[0] | ((uint32_t)three[1] << 8) | ((uint32_t)three[2] << 16)) * ACB_PAIR_MUL;
-}
-
 #endif

@@ -392,28 +392,14 @@ static void build_filter(acb_trie *t, Flat &f) {
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     acb_hash_multipliers(g, 1, mul1);
     acb_hash_multipliers(g, 2, mul2);
-    /* PAIR placement halves the shared-memory loads and index arithmetic of a stride-1 filter over 4-byte
-     * grams, at the price of entering every gram twice (acb_hash.h).  Taken only while the doubled fill keeps
-     * the predicted stage-1 pass rate of random text under 1 %.  ACB_PAIR=0/1 overrides. */
-    bool pair = false;
-    if (g == 4 && s == 1 && L == 1) {
-        const double frac_set = std::min(1.0, 4.0 * (double)best_grams.size() / (0.875 * std::pow(2.0, best.log1)));
-        pair = frac_set * frac_set < 0.01;
-        if (const char *env = getenv("ACB_PAIR")) pair = atoi(env) != 0;
-    }
-    f.filter_flags = (acb_hash_is_wide(g) ? ACB_FILTER_WIDE : 0) | (pair ? ACB_FILTER_PAIR : 0);
+    f.filter_flags = acb_hash_is_wide(g) ? ACB_FILTER_WIDE : 0;
     for (const auto &gr : best_grams) {
         const uint64_t hw = acb_hash_bytes_wide(gr.data(), g, mul1);
         uint32_t h1 = (uint32_t)hw, h2 = acb_hash_bytes(gr.data(), g, mul2) | 1u;
         /* two bits per gram inside one word (a blocked Bloom filter with k = 2): the probe costs one
            shared-memory load either way, and a random gram now has to find BOTH bits set */
         const uint32_t bits = (1u << acb_stage1_bit_a(hw, g, best.log1)) | (1u << acb_stage1_bit_b(hw));
-        if (pair) {
-            f.bm1[(size_t)(((uint64_t)acb_pair_hash3(gr.data() + 1) * mulw1) >> 32)] |= bits;     /* even role */
-            f.bm1[(size_t)(((uint64_t)acb_pair_hash3(gr.data()) * mulw1) >> 32)] |= bits;         /* odd role  */
-        } else {
-            f.bm1[(size_t)(((uint64_t)h1 * mulw1) >> 32)] |= bits;
-        }
+        f.bm1[(size_t)(((uint64_t)h1 * mulw1) >> 32)] |= bits;
         f.bm2[h2 >> (40 - best.log1)] |= 1u << ((h2 >> (35 - best.log1)) & 31);
     }
 

@@ -62,18 +62,7 @@ def hash_bytes_wide(buf, q, g, mul):
     return h
 
 
-FILTER_WIDE, FILTER_PAIR = 1, 2
-PAIR_MUL = (S1[1] << 8) & M32
-
-
-def _pair_hash3(buf, q):
-    """acb_pair_hash3 of buf[q:q+3] (zero filled past the end)"""
-    n = len(buf)
-    w = 0
-    for b in range(3):
-        if q + b < n:
-            w |= int(buf[q + b]) << (8 * b)
-    return (w * PAIR_MUL) & M32
+FILTER_WIDE = 1
 
 
 def _bit(bm, idx):
@@ -131,12 +120,7 @@ def emul_filter(f, buf, offsets=None, stride_bytes=0):
         flags = f["filter_flags"]
         assert bool(flags & FILTER_WIDE) == (g % 4 == 0)
         bit_a = ((hw >> 32) & 31) if flags & FILTER_WIDE else ((h1 >> (32 - l1)) & 31)
-        if flags & FILTER_PAIR:                  # probes q (even) and q+1 share the word of the bytes they share
-            assert g == 4 and s == 1
-            hsel = _pair_hash3(buf, q + 1) if q % 2 == 0 else _pair_hash3(buf, q)
-        else:
-            hsel = h1
-        w1 = int(f["bitmap1"][(hsel * (7 << (l1 - 8))) >> 32])
+        w1 = int(f["bitmap1"][(h1 * (7 << (l1 - 8))) >> 32])
         if not ((w1 >> bit_a) & (w1 >> (h1 & 31)) & 1):
             continue
         if q + g > total:

@@ -104,9 +104,9 @@ def test_filter_choice_for_baseline_configs():
     w = synth.make("C2", scale=0.001)
     f = synth.build_automaton(w.keys).flat()
     assert (f["gram_bytes"], f["stride"], f["log2_bits1"]) == (4, 1, 20)
-    assert f["filter_flags"] == emul.FILTER_WIDE | emul.FILTER_PAIR      # g = 4, s = 1, sparse enough: pair placement
+    assert f["filter_flags"] == emul.FILTER_WIDE          # g % 4 == 0: first bit from the high half of the 64-bit sum
     fill = np.unpackbits(f["bitmap1"].view(np.uint8)).mean()
-    assert 0.03 < fill < 0.06               # two bits per gram (blocked Bloom, k = 2), entered for both pair roles
+    assert 0.015 < fill < 0.03              # two bits per gram (blocked Bloom, k = 2) in 7/8 of 2^20 bits
     assert 0.02 < np.unpackbits(f["bitmap2"].view(np.uint8)).mean() < 0.09
     a = f["anchors"]
     used = a[a[:, 0] != 0]
@@ -153,33 +153,3 @@ def test_pickle_round_trip_keeps_keys_values_and_kind():
         T.add_word(conv("abc"))
         D = pickle.loads(pickle.dumps(T))
         assert D.kind == ac.TRIE and D.get(conv("abc")) == 3 and D.store == ac.STORE_LENGTH
-
-
-def test_pair_placement_is_optional_and_declined_for_dense_key_sets(monkeypatch):
-    """ACB_FILTER_PAIR (include/acb200.h): taken for g=4/s=1 while the doubled fill stays small, never otherwise;
-    with it forced off the same keys give the single placement and the same matches."""
-    rng = np.random.default_rng(77)
-    al = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz0123456789", dtype=np.uint8)
-    keys = synth.draw_keys(rng, al, 4000, 4, 9)
-    hay = synth.random_haystacks(rng, al, 16, 128)
-    synth.plant(rng, hay, keys, np.arange(16))
-    flat = hay.reshape(-1)
-    O = oracle.OracleAutomaton()
-    for i, k in enumerate(keys):
-        O.add_word(k, i)
-    O.make_automaton()
-    want = [tuple(r) for r in O.scan_batch_bytes(flat, np.arange(17, dtype=np.int64) * 128).tolist()]
-    f_pair = synth.build_automaton(keys).flat()
-    assert f_pair["filter_flags"] & emul.FILTER_PAIR
-    assert emul.emul_filter(f_pair, flat, None, 128) == want
-    monkeypatch.setenv("ACB_PAIR", "0")
-    f_single = synth.build_automaton(keys).flat()
-    assert not f_single["filter_flags"] & emul.FILTER_PAIR
-    assert emul.emul_filter(f_single, flat, None, 128) == want
-    assert np.unpackbits(f_single["bitmap1"].view(np.uint8)).sum() < np.unpackbits(f_pair["bitmap1"].view(np.uint8)).sum()
-    monkeypatch.delenv("ACB_PAIR")
-    dense = synth.draw_keys(rng, al, 60000, 4, 8)                         # 4 * grams / bits > 10 %: declined
-    assert not synth.build_automaton(dense).flat()["filter_flags"] & emul.FILTER_PAIR
-    long_keys = synth.draw_keys(rng, al, 200, 12, 16)                     # longer grams / strides: never
-    fl = synth.build_automaton(long_keys).flat()
-    assert not fl["filter_flags"] & emul.FILTER_PAIR and (fl["gram_bytes"], fl["stride"]) != (4, 1)
