@@ -383,7 +383,7 @@ static void build_filter(acb_trie *t, Flat &f) {
     f.log1 = best.log1;
     /* The 2^log1 bits of shared memory are split 7/8 : 1/8 between the stage-1 bitmap (probed at
      * every position, indexed by hash1) and the stage-2 bitmap (probed only by stage-1 survivors,
-     * indexed by hash2):  word1 = umulhi(hash1, 7 << (log1-8)), bits (hash1 >> (32-log1)) & 31 AND hash1 & 31;
+     * indexed by hash2):  word1 = umulhi(hash1, 7 << (log1-8)), bits acb_stage1_bit_a AND acb_stage1_bit_b (acb_hash.h);
      *                     word2 = hash2 >> (40-log1),           bit2 = (hash2 >> (35-log1)) & 31. */
     const uint32_t mulw1 = 7u << (best.log1 - 8);
     f.bm1.assign((size_t)7 << (best.log1 - 8), 0);
