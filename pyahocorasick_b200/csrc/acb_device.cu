@@ -411,33 +411,31 @@ __device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (
            has room; c.two == 2 is opaque to the compiler), so probe i ends up in bit kProbes-1-i.  Blocked Bloom,
            k = 2: both bits of the gram must be set in its word (wrap shifts use the low 5 bits of the hash). */
         uint32_t acc = 0;
-        {
 #pragma unroll
-            for (int t = 0; t < kFChunk; t += STRIDE) {
-                uint32_t h = 0, ha;
-                if (WIDE) {                          /* 64-bit products: low half = hash1, high half -> first bit */
-                    unsigned long long hw = 0;
+        for (int t = 0; t < kFChunk; t += STRIDE) {
+            uint32_t h = 0, ha;
+            if (WIDE) {                          /* 64-bit products: low half = hash1, high half -> first bit */
+                unsigned long long hw = 0;
 #pragma unroll
-                    for (int k = 0; k < NW; k++) {
-                        const int wi = (t >> 2) + k;
-                        const uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
-                        hw = mad_wide(w, mul[k], hw);
-                    }
-                    h = (uint32_t)hw;
-                    ha = (uint32_t)(hw >> 32);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < NW; k++) {
-                        const int wi = (t >> 2) + k;
-                        const uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
-                        h += w * mul[k];
-                    }
-                    ha = h >> c.sh_bit;
+                for (int k = 0; k < NW; k++) {
+                    const int wi = (t >> 2) + k;
+                    const uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
+                    hw = mad_wide(w, mul[k], hw);
                 }
-                const uint32_t word = lds_word(__umulhi(h, c.mul_word) * c.four + c.sbm);
-                const uint32_t both = __funnelshift_r(word, 0u, ha) & __funnelshift_r(word, 0u, h) & 1u;
-                acc = acc * c.two + both;
+                h = (uint32_t)hw;
+                ha = (uint32_t)(hw >> 32);
+            } else {
+#pragma unroll
+                for (int k = 0; k < NW; k++) {
+                    const int wi = (t >> 2) + k;
+                    const uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
+                    h += w * mul[k];
+                }
+                ha = h >> c.sh_bit;
             }
+            const uint32_t word = lds_word(__umulhi(h, c.mul_word) * c.four + c.sbm);
+            const uint32_t both = __funnelshift_r(word, 0u, ha) & __funnelshift_r(word, 0u, h) & 1u;
+            acc = acc * c.two + both;
         }
         uint32_t hits = __brev(acc) >> (32 - kProbes);                             /* bit i = probe i */
         if (GUARD && pos0 + kFChunk > c.seg_len) {                                 /* probes that start past the segment */
