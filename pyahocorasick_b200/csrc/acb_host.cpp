@@ -14,13 +14,13 @@
 #include "acb_hash.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
-#include <unordered_set>
 #include <vector>
 
 /* ------------------------------------------------------------------ errors */
@@ -252,6 +252,19 @@ extern "C" int64_t acb_trie_links(const acb_trie *t) { return (t && t->live_node
 /* ---------------------------------------------------------- gram filter */
 namespace {
 
+/* ACB_TRACE=1: phase times of make_automaton on stderr */
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(getenv("ACB_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[make_automaton] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 struct FilterChoice {
     int g = 0, s = 0, log1 = 0;
     double cost = 1e300;
@@ -259,23 +272,47 @@ struct FilterChoice {
 
 static inline void set_bit(std::vector<uint32_t> &bm, uint32_t idx) { bm[idx >> 5] |= 1u << (idx & 31); }
 
-/* distinct grams of the m-prefixes at offsets 0, L, .., s-L */
-static void collect_grams(const std::vector<std::vector<uint8_t>> &prefixes, int g, int s, int L,
-                          std::vector<std::vector<uint8_t>> &out) {
-    struct H {
-        size_t operator()(const std::vector<uint8_t> &v) const {
-            uint64_t h = 1469598103934665603ULL;
-            for (uint8_t b : v) { h ^= b; h *= 1099511628211ULL; }
-            return (size_t)h;
-        }
-    };
-    std::unordered_set<std::vector<uint8_t>, H> seen;
+/* a gram (g <= 16 bytes) as two zero-padded little-endian words: cheap to copy, sort and compare */
+struct Gram16 {
+    uint64_t a = 0, b = 0;
+    const uint8_t *data() const { return reinterpret_cast<const uint8_t *>(this); }
+    bool operator<(const Gram16 &o) const { return a != o.a ? a < o.a : b < o.b; }
+    bool operator==(const Gram16 &o) const { return a == o.a && b == o.b; }
+};
+static inline Gram16 load_gram(const uint8_t *p, int g) {
+    Gram16 x;
+    memcpy(&x, p, (size_t)g);
+    return x;
+}
+static inline uint64_t mix_gram(const Gram16 &x) {
+    uint64_t h = x.a * 0x9E3779B97F4A7C15ULL ^ (x.b + 0xC2B2AE3D27D4EB4FULL) * 0xFF51AFD7ED558CCDULL;
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ULL; h ^= h >> 29;
+    return h;
+}
+
+/* number of distinct grams of the m-prefixes at offsets 0, L, .., s-L (the cost model's E): counted over
+ * 64-bit fingerprints, so the candidate shapes can be compared without materialising their gram sets */
+static size_t count_grams(const std::vector<std::vector<uint8_t>> &prefixes, int g, int s, int L, std::vector<uint64_t> &scratch) {
+    scratch.clear();
     for (const auto &p : prefixes)
         for (int j = 0; j + L <= s; j += L) {
             if (j + g > (int)p.size()) break;
-            std::vector<uint8_t> gr(p.begin() + j, p.begin() + j + g);
-            if (seen.insert(gr).second) out.push_back(std::move(gr));
+            scratch.push_back(mix_gram(load_gram(p.data() + j, g)));
         }
+    std::sort(scratch.begin(), scratch.end());
+    return (size_t)(std::unique(scratch.begin(), scratch.end()) - scratch.begin());
+}
+
+/* the distinct grams themselves (for the chosen shape only) */
+static void collect_grams(const std::vector<std::vector<uint8_t>> &prefixes, int g, int s, int L, std::vector<Gram16> &out) {
+    out.clear();
+    for (const auto &p : prefixes)
+        for (int j = 0; j + L <= s; j += L) {
+            if (j + g > (int)p.size()) break;
+            out.push_back(load_gram(p.data() + j, g));
+        }
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
 }
 
 static int ceil_log2_u64(uint64_t x) {
@@ -288,10 +325,10 @@ static int ceil_log2_u64(uint64_t x) {
 
 /* unique key below node v (live_below == 1): its id and all of its bytes */
 static int32_t unique_key_below(const acb_trie *t, int32_t v, std::vector<uint8_t> &bytes) {
-    bytes.clear();
-    std::vector<uint8_t> up;
-    for (int32_t x = v; x > 0; x = t->nodes[x].parent) up.push_back(t->nodes[x].byte);
-    bytes.assign(up.rbegin(), up.rend());
+    size_t d = 0;
+    for (int32_t x = v; x > 0; x = t->nodes[x].parent) d++;
+    bytes.resize(d);
+    for (int32_t x = v; x > 0; x = t->nodes[x].parent) bytes[--d] = t->nodes[x].byte;
     int32_t x = v;
     while (t->nodes[x].key_id < 0) {
         int32_t nxt = -1;
@@ -318,6 +355,7 @@ static int32_t unique_key_below(const acb_trie *t, int32_t v, std::vector<uint8_
  * Entry = 8 x uint32: tag (hash2|1, 0 = empty), key_id (-1 = MULTI), j | len<<8 | last<<16 (last = no
  * further entry with this tag in the probe sequence), 20 key/gram bytes. */
 static void build_filter(acb_trie *t, Flat &f) {
+    PhaseTimer pt;
     const int L = t->letter_bytes;
     const int m = f.min_key_bytes;
     /* live nodes down to depth m, with depths */
@@ -343,12 +381,14 @@ static void build_filter(acb_trie *t, Flat &f) {
                 if (t->nodes[c].live_below > 0) { depth[c] = depth[nd] + 1; stack.push_back(c); }
         }
     }
+    pt.lap("filter: prefixes");
     int forced_g = 0, forced_s = 0, forced_l1 = 0;
     if (const char *env = getenv("ACB_FILTER")) sscanf(env, "%d,%d,%d", &forced_g, &forced_s, &forced_l1);
 
     const double Kb = std::max(1, f.K - 1);
     FilterChoice best;
-    std::vector<std::vector<uint8_t>> best_grams;
+    std::vector<Gram16> best_grams;
+    std::vector<uint64_t> scratch;
     for (int s = L; s <= 16; s *= 2) {
         if (forced_s && s != forced_s) continue;
         int gmax = std::min(ACB_MAX_GRAM, m - s + L);
@@ -359,9 +399,7 @@ static void build_filter(acb_trie *t, Flat &f) {
         for (int g = 12; g >= 4; g -= 4) if (g < gmax && g % L == 0) gs.push_back(g);
         for (int g : gs) {
             if (forced_g && g != forced_g) continue;
-            std::vector<std::vector<uint8_t>> grams;
-            collect_grams(prefixes, g, s, L, grams);
-            const double E = (double)grams.size();
+            const double E = (double)count_grams(prefixes, g, s, L, scratch);
             int log1 = std::min(20, std::max(13, ceil_log2_u64((uint64_t)(E * 64.0) + 1)));
             if (forced_l1) log1 = forced_l1;
             double space = std::pow(Kb, (double)g);
@@ -373,10 +411,11 @@ static void build_filter(acb_trie *t, Flat &f) {
             double cost = ((4.0 + 3.0 * nw) + pass1 * 40.0 + p_true * (s / L) * 40.0) / s;
             if (cost < best.cost) {
                 best.g = g; best.s = s; best.log1 = log1; best.cost = cost;
-                best_grams.swap(grams);
             }
         }
     }
+    collect_grams(prefixes, best.g, best.s, L, best_grams);
+    pt.lap("filter: choose gram/stride");
     const int g = best.g, s = best.s;
     f.gram = g;
     f.stride = s;
@@ -403,28 +442,32 @@ static void build_filter(acb_trie *t, Flat &f) {
         f.bm2[h2 >> (40 - best.log1)] |= 1u << ((h2 >> (35 - best.log1)) & 31);
     }
 
+    pt.lap("filter: bitmaps");
     /* ---- anchor table ---- */
-    struct Cand { std::vector<uint8_t> gram; int j; int32_t node; };
+    struct Cand { Gram16 gram; int j; int32_t node; };
     std::vector<Cand> cands;
     for (int32_t nd : upto_m) {
         int d = depth[nd];
         int j = d - g;
         if (j < 0 || j > s - L || (j % L)) continue;
         Cand c;
-        c.gram.resize(g);
+        uint8_t gb[16] = {0};
         int32_t x = nd;
-        for (int i = g - 1; i >= 0; i--) { c.gram[i] = t->nodes[x].byte; x = t->nodes[x].parent; }
+        for (int i = g - 1; i >= 0; i--) { gb[i] = t->nodes[x].byte; x = t->nodes[x].parent; }
+        c.gram = load_gram(gb, g);
         c.j = j;
         c.node = nd;
-        cands.push_back(std::move(c));
+        cands.push_back(c);
     }
-    std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) {
+    std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) {      /* groups (j, gram); any total order will do */
         if (a.j != b.j) return a.j < b.j;
-        return a.gram < b.gram;
+        if (!(a.gram == b.gram)) return a.gram < b.gram;
+        return a.node < b.node;
     });
     struct Entry { uint32_t w[8]; };
-    std::vector<Entry> entries;
+    std::vector<Entry> entries, group;
     std::vector<uint8_t> kb;
+    entries.reserve(cands.size());
     auto pack = [](Entry &e, uint32_t tag, int32_t key_id, int j, int len, const uint8_t *bytes) {
         memset(&e, 0, sizeof(e));
         e.w[0] = tag;
@@ -437,7 +480,7 @@ static void build_filter(acb_trie *t, Flat &f) {
         while (b < cands.size() && cands[b].j == cands[a].j && cands[b].gram == cands[a].gram) b++;
         uint32_t tag = acb_hash_bytes(cands[a].gram.data(), g, mul2) | 1u;
         bool multi = false;
-        std::vector<Entry> group;
+        group.clear();
         for (size_t i = a; i < b && !multi; i++) {
             const Node &nd = t->nodes[cands[i].node];
             if (nd.live_below != 1) { multi = true; break; }
@@ -456,6 +499,7 @@ static void build_filter(acb_trie *t, Flat &f) {
         }
         a = b;
     }
+    pt.lap("filter: anchor entries");
     /* stage 3: a bitmap in global memory over a re-mix of the tag, 64 bits per distinct tag.  Only used
      * when the shared-memory bitmaps are too full to reject much (large key sets): it keeps the flood of
      * survivors away from the anchor table at the price of one L2 access each. */
@@ -486,6 +530,7 @@ static void build_filter(acb_trie *t, Flat &f) {
         while (f.anchors[i * 8] != 0) i = (i + 1) & mask;
         memcpy(&f.anchors[i * 8], e.w, sizeof(e.w));
     }
+    pt.lap("filter: stage 3 + anchor table");
 }
 
 /* ----------------------------------------------- make_automaton + flatten */
@@ -494,6 +539,7 @@ extern "C" int acb_trie_make_automaton(acb_trie *t, int32_t *built) {
     if (built) *built = 0;
     if (t->kind != ACB_TRIE) return ACB_OK;              /* src/Automaton.c:574-575 */
     try {
+        PhaseTimer pt;
         Flat &f = t->flat;
         f = Flat();
         const int64_t S64 = t->live_nodes;
@@ -600,6 +646,7 @@ extern "C" int acb_trie_make_automaton(acb_trie *t, int32_t *built) {
             for (int32_t x = (f.key_of[s] >= 0) ? s : osuf[s]; x >= 0; x = osuf[x]) f.out_idx[w++] = f.key_of[x];
         }
 
+        pt.lap("goto / fail / outputs");
         if (f.n_keys > 0) build_filter(t, f);
         else {                                               /* nothing can ever match */
             f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.log2 = 10; f.logA = 10;
