@@ -227,6 +227,12 @@ int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_bytes,
 /* copy the first n records of the last acb_scan_host(out = NULL) call into `out` */
 int acb_copy_records(acb_table *tb, acb_match *out, int64_t n);
 
+/* ... or take them without a copy: *ptr is the pinned staging buffer itself (*n records, room for *cap), owned
+ * by the caller from now on and to be given back with acb_release_records(ptr, cap) when done -- it then serves a
+ * later scan.  *ptr == NULL when the last scan found nothing. */
+int  acb_take_records(acb_table *tb, acb_match **ptr, int64_t *n, int64_t *cap);
+void acb_release_records(acb_match *ptr, int64_t cap);
+
 /* Sort n device-resident records into the reference's order (hay_id, end_index ascending, longest
  * key first) with a 64-bit radix sort, asynchronously on `stream`.  max_hay_letters bounds end_index.
  * ACB_ERANGE when hay_id/end_index/length do not fit one 64-bit key (sort on the host then). */

@@ -62,6 +62,23 @@ def _space_mask(letters: np.ndarray, bytes_flavour: bool) -> np.ndarray:
     return np.isin(vals, spaces)
 
 
+class _PinnedRecords:
+    """Owner of one pinned record buffer taken from the library (acb_take_records): exposes it to numpy through
+    the array interface, gives it back (acb_release_records) when the last view is garbage collected."""
+    __slots__ = ("_lib", "_ptr", "_cap", "__array_interface__")
+
+    def __init__(self, lib, ptr: int, n: int, cap: int):
+        self._lib, self._ptr, self._cap = lib, ptr, cap
+        self.__array_interface__ = {"version": 3, "shape": (n,), "typestr": "|V12", "descr": N.MATCH_DTYPE.descr,
+                                    "data": (ptr, False)}
+
+    def __del__(self):
+        try:
+            self._lib.acb_release_records(self._ptr, self._cap)
+        except Exception:                                   # interpreter shutdown
+            pass
+
+
 class Matches:
     """Result of a batch search: parallel int32 arrays in the reference's order
     (hay_id, then end_index ascending, then longest key first)."""
@@ -562,10 +579,15 @@ class Automaton:
                 self._match_cap = cap
                 continue
             N.check(rc)
-            out = np.empty(found.value, dtype=N.MATCH_DTYPE)   # exact size, one copy out of the pinned staging
-            if found.value:
-                N.check(self._lib.acb_copy_records(tb, N.ptr(out), found.value))
-            return out
+            if not found.value:
+                return np.empty(0, dtype=N.MATCH_DTYPE)
+            # no copy: the records stay in the pinned buffer the D2H landed in; it returns to the library's pool
+            # when the last array that views it is gone (_PinnedRecords.__del__)
+            ptr, n, room = ctypes.c_void_p(), ctypes.c_int64(0), ctypes.c_int64(0)
+            N.check(self._lib.acb_take_records(tb, ctypes.byref(ptr), ctypes.byref(n), ctypes.byref(room)))
+            if not ptr.value or n.value != found.value:
+                raise N.NativeError("acb_take_records: no records to take")
+            return np.asarray(_PinnedRecords(self._lib, ptr.value, n.value, room.value))
 
     def _scan_device_tensor(self, t, algo: str, sort: bool) -> np.ndarray:
         """Batch already resident in HBM: a C-contiguous uint8 torch CUDA tensor [n, stride].  No host copy of

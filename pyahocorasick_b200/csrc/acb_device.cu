@@ -34,6 +34,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -1052,6 +1053,51 @@ extern "C" int acb_copy_records(acb_table *tb, acb_match *out, int64_t n) {
     return ACB_OK;
 }
 
+/* Zero-copy hand-over of the records.  The pinned staging buffer of the last acb_scan_host can be taken by the
+ * caller (no memcpy, no page faults of a fresh destination); it comes back through acb_release_records into a
+ * small process-wide pool from which the next scan that needs a staging buffer is served.  A buffer that is
+ * never released is simply not reused. */
+namespace {
+struct PinnedBuf { acb_match *p; size_t cap; };
+std::mutex g_pool_mu;
+std::vector<PinnedBuf> g_pool;
+constexpr size_t kPoolMax = 4;
+
+acb_match *pool_take(size_t need, size_t *cap) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    size_t best = g_pool.size();
+    for (size_t i = 0; i < g_pool.size(); i++)
+        if (g_pool[i].cap >= need && (best == g_pool.size() || g_pool[i].cap < g_pool[best].cap)) best = i;
+    if (best == g_pool.size()) return nullptr;
+    acb_match *p = g_pool[best].p;
+    *cap = g_pool[best].cap;
+    g_pool.erase(g_pool.begin() + (long)best);
+    return p;
+}
+} // namespace
+
+extern "C" int acb_take_records(acb_table *tb, acb_match **ptr, int64_t *n, int64_t *cap) {
+    if (!tb || !ptr || !n || !cap) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    *ptr = nullptr; *n = 0; *cap = 0;
+    if (tb->h_out_n == 0 || !tb->h_out) return ACB_OK;       /* nothing to hand over */
+    *ptr = tb->h_out;
+    *n = (int64_t)tb->h_out_n;
+    *cap = (int64_t)tb->h_out_cap;
+    tb->h_out = nullptr;                                     /* the next scan gets a buffer from the pool or a new one */
+    tb->h_out_cap = 0;
+    tb->h_out_n = 0;
+    return ACB_OK;
+}
+
+extern "C" void acb_release_records(acb_match *ptr, int64_t cap) {
+    if (!ptr || cap <= 0) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool.size() < kPoolMax) { g_pool.push_back({ptr, (size_t)cap}); return; }
+    }
+    cudaFreeHost(ptr);
+}
+
 /* ------------------------------------------------------------ record sort */
 /* Reference order: haystack, then end_index ascending, then longest key first.  One
  * 64-bit radix key per record: hay_id | end_index | (max_len - len), packed into the fewest bits. */
@@ -1155,10 +1201,16 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
     }
     if (n) {
         if (tb->h_out_cap < n) {                               /* pinned staging: D2H at full PCIe rate */
-            if (tb->h_out) { cudaFreeHost(tb->h_out); tb->h_out = nullptr; tb->h_out_cap = 0; }
-            size_t want = (size_t)n + (size_t)n / 4 + 1024;
-            CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&tb->h_out), want * sizeof(acb_match)));
-            tb->h_out_cap = want;
+            if (tb->h_out) { acb_release_records(tb->h_out, (int64_t)tb->h_out_cap); tb->h_out = nullptr; tb->h_out_cap = 0; }
+            size_t got = 0;
+            if (acb_match *p = pool_take((size_t)n, &got)) {  /* a buffer some caller has given back */
+                tb->h_out = p;
+                tb->h_out_cap = got;
+            } else {
+                size_t want = (size_t)n + (size_t)n / 4 + 1024;
+                CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&tb->h_out), want * sizeof(acb_match)));
+                tb->h_out_cap = want;
+            }
         }
         bool host_sort = sort != 0;
         if (sort) {                                            /* radix sort on the device when the key fits 64 bits */

@@ -49,3 +49,32 @@ def test_host_calls_work_without_a_gpu_and_scan_fails_loudly():
             N.check(rc)
     L.acb_trie_free(t)
     assert L.acb_trie_new(3) is None and "letter_bytes" in N.last_error()
+
+
+def test_pinned_record_holder_releases_once_after_the_last_view():
+    """automaton._PinnedRecords: numpy views keep the taken buffer alive; it goes back to the library exactly once"""
+    import ctypes
+    import gc
+    import numpy as np
+    from pyahocorasick_b200 import automaton as am
+
+    calls = []
+
+    class FakeLib:
+        def acb_release_records(self, p, cap):
+            calls.append((p, cap))
+
+    raw = (ctypes.c_int32 * 24)(*range(24))
+    a = np.asarray(am._PinnedRecords(FakeLib(), ctypes.addressof(raw), 5, 8))
+    assert a.dtype == N.MATCH_DTYPE and a.shape == (5,)
+    assert a["hay_id"].tolist() == [0, 3, 6, 9, 12] and a["key_id"].tolist() == [2, 5, 8, 11, 14]
+    v, w = a["end_index"], a[1:3]
+    del a
+    gc.collect()
+    assert calls == []
+    del v
+    gc.collect()
+    assert calls == [] and w["end_index"].tolist() == [4, 7]
+    del w
+    gc.collect()
+    assert calls == [(ctypes.addressof(raw), 8)]

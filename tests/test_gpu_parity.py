@@ -299,3 +299,29 @@ def test_device_resident_entry_and_overflow_retry():
     torch.cuda.synchronize()
     got = sorted(map(tuple, d_out.cpu().numpy().tolist()))
     assert got == sorted(want)
+
+
+@pytest.mark.gpu
+def test_records_are_handed_over_without_a_copy_and_stay_valid():
+    """acb_take_records: a result keeps its pinned buffer while any view of it is alive (a later scan must not
+    overwrite it), and the buffer is reused once the result is dropped"""
+    import gc
+    w = synth.make("C2", scale=0.004)
+    A = synth.build_automaton(w.keys)
+    first = A.find_all_batch(w.haystacks)
+    snap = (first.hay_id.copy(), first.end_index.copy(), first.key_id.copy())
+    addr = first.end_index.__array_interface__["data"][0]
+    other = A.find_all_batch(w.haystacks[::-1].copy())          # a different scan while `first` is still held
+    assert other.end_index.__array_interface__["data"][0] != addr
+    for got, want in zip((first.hay_id, first.end_index, first.key_id), snap):
+        assert np.array_equal(got, want)
+    again = A.find_all_batch(w.haystacks)
+    for got, want in zip((again.hay_id, again.end_index, again.key_id), snap):
+        assert np.array_equal(got, want)
+    del first, other, again
+    gc.collect()
+    for _ in range(3):                                          # steady state: results dropped before the next call
+        m = A.find_all_batch(w.haystacks)
+        assert np.array_equal(m.end_index, snap[1])
+        del m
+        gc.collect()
