@@ -78,3 +78,31 @@ def test_pinned_record_holder_releases_once_after_the_last_view():
     del w
     gc.collect()
     assert calls == [(ctypes.addressof(raw), 8)]
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/acb200.h is a C ABI: it compiles as C99 (-pedantic) and a C program links against libacb200.so"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.c"
+    src.write_text(
+        '#include "acb200.h"\n'
+        "int main(void) {\n"
+        "    acb_trie *t = acb_trie_new(1);\n"
+        "    int32_t prev = 0, built = 0, kid = -1, pre = 0;\n"
+        "    if (!t || acb_abi_version() != ACB_ABI_VERSION) return 1;\n"
+        '    if (acb_trie_add_word(t, (const uint8_t *)"he", 2, 0, &prev) != ACB_OK) return 2;\n'
+        "    if (acb_trie_make_automaton(t, &built) != ACB_OK || !built || acb_trie_kind(t) != ACB_AHOCORASICK) return 3;\n"
+        '    if (acb_trie_find(t, (const uint8_t *)"he", 2, &kid, &pre) != ACB_OK || kid != 0) return 4;\n'
+        "    acb_trie_free(t);\n"
+        "    return 0;\n"
+        "}\n")
+    libdir = os.path.dirname(N.LIB_PATH)
+    exe = tmp_path / "t"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-lacb200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
+    assert subprocess.run([str(exe)]).returncode == 0
