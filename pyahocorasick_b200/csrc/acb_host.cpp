@@ -323,24 +323,6 @@ static int ceil_log2_u64(uint64_t x) {
 
 } // namespace
 
-/* unique key below node v (live_below == 1): its id and all of its bytes */
-static int32_t unique_key_below(const acb_trie *t, int32_t v, std::vector<uint8_t> &bytes) {
-    size_t d = 0;
-    for (int32_t x = v; x > 0; x = t->nodes[x].parent) d++;
-    bytes.resize(d);
-    for (int32_t x = v; x > 0; x = t->nodes[x].parent) bytes[--d] = t->nodes[x].byte;
-    int32_t x = v;
-    while (t->nodes[x].key_id < 0) {
-        int32_t nxt = -1;
-        for (int32_t c = t->nodes[x].first_child; c >= 0; c = t->nodes[c].next_sibling)
-            if (t->nodes[c].live_below > 0) { nxt = c; break; }
-        if (nxt < 0) return -1;            /* cannot happen for live_below == 1 */
-        bytes.push_back(t->nodes[nxt].byte);
-        x = nxt;
-    }
-    return t->nodes[x].key_id;
-}
-
 /* Gram filter + anchor table (DESIGN.md "filter kernel").
  *
  * Every occurrence of a key K at byte position p contains exactly one probe position
@@ -360,7 +342,6 @@ static void build_filter(acb_trie *t, Flat &f) {
     const int m = f.min_key_bytes;
     /* live nodes down to depth m, with depths */
     std::vector<int32_t> depth(t->nodes.size(), -1);
-    std::vector<int32_t> upto_m;           /* nodes with 1 <= depth <= m */
     std::vector<std::vector<uint8_t>> prefixes;
     {
         std::vector<int32_t> stack;
@@ -369,7 +350,6 @@ static void build_filter(acb_trie *t, Flat &f) {
         while (!stack.empty()) {
             int32_t nd = stack.back();
             stack.pop_back();
-            if (depth[nd] > 0) upto_m.push_back(nd);
             if (depth[nd] == m) {
                 std::vector<uint8_t> p(m);
                 int32_t x = nd;
@@ -444,20 +424,59 @@ static void build_filter(acb_trie *t, Flat &f) {
 
     pt.lap("filter: bitmaps");
     /* ---- anchor table ---- */
-    struct Cand { Gram16 gram; int j; int32_t node; };
+    /* candidates: every live node at depth j + g (j a probe offset) with the last g bytes of its path.  One
+       LIFO walk with the path kept per depth -- no parent chasing; for a node with a single key below it the key
+       is read off right here (path + the one chain down to it). */
+    struct Cand { Gram16 gram; int j; int32_t node; int32_t uniq; };
+    struct Uniq { int32_t key_id; uint8_t len; uint8_t bytes[20]; };      /* len 255: longer than an entry can carry */
     std::vector<Cand> cands;
-    for (int32_t nd : upto_m) {
-        int d = depth[nd];
-        int j = d - g;
-        if (j < 0 || j > s - L || (j % L)) continue;
-        Cand c;
-        uint8_t gb[16] = {0};
-        int32_t x = nd;
-        for (int i = g - 1; i >= 0; i--) { gb[i] = t->nodes[x].byte; x = t->nodes[x].parent; }
-        c.gram = load_gram(gb, g);
-        c.j = j;
-        c.node = nd;
-        cands.push_back(c);
+    std::vector<Uniq> uniqs;
+    {
+        std::vector<uint8_t> path((size_t)m + 1, 0);
+        std::vector<int32_t> stack;
+        stack.push_back(0);
+        while (!stack.empty()) {
+            const int32_t nd = stack.back();
+            stack.pop_back();
+            const int d = depth[nd];
+            if (d > 0) {
+                path[d - 1] = t->nodes[nd].byte;
+                const int j = d - g;
+                if (j >= 0 && j <= s - L && (j % L) == 0) {
+                    Cand c;
+                    c.gram = load_gram(&path[d - g], g);
+                    c.j = j;
+                    c.node = nd;
+                    c.uniq = -1;
+                    if (t->nodes[nd].live_below == 1) {
+                        Uniq u;
+                        u.key_id = -1;
+                        u.len = 255;
+                        uint8_t kb[20];
+                        int n = 0;
+                        bool fits = d <= 20;
+                        if (fits) { memcpy(kb, path.data(), (size_t)d); n = d; }
+                        int32_t x = nd;
+                        while (fits && t->nodes[x].key_id < 0) {
+                            int32_t nxt = -1;
+                            for (int32_t ch = t->nodes[x].first_child; ch >= 0; ch = t->nodes[ch].next_sibling)
+                                if (t->nodes[ch].live_below > 0) { nxt = ch; break; }
+                            if (nxt < 0) { fits = false; break; }            /* cannot happen for live_below == 1 */
+                            if (n == 20) { fits = false; break; }
+                            kb[n++] = t->nodes[nxt].byte;
+                            x = nxt;
+                        }
+                        if (fits) { u.key_id = t->nodes[x].key_id; u.len = (uint8_t)n; memcpy(u.bytes, kb, (size_t)n); }
+                        c.uniq = (int32_t)uniqs.size();
+                        uniqs.push_back(u);
+                    }
+                    cands.push_back(c);
+                }
+            }
+            if (d < m)
+                for (int32_t ch = t->nodes[nd].first_child; ch >= 0; ch = t->nodes[ch].next_sibling)
+                    if (t->nodes[ch].live_below > 0) stack.push_back(ch);
+        }
     }
     std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) {      /* groups (j, gram); any total order will do */
         if (a.j != b.j) return a.j < b.j;
@@ -466,7 +485,6 @@ static void build_filter(acb_trie *t, Flat &f) {
     });
     struct Entry { uint32_t w[8]; };
     std::vector<Entry> entries, group;
-    std::vector<uint8_t> kb;
     entries.reserve(cands.size());
     auto pack = [](Entry &e, uint32_t tag, int32_t key_id, int j, int len, const uint8_t *bytes) {
         memset(&e, 0, sizeof(e));
@@ -482,12 +500,11 @@ static void build_filter(acb_trie *t, Flat &f) {
         bool multi = false;
         group.clear();
         for (size_t i = a; i < b && !multi; i++) {
-            const Node &nd = t->nodes[cands[i].node];
-            if (nd.live_below != 1) { multi = true; break; }
-            int32_t kid = unique_key_below(t, cands[i].node, kb);
-            if (kid < 0 || kb.size() > 20) { multi = true; break; }
+            if (cands[i].uniq < 0) { multi = true; break; }                /* more than one key below the node */
+            const Uniq &u = uniqs[cands[i].uniq];
+            if (u.key_id < 0 || u.len > 20) { multi = true; break; }
             Entry e;
-            pack(e, tag, kid, cands[a].j, (int)kb.size(), kb.data());
+            pack(e, tag, u.key_id, cands[a].j, (int)u.len, u.bytes);
             group.push_back(e);
         }
         if (multi) {
