@@ -863,7 +863,7 @@ class AutomatonSearchIter:
                 if self._hist.dtype != old.dtype:
                     self._hist = self._hist.astype(old.dtype)
             hist = np.concatenate([self._hist, old])
-            self._hist = hist[len(hist) - keep:] if keep else hist[:0]
+            self._hist = hist[max(len(hist) - keep, 0):] if keep else hist[:0]
             # outputs of the current position not yet returned stay pending (iter->output survives set())
             if not self._pending:
                 self._pending = [k for i, k in self._matches[self._cursor:] if i == self._index]

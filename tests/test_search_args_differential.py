@@ -1,0 +1,109 @@
+"""iter() / find_all() argument handling against the reference extension, randomised: start / end (negative too),
+ignore_white_space, find_all's callback form, chunked iteration with set() at random points.  The device is
+the CPU emulation (tests/emul.py); what is under test is the host layer's index arithmetic and state carry-over
+(src/Automaton.c:875-966, src/utils.c:293-359, src/AutomatonSearchIter.c:243-368)."""
+import numpy as np
+import pytest
+
+import emul
+import oracle
+import pyahocorasick_b200 as pkg
+
+pytestmark = pytest.mark.skipif(not oracle.ref_available("bytes"), reason="needs oracle/_ref")
+
+
+def _pair(fl, rng, with_space):
+    ref, mod = oracle.ref_module(fl), pkg.flavour(fl)
+    al = "abc " if with_space else "abc"
+
+    def word(lo, hi, alphabet=al):
+        s = "".join(alphabet[int(j)] for j in rng.integers(0, len(alphabet), size=int(rng.integers(lo, hi))))
+        return s.encode() if fl == "bytes" else s
+
+    keys = list({word(1, 5, "abc") for _ in range(int(rng.integers(1, 9)))})
+    A, R = mod.Automaton(), ref.Automaton()
+    for i, k in enumerate(keys):
+        A.add_word(k, i), R.add_word(k, i)
+    A.make_automaton(), R.make_automaton()
+    return A, R, word
+
+
+def _call(fn, *a, **kw):
+    try:
+        return ("ok", list(fn(*a, **kw)))
+    except Exception as e:                       # same exception type is part of the contract
+        return ("exc", type(e).__name__)
+
+
+@pytest.mark.parametrize("fl", ["bytes", "unicode"])
+def test_iter_ranges_and_white_space(fl, monkeypatch):
+    emul.install(monkeypatch, "filter")
+    rng = np.random.default_rng(21)
+    for _ in range(120):
+        A, R, word = _pair(fl, rng, with_space=True)
+        hay = word(0, 30)
+        n = len(hay)
+        for _ in range(6):
+            # iter() takes start / end as they come (:953-959): -1 means "default", any other negative start and any
+            # end past the buffer make the reference read outside it -- undefined, so not part of the contract
+            args = [hay]
+            if rng.integers(0, 3):
+                args.append(int(rng.integers(-1, n + 4)))
+                if rng.integers(0, 2):
+                    args.append(int(rng.integers(-1, n + 1)))
+            kw = {"ignore_white_space": True} if rng.integers(0, 3) == 0 else {}
+            assert _call(A.iter, *args, **kw) == _call(R.iter, *args, **kw), (fl, hay, args, kw)
+
+
+@pytest.mark.parametrize("fl", ["bytes", "unicode"])
+def test_find_all_ranges(fl, monkeypatch):
+    emul.install(monkeypatch, "filter")
+    rng = np.random.default_rng(22)
+    for _ in range(100):
+        A, R, word = _pair(fl, rng, with_space=False)
+        hay = word(0, 30)
+        n = len(hay)
+        for _ in range(5):
+            extra = []
+            if rng.integers(0, 3):
+                extra.append(int(rng.integers(-n - 3, n + 4)))
+                if rng.integers(0, 2):
+                    extra.append(int(rng.integers(-n - 3, n + 4)))
+            got, want = [], []
+
+            def run(X, acc):
+                try:
+                    X.find_all(hay, lambda i, v: acc.append((i, v)), *extra)
+                    return "ok"
+                except Exception as e:
+                    return type(e).__name__
+            assert (run(A, got), got) == (run(R, want), want), (fl, hay, extra)
+
+
+@pytest.mark.parametrize("ws", [False, True])
+@pytest.mark.parametrize("fl", ["bytes", "unicode"])
+def test_iter_set_at_random_points(fl, ws, monkeypatch):
+    """chunks shorter than the longest key (the history then holds everything seen so far), empty chunks, extra
+    next() calls past exhaustion (each moves the reference's index on by one), reset, ignore_white_space"""
+    emul.install(monkeypatch, "filter")
+    rng = np.random.default_rng(23 + ws)
+    kw = {"ignore_white_space": True} if ws else {}
+    for _ in range(150):
+        A, R, word = _pair(fl, rng, with_space=ws)
+        chunks = [word(0, 14) for _ in range(4)]
+        ia, ir = A.iter(chunks[0], **kw), R.iter(chunks[0], **kw)
+        got, want = [], []
+        for c in chunks[1:] + [None]:
+            for _ in range(int(rng.integers(0, 7))):
+                for it, acc in ((ir, want), (ia, got)):
+                    try:
+                        acc.append(next(it))
+                    except StopIteration:
+                        acc.append("stop")
+            if c is None:
+                break
+            reset = bool(rng.integers(0, 4) == 0)
+            ir.set(c, reset), ia.set(c, reset)
+        got += list(ia)
+        want += list(ir)
+        assert got == want, (fl, chunks)
