@@ -107,3 +107,52 @@ def test_iter_set_at_random_points(fl, ws, monkeypatch):
         got += list(ia)
         want += list(ir)
         assert got == want, (fl, chunks)
+
+
+@pytest.mark.parametrize("fl", ["bytes", "unicode"])
+def test_batch_input_forms_equal_looping_the_reference(fl, monkeypatch):
+    """find_all_batch over a list, over (flat, offsets), over a uint8 matrix == iter() of the reference per haystack"""
+    emul.install(monkeypatch, "filter")
+    ref, mod = oracle.ref_module(fl), pkg.flavour(fl)
+    rng = np.random.default_rng(31)
+    al = "abł" if fl == "unicode" else "abc"
+
+    def word(lo, hi):
+        s = "".join(al[int(j)] for j in rng.integers(0, len(al), size=int(rng.integers(lo, hi))))
+        return s.encode() if fl == "bytes" else s
+
+    for _ in range(60):
+        keys = list({word(1, 6) for _ in range(int(rng.integers(1, 8)))})
+        A, R = mod.Automaton(), ref.Automaton()
+        for i, k in enumerate(keys):
+            A.add_word(k, (i, k)), R.add_word(k, (i, k))
+        A.make_automaton(), R.make_automaton()
+        hays = [word(0, 20) for _ in range(int(rng.integers(0, 6)))]
+        want = [(h, e, v) for h, hay in enumerate(hays) for e, v in R.iter(hay)]
+        m = A.find_all_batch(hays)
+        assert list(m) == want
+        assert m.per_haystack(len(hays)) == [list(R.iter(h)) for h in hays]
+        if fl == "bytes" and hays:
+            flat = np.frombuffer(b"".join(hays), dtype=np.uint8)
+            off = np.concatenate([[0], np.cumsum([len(h) for h in hays])]).astype(np.int64)
+            assert list(A.find_all_batch((flat, off))) == want
+            rows = rng.integers(97, 100, size=(int(rng.integers(1, 5)), int(rng.integers(1, 12))), dtype=np.uint8)
+            assert list(A.find_all_batch(rows)) == [(h, e, v) for h in range(rows.shape[0]) for e, v in R.iter(rows[h].tobytes())]
+
+
+@pytest.mark.parametrize("fl", ["bytes", "unicode"])
+def test_key_sequences_iter_and_iter_long(fl, monkeypatch):
+    emul.install(monkeypatch, "filter")
+    ref, mod = oracle.ref_module(fl), pkg.flavour(fl)
+    rng = np.random.default_rng(32)
+    vals = [0, 1, 97, 255, 256, 65535 if fl == "bytes" else 2 ** 32 - 1]
+    for _ in range(80):
+        keys = list({tuple(int(vals[j]) for j in rng.integers(0, len(vals), size=int(rng.integers(1, 5))))
+                     for _ in range(int(rng.integers(1, 6)))})
+        A, R = mod.Automaton(mod.STORE_INTS, mod.KEY_SEQUENCE), ref.Automaton(ref.STORE_INTS, ref.KEY_SEQUENCE)
+        for i, k in enumerate(keys):
+            A.add_word(k, i), R.add_word(k, i)
+        A.make_automaton(), R.make_automaton()
+        hay = tuple(int(vals[j]) for j in rng.integers(0, len(vals), size=int(rng.integers(0, 25))))
+        assert list(A.iter(hay)) == list(R.iter(hay))
+        assert list(A.iter_long(hay)) == list(R.iter_long(hay))
