@@ -115,3 +115,32 @@ def test_wildcards_stores_and_errors(fl):
         A.add_word(c("new"), 3)
         with pytest.raises(ValueError):
             next(it)
+
+
+@pytest.mark.parametrize("fl", ["bytes", "unicode"])
+def test_get_stats_counts_the_letter_trie_like_the_reference(fl):
+    """nodes / links / words / longest_word of get_stats() (src/Automaton.c:1044-1097) after random add_word /
+    remove_word / make_automaton / clear -- also for 4-byte letters, where the host arena holds one node per byte"""
+    ref, mod = oracle.ref_module(fl), ac.flavour(fl)
+    rng = np.random.default_rng(77)
+    al = "ab\u0142\U0001f600" if fl == "unicode" else "abc"
+
+    def word():
+        s = "".join(al[int(j)] for j in rng.integers(0, len(al), size=int(rng.integers(1, 7))))
+        return s.encode() if fl == "bytes" else s
+
+    for _ in range(120):
+        A, R = mod.Automaton(), ref.Automaton()
+        ws = [word() for _ in range(int(rng.integers(0, 10)))]
+        for i, w in enumerate(ws):
+            A.add_word(w, i), R.add_word(w, i)
+        for w in ws[::3]:
+            assert A.remove_word(w) == R.remove_word(w)
+        if rng.integers(0, 2) and len(R):
+            A.make_automaton(), R.make_automaton()
+        if rng.integers(0, 6) == 0:
+            A.clear(), R.clear()
+        a, r = A.get_stats(), R.get_stats()
+        assert sorted(a) == sorted(r)
+        for k in ("nodes_count", "words_count", "longest_word", "links_count"):
+            assert a[k] == r[k], (k, ws)

@@ -115,7 +115,7 @@ def test_batch_input_forms_equal_looping_the_reference(fl, monkeypatch):
     emul.install(monkeypatch, "filter")
     ref, mod = oracle.ref_module(fl), pkg.flavour(fl)
     rng = np.random.default_rng(31)
-    al = "abł" if fl == "unicode" else "abc"
+    al = "ab\u0142" if fl == "unicode" else "abc"
 
     def word(lo, hi):
         s = "".join(al[int(j)] for j in rng.integers(0, len(al), size=int(rng.integers(lo, hi))))
