@@ -9,7 +9,7 @@ import emul
 import oracle
 import pyahocorasick_b200 as pkg
 
-pytestmark = pytest.mark.skipif(not oracle.ref_available("bytes"), reason="needs oracle/_ref")
+needs_ref = pytest.mark.skipif(not oracle.ref_available("bytes"), reason="needs oracle/_ref")
 
 
 def _pair(fl, rng, with_space):
@@ -35,6 +35,7 @@ def _call(fn, *a, **kw):
         return ("exc", type(e).__name__)
 
 
+@needs_ref
 @pytest.mark.parametrize("fl", ["bytes", "unicode"])
 def test_iter_ranges_and_white_space(fl, monkeypatch):
     emul.install(monkeypatch, "filter")
@@ -55,6 +56,7 @@ def test_iter_ranges_and_white_space(fl, monkeypatch):
             assert _call(A.iter, *args, **kw) == _call(R.iter, *args, **kw), (fl, hay, args, kw)
 
 
+@needs_ref
 @pytest.mark.parametrize("fl", ["bytes", "unicode"])
 def test_find_all_ranges(fl, monkeypatch):
     emul.install(monkeypatch, "filter")
@@ -80,6 +82,7 @@ def test_find_all_ranges(fl, monkeypatch):
             assert (run(A, got), got) == (run(R, want), want), (fl, hay, extra)
 
 
+@needs_ref
 @pytest.mark.parametrize("ws", [False, True])
 @pytest.mark.parametrize("fl", ["bytes", "unicode"])
 def test_iter_set_at_random_points(fl, ws, monkeypatch):
@@ -109,6 +112,7 @@ def test_iter_set_at_random_points(fl, ws, monkeypatch):
         assert got == want, (fl, chunks)
 
 
+@needs_ref
 @pytest.mark.parametrize("fl", ["bytes", "unicode"])
 def test_batch_input_forms_equal_looping_the_reference(fl, monkeypatch):
     """find_all_batch over a list, over (flat, offsets), over a uint8 matrix == iter() of the reference per haystack"""
@@ -140,6 +144,7 @@ def test_batch_input_forms_equal_looping_the_reference(fl, monkeypatch):
             assert list(A.find_all_batch(rows)) == [(h, e, v) for h in range(rows.shape[0]) for e, v in R.iter(rows[h].tobytes())]
 
 
+@needs_ref
 @pytest.mark.parametrize("fl", ["bytes", "unicode"])
 def test_key_sequences_iter_and_iter_long(fl, monkeypatch):
     emul.install(monkeypatch, "filter")
@@ -156,3 +161,38 @@ def test_key_sequences_iter_and_iter_long(fl, monkeypatch):
         hay = tuple(int(vals[j]) for j in rng.integers(0, len(vals), size=int(rng.integers(0, 25))))
         assert list(A.iter(hay)) == list(R.iter(hay))
         assert list(A.iter_long(hay)) == list(R.iter_long(hay))
+
+
+def test_streaming_over_mixed_narrow_and_wide_chunks_equals_the_oracle(monkeypatch):
+    """unicode flavour, chunks that are latin-1 (scanned with the 1-byte automaton) and chunks that are not, set() at
+    random points: against the C restatement (oracle/ac_oracle.c), which has no storage-kind special cases"""
+    emul.install(monkeypatch, "filter")
+    rng = np.random.default_rng(5)
+    mod = pkg.flavour("unicode")
+
+    def word(al, lo, hi):
+        return "".join(al[int(j)] for j in rng.integers(0, len(al), size=int(rng.integers(lo, hi))))
+
+    for _ in range(250):
+        kal = ["ab\xe9", "abł", "ab\xe9ł\U0001f600"][int(rng.integers(0, 3))]
+        keys = list({word(kal, 1, 6) for _ in range(int(rng.integers(1, 7)))})
+        A, O = mod.Automaton(mod.STORE_INTS), oracle.OracleAutomaton()
+        for i, k in enumerate(keys):
+            A.add_word(k, i), O.add_word(k, i)
+        A.make_automaton(), O.make_automaton()
+        chunks = [word(["ab\xe9", "abł\U0001f600", "ab"][int(rng.integers(0, 3))], 0, 12) for _ in range(int(rng.integers(1, 6)))]
+        ia, io = A.iter(chunks[0]), O.iter(chunks[0])
+        got, want = [], []
+        for ci in range(len(chunks)):
+            for _ in range(int(rng.integers(0, 6))):
+                for it, acc in ((io, want), (ia, got)):
+                    try:
+                        acc.append(next(it))
+                    except StopIteration:
+                        acc.append("stop")
+            if ci + 1 < len(chunks):
+                reset = bool(rng.integers(0, 5) == 0)
+                io.set(chunks[ci + 1], reset), ia.set(chunks[ci + 1], reset)
+        got += list(ia)
+        want += list(io)
+        assert got == want, (keys, chunks)
