@@ -196,3 +196,30 @@ def test_streaming_over_mixed_narrow_and_wide_chunks_equals_the_oracle(monkeypat
         got += list(ia)
         want += list(io)
         assert got == want, (keys, chunks)
+
+
+@needs_ref
+@pytest.mark.parametrize("fl", ["bytes", "unicode"])
+def test_ignore_white_space_uses_the_c_library_classes(fl, monkeypatch):
+    """which letters count as white space is libc's business (iswspace / isspace, src/AutomatonSearchIter.c:265-270):
+    control characters, NEL, no-break space, and for the unicode build the wide ones"""
+    emul.install(monkeypatch, "filter")
+    ref, mod = oracle.ref_module(fl), pkg.flavour(fl)
+    rng = np.random.default_rng(9)
+    ws = [" ", "\t", "\n", "\x0b", "\x0c", "\r", "\x85", "\xa0", "\x1c", "\x1f"]
+    if fl == "unicode":
+        ws += [" ", "　", "​", " "]
+    al = list("ab") + ws
+
+    def word(lo, hi, alphabet):
+        s = "".join(alphabet[int(j)] for j in rng.integers(0, len(alphabet), size=int(rng.integers(lo, hi))))
+        return s.encode("latin-1") if fl == "bytes" else s
+
+    for _ in range(150):
+        keys = list({word(1, 5, list("ab")) for _ in range(int(rng.integers(1, 6)))})
+        A, R = mod.Automaton(), ref.Automaton()
+        for i, k in enumerate(keys):
+            A.add_word(k, i), R.add_word(k, i)
+        A.make_automaton(), R.make_automaton()
+        hay = word(0, 25, al)
+        assert list(A.iter(hay, ignore_white_space=True)) == list(R.iter(hay, ignore_white_space=True)), (keys, hay)
