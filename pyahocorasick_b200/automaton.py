@@ -552,7 +552,9 @@ class Automaton:
         S, K = fv.n_states, fv.n_classes
 
         def arr(p, n, dt):
-            return np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].astype(dt, copy=True)
+            if n == 0 or not p:                       # e.g. no outputs at all once every key has been removed
+                return np.empty(0, dtype=dt)
+            return np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True)
         n_out = int(np.ctypeslib.as_array(fv.out_ptr, shape=(S + 1,))[S])
         return dict(
             n_states=S, n_classes=K, n_keys=fv.n_keys, letter_bytes=fv.letter_bytes,

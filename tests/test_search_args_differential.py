@@ -223,3 +223,46 @@ def test_ignore_white_space_uses_the_c_library_classes(fl, monkeypatch):
         A.make_automaton(), R.make_automaton()
         hay = word(0, 25, al)
         assert list(A.iter(hay, ignore_white_space=True)) == list(R.iter(hay, ignore_white_space=True)), (keys, hay)
+
+
+@needs_ref
+@pytest.mark.parametrize("fl", ["bytes", "unicode"])
+def test_searches_between_random_mutations(fl, monkeypatch):
+    """add_word / remove_word / make_automaton in random order, searching whenever the reference can (and raising
+    like it when it cannot) -- including automata from which every key has been removed again"""
+    emul.install(monkeypatch, "filter")
+    ref, mod = oracle.ref_module(fl), pkg.flavour(fl)
+    rng = np.random.default_rng(13)
+    al = "abc" if fl == "bytes" else "abł"
+
+    def word(lo, hi):
+        s = "".join(al[int(j)] for j in rng.integers(0, len(al), size=int(rng.integers(lo, hi))))
+        return s.encode() if fl == "bytes" else s
+
+    def outcome(X, hay):
+        try:
+            return list(X.iter(hay))
+        except Exception as e:
+            return type(e).__name__
+
+    for _ in range(120):
+        A, R = mod.Automaton(), ref.Automaton()
+        first = word(1, 2)
+        A.add_word(first, -1), R.add_word(first, -1)            # the reference asserts on a never-filled trie
+        for _ in range(int(rng.integers(3, 25))):
+            op, w = int(rng.integers(0, 10)), word(1, 6)
+            if op < 5:
+                v = int(rng.integers(0, 100))
+                assert A.add_word(w, v) == R.add_word(w, v)
+            elif op < 7:
+                assert A.remove_word(w) == R.remove_word(w)
+            elif op < 9:
+                assert A.make_automaton() == R.make_automaton()
+                if R.kind == ref.AHOCORASICK:
+                    hay = word(0, 30)
+                    assert list(A.iter(hay)) == list(R.iter(hay))
+                    assert list(A.iter_long(hay)) == list(R.iter_long(hay))
+            else:
+                hay = word(0, 12)
+                assert outcome(A, hay) == outcome(R, hay)
+        assert len(A) == len(R) and A.kind == R.kind
