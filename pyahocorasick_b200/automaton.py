@@ -649,7 +649,9 @@ class Automaton:
         return rec
 
     def _scan_one(self, letters: np.ndarray, algo: str = "auto") -> np.ndarray:
-        narrow = self._uses_narrow() and letters.dtype == np.uint8
+        narrow = self._uses_narrow() and letters.dtype == np.uint8 and algo != "long"
+        if self._uses_narrow() and letters.dtype == np.uint8 and not narrow:
+            letters = letters.astype("<u4")                  # iter_long never runs on the latin-1 automaton
         flat = np.ascontiguousarray(letters).view(np.uint8)
         if flat.size == 0:
             return np.empty(0, dtype=N.MATCH_DTYPE)
@@ -720,7 +722,7 @@ class Automaton:
             raise AttributeError("not an automaton yet; add some words and call make_automaton")
         if len(args) < 1:
             raise IndexError("tuple index out of range")
-        letters = self._hay_letters(args[0], required=True)
+        letters = self._letters(args[0], required=True)      # never the latin-1 automaton: see find_all_batch
         start, end = _parse_start_end(args, 1, 2, 0, len(letters))
         return AutomatonSearchIterLong(self, letters, start, end)
 
@@ -774,7 +776,11 @@ class Automaton:
             n = len(offs) - 1
             rec = self._scan_flat(flat, offs, n, 0, algo=algo, sort=sort, device=device) if n and flat.size else np.empty(0, dtype=N.MATCH_DTYPE)
             return Matches(rec, self._values)
-        letters = [self._hay_letters(h, required=True) for h in haystacks]
+        # the latin-1 automaton finds exactly the matches of a latin-1 haystack -- all of them.  iter_long's walk is
+        # different: which match it keeps depends on the whole trie (a non-latin-1 key whose prefix is latin-1 adds
+        # nodes the walk passes through, src/AutomatonSearchIterLong.c:118-126), so it always runs on the full one
+        get = self._letters if algo == "long" else self._hay_letters
+        letters = [get(h, required=True) for h in haystacks]
         narrow = self._uses_narrow() and len(letters) > 0 and all(a.dtype == np.uint8 for a in letters)
         if self._uses_narrow() and not narrow:                   # mixed batch: everything at 4 bytes per letter
             letters = [a.astype("<u4") if a.dtype == np.uint8 else a for a in letters]
@@ -946,7 +952,7 @@ class AutomatonSearchIterLong:
         the current index to the offset of the reported positions -- unless `reset`."""
         if len(args) < 1:
             raise IndexError("tuple index out of range")
-        letters = self._A._hay_letters(args[0], required=True)
+        letters = self._A._letters(args[0], required=True)
         reset = bool(args[1]) if len(args) >= 2 else False
         if reset:
             self._shift = 0
