@@ -266,3 +266,35 @@ def test_searches_between_random_mutations(fl, monkeypatch):
                 hay = word(0, 12)
                 assert outcome(A, hay) == outcome(R, hay)
         assert len(A) == len(R) and A.kind == R.kind
+
+
+@needs_ref
+@pytest.mark.parametrize("fl", ["bytes", "unicode"])
+def test_iter_long_ranges_and_batch(fl, monkeypatch):
+    """iter_long(string, [start, [end]]) uses find_all's range rules (src/Automaton.c:968-1040); find_long_batch ==
+    looping it.  The unicode key sets mix latin-1 and other letters over latin-1 haystacks on purpose."""
+    emul.install(monkeypatch, "filter")
+    ref, mod = oracle.ref_module(fl), pkg.flavour(fl)
+    rng = np.random.default_rng(17)
+    al = "abc" if fl == "bytes" else "abł"
+
+    def word(lo, hi):
+        s = "".join(al[int(j)] for j in rng.integers(0, len(al), size=int(rng.integers(lo, hi))))
+        return s.encode() if fl == "bytes" else s
+
+    for _ in range(120):
+        keys = list({word(1, 6) for _ in range(int(rng.integers(1, 8)))})
+        A, R = mod.Automaton(), ref.Automaton()
+        for i, k in enumerate(keys):
+            A.add_word(k, i), R.add_word(k, i)
+        A.make_automaton(), R.make_automaton()
+        hays = [word(0, 25) for _ in range(int(rng.integers(1, 5)))]
+        assert list(A.find_long_batch(hays)) == [(h, e, v) for h, hay in enumerate(hays) for e, v in R.iter_long(hay)]
+        for hay in hays:
+            n = len(hay)
+            args = [hay]
+            if rng.integers(0, 2):
+                args.append(int(rng.integers(-n - 2, n + 3)))
+                if rng.integers(0, 2):
+                    args.append(int(rng.integers(-n - 2, n + 3)))
+            assert _call(A.iter_long, *args) == _call(R.iter_long, *args), (keys, args)
