@@ -51,7 +51,7 @@ def _worker_body(rank, world, port, n_hay, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_hay", [37, 64])
+@pytest.mark.parametrize("n_hay", [1, 37, 64])
 def test_two_rank_sharded_scan(n_hay):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
