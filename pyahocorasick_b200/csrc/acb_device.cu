@@ -1,30 +1,32 @@
 /*
- * acb_device.cu -- sm_100a scan kernels and the device half of the C ABI.
+ * acb_device.cu -- sm_100a scan kernels and the device half of the C ABI (include/acb200.h).
  *
  * ACB_ALGO_FILTER (the fast path) is two launches per <= 2 GiB segment of the batch:
  *
- *  acb_filter_kernel<NW,STRIDE> streams the haystack bytes once (stage 1); each warp resolves
- *  its own survivors between work units (stage 2/3) while the other warps keep streaming.
- *  Only when a warp's queue overflows are candidates spilled to a global list, which
- *  acb_verify_kernel resolves afterwards (normally that list is empty).
- *      Start-anchored search.  Every probe position is first tested against a gram
- *      bitmap held in shared memory (stage 1).  Survivors look their gram up in the
- *      anchor table in global memory (stage 2, one 32-byte slot): a UNIQUE anchor
- *      carries the only key that can match there, which is compared with the text
- *      directly; a MULTI anchor (keys sharing that prefix) walks the trie through
- *      the column-major goto table (stage 3).  No failure links are followed: an
- *      occurrence is found exactly once, from its first byte, so the result set
- *      equals what the reference produces by walking fail chains at every position
+ *  acb_filter_kernel<NW,STRIDE,WIDE>   persistent, one CTA per SM; streams the haystack bytes once.
+ *      Start-anchored search.  Every probe position is tested against the stage-1 gram filter in shared memory
+ *      (a blocked Bloom filter, two bits per gram in one word).  The rare survivors are hashed a second time
+ *      and tested against stage 2 (shared memory) and, for large key sets, stage 3 (global memory), then queued
+ *      per warp.  Between work units a warp resolves its queue through the anchor table in global memory (one
+ *      32-byte slot): a UNIQUE anchor carries the only key that can match there, which is compared with the
+ *      text directly; a MULTI anchor (keys sharing that prefix) walks the trie through the column-major goto
+ *      table.  No failure links are followed: an occurrence is found exactly once, from its first byte, so the
+ *      result set equals what the reference produces by walking fail chains at every position
  *      (src/AutomatonSearchIter.c:157-197, src/Automaton.c:693-714).
+ *  acb_verify_kernel                   resolves the candidates a warp had to spill to the global list because
+ *      its queue was full (normally none), re-arms the counters, flags an overflowed list.
  *
- *  acb_dfa_kernel                 (ACB_ALGO_DFA)
- *      The textbook automaton: goto, else fail until root (src/trie.c:177-194),
- *      outputs from CSR lists.  One lane per 64-byte span with a max_key-1 byte
- *      warm-up.  Slower (every byte is a dependent L2 lookup) but insensitive to
- *      key-set shape; also used to cross-check the filter kernel on the GPU.
+ *  acb_dfa_kernel                      (ACB_ALGO_DFA)
+ *      The textbook automaton: goto, else fail until root (src/trie.c:177-194), outputs from CSR lists.  One
+ *      lane per 64-byte span with a max_key-1 byte warm-up.  Slower (every byte is a dependent L2 lookup) but
+ *      insensitive to key-set shape; also used to cross-check the filter kernel on the GPU.
  *
- * Match records are compacted per warp in shared memory and appended to the
- * global buffer with one atomicAdd per warp flush.
+ *  acb_long_kernel                     (ACB_ALGO_LONG)
+ *      iter_long: the reference's longest-match walk (src/AutomatonSearchIterLong.c:89-153) replayed letter by
+ *      letter on the flattened tables, one lane per haystack.
+ *
+ * Match records are compacted per warp in shared memory and appended to the global buffer with one atomicAdd
+ * per warp flush; acb_sort_matches_device puts them into the reference's order with one radix sort.
  */
 #include "acb_internal.h"
 #include "acb_hash.h"
