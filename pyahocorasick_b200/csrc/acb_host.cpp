@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <new>
 #include <vector>
 
@@ -830,6 +831,9 @@ extern "C" int acb_trie_export_nodes(const acb_trie *t, int letter_width, const 
     } catch (const std::bad_alloc &) {
         acb_set_error("out of memory");
         return ACB_ENOMEM;
+    } catch (const std::exception &e) {                      /* e.g. std::length_error: nothing may cross the C ABI */
+        acb_set_error("%s", e.what());
+        return ACB_EINVAL;
     }
 }
 
@@ -845,6 +849,11 @@ extern "C" int acb_trie_import_nodes(acb_trie *t, const uint8_t *buf, int64_t le
     if (key_need) *key_need = 0;
     if (key_off && cap_keys >= 0) key_off[0] = 0;
     if (n_nodes == 0) return ACB_OK;
+    if (n_nodes > len / (kNodeRecBytes + (mode == ACB_NODES_SAVE ? 8 : 0))) {     /* before anything is sized by it */
+        acb_set_error("%lld nodes announced, but the data can hold at most %lld", (long long)n_nodes,
+                      (long long)(len / (kNodeRecBytes + (mode == ACB_NODES_SAVE ? 8 : 0))));
+        return ACB_EINVAL;
+    }
     try {
         const int L = t->letter_bytes;
         const int pair_bytes = letter_width + 8;
@@ -950,6 +959,9 @@ extern "C" int acb_trie_import_nodes(acb_trie *t, const uint8_t *buf, int64_t le
     } catch (const std::bad_alloc &) {
         acb_set_error("out of memory");
         return ACB_ENOMEM;
+    } catch (const std::exception &e) {                      /* e.g. std::length_error: nothing may cross the C ABI */
+        acb_set_error("%s", e.what());
+        return ACB_EINVAL;
     }
 }
 

@@ -207,6 +207,10 @@ def test_argument_rules_and_malformed_input(tmp_path):
         open(p, "wb").write(bad)
         with pytest.raises(exc):
             mod.load(p, pickle.loads)
+    huge = good[:-24] + struct.pack("<Q", 1 << 50) + good[-16:]     # footer announces 2^50 nodes
+    open(p, "wb").write(huge)
+    with pytest.raises(ValueError, match="nodes announced"):
+        mod.load(p, pickle.loads)
     # constructor (src/Automaton.c:106-147, src/Automaton_pickle.c:270-303)
     args = serialize.reduce_args(A)
     with pytest.raises(TypeError, match="Expected list"):
