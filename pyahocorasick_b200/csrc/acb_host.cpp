@@ -195,6 +195,9 @@ extern "C" int acb_trie_add_word(acb_trie *t, const uint8_t *key, int64_t nbytes
     } catch (const std::bad_alloc &) {
         acb_set_error("out of memory");
         return ACB_ENOMEM;
+    } catch (const std::exception &e) {
+        acb_set_error("add_word: %s", e.what());
+        return ACB_ERANGE;
     }
 }
 
@@ -683,6 +686,10 @@ extern "C" int acb_trie_make_automaton(acb_trie *t, int32_t *built) {
         t->flat = Flat();
         acb_set_error("out of memory while flattening");
         return ACB_ENOMEM;
+    } catch (const std::exception &e) {                      /* std::length_error etc.: nothing may cross the C ABI */
+        t->flat = Flat();
+        acb_set_error("make_automaton: %s", e.what());
+        return ACB_ERANGE;
     }
 }
 
