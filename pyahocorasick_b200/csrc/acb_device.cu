@@ -41,6 +41,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <new>
 #include <vector>
 
@@ -823,9 +824,16 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         tb->min_key_bytes = f.min_key_bytes; tb->max_key_bytes = f.max_key_bytes;
         acb_hash_multipliers(tb->gram, 1, tb->mul1);
         acb_hash_multipliers(tb->gram, 2, tb->mul2);
-        tb->key_len.assign(f.key_len, f.key_len + f.n_keys);
         /* goto entries get a flag bit when the child ends a key, saving a key_of lookup per step */
-        std::vector<int32_t> flagged((size_t)f.n_classes * f.n_states);
+        std::vector<int32_t> flagged;
+        try {
+            tb->key_len.assign(f.key_len, f.key_len + f.n_keys);
+            flagged.resize((size_t)f.n_classes * f.n_states);
+        } catch (const std::exception &) {                   /* nothing may cross the C ABI */
+            acb_set_error("out of host memory while staging the tables");
+            rc = ACB_ENOMEM;
+            break;
+        }
         for (size_t i = 0; i < flagged.size(); i++) {
             int32_t v = f.goto_cm[i];
             flagged[i] = (v >= 0 && f.key_of[v] >= 0) ? (v | kTermBit) : v;
