@@ -221,6 +221,21 @@ class Automaton:
             raise TypeError("bytes required" if required else "bytes expected")
         return np.frombuffer(obj, dtype=np.uint8)
 
+    def _raw_key(self, key):
+        """key object -> (its letters as bytes, number of letters), without the numpy detour for plain string
+        keys: the dict-like methods are called once per key, not once per batch"""
+        if self._key_type == KEY_STRING:
+            if self._UNICODE:
+                if not isinstance(key, str):
+                    raise TypeError("string expected")
+                raw = key.encode("utf-32-le", "surrogatepass")
+                return raw, len(raw) >> 2
+            if not isinstance(key, bytes):
+                raise TypeError("bytes expected")
+            return key, len(key)
+        letters = self._letters(key)
+        return letters.tobytes(), len(letters)
+
     def _hashable(self, key):
         return key
 
@@ -241,8 +256,7 @@ class Automaton:
         if not args:
             raise TypeError("add_word() requires a key")      # PyTuple_GetItem -> IndexError in the reference
         key = args[0]
-        letters = self._letters(key)
-        n = len(letters)
+        raw, n = self._raw_key(key)
         if self._store == STORE_ANY:
             if len(args) < 2:
                 raise ValueError("A value object is required as second argument.")
@@ -270,7 +284,6 @@ class Automaton:
         hk = self._hashable(key)
         kid = self._key_ids.get(hk)
         new_id = len(self._values) if kid is None else kid
-        raw = letters.tobytes()
         prev = ctypes.c_int32(-1)
         N.check(self._lib.acb_trie_add_word(self._trie, raw, len(raw), new_id, ctypes.byref(prev)))
         self._drop_table()                                      # kind is TRIE again (src/trie.c:60)
@@ -284,8 +297,7 @@ class Automaton:
         return False
 
     def _lookup(self, key):
-        letters = self._letters(key)
-        raw = letters.tobytes()
+        raw, _ = self._raw_key(key)
         kid = ctypes.c_int32(-1)
         pre = ctypes.c_int32(0)
         N.check(self._lib.acb_trie_find(self._trie, raw, len(raw), ctypes.byref(kid), ctypes.byref(pre)))
@@ -298,13 +310,12 @@ class Automaton:
 
     def match(self, key) -> bool:
         if self.kind == EMPTY:
-            self._letters(key)
+            self._raw_key(key)
             return False
         return self._lookup(key)[1]
 
     def longest_prefix(self, key) -> int:
-        letters = self._letters(key)
-        raw = letters.tobytes()
+        raw, _ = self._raw_key(key)
         return int(self._lib.acb_trie_longest_prefix(self._trie, raw, len(raw)))
 
     _MISSING = object()
@@ -320,10 +331,9 @@ class Automaton:
         raise KeyError(args[0])
 
     def _remove(self, key):
-        letters = self._letters(key)
-        if len(letters) == 0:
+        raw, n = self._raw_key(key)
+        if n == 0:
             return None
-        raw = letters.tobytes()
         kid = ctypes.c_int32(-1)
         N.check(self._lib.acb_trie_remove_word(self._trie, raw, len(raw), ctypes.byref(kid)))
         if kid.value < 0:
