@@ -153,6 +153,19 @@ extern "C" int acb_trie_clear(acb_trie *t) {
     return ACB_OK;
 }
 
+/* child of nd along `byte`, or -1.  Most nodes have one or two children (every byte of a wide letter but the
+ * first, every node of a key's private tail), and those sit next to their parent in the arena: a short walk of
+ * the sibling list answers without touching the big edge table, which is only consulted for wide fan-outs. */
+static inline int32_t child_of(const acb_trie *t, int32_t nd, uint8_t byte) {
+    int32_t c = t->nodes[nd].first_child;
+    for (int k = 0; k < 4 && c >= 0; k++) {
+        if (t->nodes[c].byte == byte) return c;
+        c = t->nodes[c].next_sibling;
+    }
+    if (c < 0) return -1;
+    return t->edges.get(nd, byte);
+}
+
 extern "C" int acb_trie_add_word(acb_trie *t, const uint8_t *key, int64_t nbytes, int32_t key_id,
                                  int32_t *prev_key_id) {
     if (!t || key_id < 0 || nbytes < 0 || (nbytes && !key)) { acb_set_error("bad argument"); return ACB_EINVAL; }
@@ -166,7 +179,7 @@ extern "C" int acb_trie_add_word(acb_trie *t, const uint8_t *key, int64_t nbytes
         if (t->nodes.empty()) { new_node(t, -1, 0); t->live_nodes = 1; }   /* root, src/trie.c:21-26 */
         int32_t nd = 0;
         for (int64_t i = 0; i < nbytes; i++) {
-            int32_t kid = t->edges.get(nd, key[i]);
+            int32_t kid = child_of(t, nd, key[i]);
             if (kid < 0) {
                 if (t->nodes.size() >= 0x7ffffff0u) { acb_set_error("too many trie nodes for int32 state ids"); return ACB_ERANGE; }
                 kid = new_node(t, nd, key[i]);
@@ -205,7 +218,7 @@ static int32_t walk(const acb_trie *t, const uint8_t *key, int64_t nbytes, int64
     int32_t nd = t->nodes.empty() ? -1 : 0;
     int64_t i = 0;
     for (; nd >= 0 && i < nbytes; i++) {
-        int32_t kid = t->edges.get(nd, key[i]);
+        int32_t kid = child_of(t, nd, key[i]);
         if (kid < 0 || t->nodes[kid].live_below == 0) break;
         nd = kid;
     }
