@@ -95,6 +95,7 @@ int64_t acb_trie_count(const acb_trie *t);         /* live keys   (len(A))      
 int64_t acb_trie_longest_word(const acb_trie *t);  /* in letters  (Automaton.longest_word)   */
 int64_t acb_trie_nodes(const acb_trie *t);         /* live nodes  (get_stats nodes_count)    */
 int64_t acb_trie_links(const acb_trie *t);         /* live edges  (get_stats links_count)    */
+int64_t acb_trie_host_bytes(const acb_trie *t);    /* bytes of the node arena + edge table (get_stats total_size) */
 
 /* Read-only view of the flattened automaton (valid until the trie changes).
  * State ids are BFS order, root = 0.  Used for upload and for white-box tests. */

@@ -69,6 +69,7 @@ def lib() -> ctypes.CDLL:
         "acb_trie_longest_word": (i64, [vp]),
         "acb_trie_nodes": (i64, [vp]),
         "acb_trie_links": (i64, [vp]),
+        "acb_trie_host_bytes": (i64, [vp]),
         "acb_trie_flat_view": (ctypes.c_int, [vp, ctypes.POINTER(FlatView)]),
         "acb_trie_export_nodes": (ctypes.c_int, [vp, ctypes.c_int, vp, i64, vp, i64, pi64, pi64, vp, vp, i64]),
         "acb_trie_import_nodes": (ctypes.c_int, [vp, vp, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, i64, pi64, pi64,
@@ -105,7 +106,7 @@ def lib() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "acb_trie_new", "acb_trie_free", "acb_trie_clear", "acb_trie_add_word", "acb_trie_remove_word",
     "acb_trie_find", "acb_trie_longest_prefix", "acb_trie_make_automaton", "acb_trie_kind",
-    "acb_trie_count", "acb_trie_longest_word", "acb_trie_nodes", "acb_trie_links", "acb_trie_flat_view",
+    "acb_trie_count", "acb_trie_longest_word", "acb_trie_nodes", "acb_trie_links", "acb_trie_host_bytes", "acb_trie_flat_view",
     "acb_trie_export_nodes", "acb_trie_import_nodes", "acb_node_records_span",
     "acb_device_count", "acb_table_upload", "acb_table_free", "acb_table_device_bytes", "acb_table_reserve_candidates",
     "acb_scan_device", "acb_scan_host", "acb_copy_records", "acb_take_records", "acb_release_records", "acb_sort_matches_device", "acb_launch_count", "acb_set_kernel_timing",

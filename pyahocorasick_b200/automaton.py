@@ -433,10 +433,9 @@ class Automaton:
         the reference counts them (one node per letter, also for 2- and 4-byte letters; longest_word is the depth
         of the live trie, so unlike the attribute behind `save` it shrinks when the longest key is removed);
         sizeof_node / total_size are this implementation's own host memory: 28-byte arena nodes, one per BYTE of
-        a letter, plus 12 bytes per edge-table entry."""
+        a letter, plus the edge table that indexes wide fan-outs (acb_trie_host_bytes)."""
         byte_nodes = int(self._lib.acb_trie_nodes(self._trie))
-        byte_links = int(self._lib.acb_trie_links(self._trie))
-        nodes, links = byte_nodes, byte_links
+        nodes, links = byte_nodes, int(self._lib.acb_trie_links(self._trie))
         if self._L > 1 and byte_nodes:
             need, n = ctypes.c_int64(0), ctypes.c_int64(0)
             N.check(self._lib.acb_trie_export_nodes(self._trie, 4 if self._L == 4 else 2, None, 0, None, 0,
@@ -445,7 +444,7 @@ class Automaton:
         longest = max((len(k) for k in self._key_objs if k is not None), default=0)
         node_bytes = 28                                   # arena Node in csrc/acb_host.cpp
         return dict(nodes_count=nodes, words_count=len(self), longest_word=longest, links_count=links,
-                    sizeof_node=node_bytes, total_size=byte_nodes * node_bytes + byte_links * 12)
+                    sizeof_node=node_bytes, total_size=int(self._lib.acb_trie_host_bytes(self._trie)))
 
     def __sizeof__(self):
         return object.__sizeof__(self) + self.get_stats()["total_size"]

@@ -95,6 +95,7 @@ struct Node {
     int32_t key_id;        /* -1 = not the end of a key ("eow" false) */
     int32_t live_below;    /* live keys ending at or below this node; 0 = pruned */
     uint8_t byte;
+    uint8_t n_children;    /* saturates at 255; children beyond the kListed-th are also in the edge table */
 };
 
 struct Flat {
@@ -128,6 +129,7 @@ static int32_t new_node(acb_trie *t, int32_t parent, uint8_t byte) {
     n.key_id = -1;
     n.live_below = 0;
     n.byte = byte;
+    n.n_children = 0;
     t->nodes.push_back(n);
     return (int32_t)(t->nodes.size() - 1);
 }
@@ -156,14 +158,16 @@ extern "C" int acb_trie_clear(acb_trie *t) {
 /* child of nd along `byte`, or -1.  Most nodes have one or two children (every byte of a wide letter but the
  * first, every node of a key's private tail), and those sit next to their parent in the arena: a short walk of
  * the sibling list answers without touching the big edge table, which is only consulted for wide fan-outs. */
+constexpr int kListed = 4;             /* children found by walking the sibling list; later ones through the edge table */
 static inline int32_t child_of(const acb_trie *t, int32_t nd, uint8_t byte) {
-    int32_t c = t->nodes[nd].first_child;
-    for (int k = 0; k < 4 && c >= 0; k++) {
+    const Node &p = t->nodes[nd];
+    int32_t c = p.first_child;
+    const int n = p.n_children < kListed ? p.n_children : kListed;
+    for (int k = 0; k < n; k++) {
         if (t->nodes[c].byte == byte) return c;
         c = t->nodes[c].next_sibling;
     }
-    if (c < 0) return -1;
-    return t->edges.get(nd, byte);
+    return p.n_children > kListed ? t->edges.get(nd, byte) : -1;
 }
 
 extern "C" int acb_trie_add_word(acb_trie *t, const uint8_t *key, int64_t nbytes, int32_t key_id,
@@ -186,7 +190,8 @@ extern "C" int acb_trie_add_word(acb_trie *t, const uint8_t *key, int64_t nbytes
                 Node &p = t->nodes[nd];
                 if (p.last_child < 0) p.first_child = kid; else t->nodes[p.last_child].next_sibling = kid;
                 p.last_child = kid;
-                t->edges.put(nd, key[i], kid);
+                if (p.n_children >= kListed) t->edges.put(nd, key[i], kid);   /* the first kListed are found by the list walk */
+                if (p.n_children < 255) p.n_children++;
             }
             nd = kid;
         }
@@ -265,6 +270,10 @@ extern "C" int64_t acb_trie_count(const acb_trie *t) { return t ? t->count : 0; 
 extern "C" int64_t acb_trie_longest_word(const acb_trie *t) { return t ? t->longest : 0; }
 extern "C" int64_t acb_trie_nodes(const acb_trie *t) { return t ? t->live_nodes : 0; }
 extern "C" int64_t acb_trie_links(const acb_trie *t) { return (t && t->live_nodes > 0) ? t->live_nodes - 1 : 0; }
+extern "C" int64_t acb_trie_host_bytes(const acb_trie *t) {
+    if (!t) return 0;
+    return (int64_t)(t->nodes.capacity() * sizeof(Node) + t->edges.keys.capacity() * (sizeof(uint64_t) + sizeof(int32_t)));
+}
 
 /* ---------------------------------------------------------- gram filter */
 namespace {
