@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ACB_ABI_VERSION 2
+#define ACB_ABI_VERSION 3
 
 enum {
     ACB_OK        =  0,
@@ -117,19 +117,17 @@ typedef struct acb_flat_view {
     /* prefilter (see DESIGN.md "filter kernel") */
     int32_t        gram_bytes;    /* g : bytes hashed per probe                               */
     int32_t        stride;        /* s : probe every s-th byte position                       */
-    int32_t        log2_bits1;    /* n: the two bitmaps share 2^n bits of shared memory, 7/8 : 1/8 */
-    int32_t        log2_bits2;    /* n - 3: the stage-2 bitmap has 2^(n-3) bits               */
-    int32_t        log2_bits3;    /* stage-3 bitmap (global memory) has 2^k bits; 0 = stage 3 unused */
+    int32_t        log2_bits1;    /* n: the gram bitmap has 2^n bits (shared memory on the device), 2^(n-5) words */
     int32_t        log2_anchor_slots; /* anchor table has 2^n slots of 8 uint32 (32 B)        */
-    const uint32_t *bitmap1;      /* 7<<(n-8) words: word = umulhi(hash1, 7<<(n-8)); a gram sets two bits of it (csrc/acb_hash.h) */
-    const uint32_t *bitmap2;      /* 1<<(n-8) words: word = hash2>>(40-n),          bit = (hash2>>(35-n))&31 */
-    const uint32_t *bitmap3;      /* 1<<(k-5) words: bit = (hash2|1) * 0x9E3779B1 >> (32-k); large key sets only */
+    const uint32_t *bitmap1;      /* a gram sets two bits of one word: single placement word = umulhi(hash1, 2^(n-5)),
+                                     pair placement acb_pair_place (csrc/acb_hash.h)          */
     const uint32_t *anchors;      /* slot: tag(hash2|1, 0=empty), key_id(-1=MULTI), j|len<<8|last<<16, 20 bytes */
-    int32_t        filter_flags;  /* ACB_FILTER_* : how stage 1 places a gram (csrc/acb_hash.h)            */
+    int32_t        filter_flags;  /* ACB_FILTER_* : how the bitmap places a gram (csrc/acb_hash.h) */
 } acb_flat_view;
 
 /* filter_flags */
-#define ACB_FILTER_WIDE 1   /* g % 4 == 0: the first stage-1 bit comes from the high half of the 64-bit hash sum  */
+#define ACB_FILTER_WIDE 1   /* single placement, g % 4 == 0: the first bit comes from the high half of the 64-bit hash sum */
+#define ACB_FILTER_PAIR 2   /* pair placement (gram 4, stride 1, 1-byte letters): two adjacent positions share one word   */
 
 int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out);
 
@@ -199,20 +197,13 @@ enum {
  *                when every haystack is `stride_bytes` long (haystack h = [h*stride, (h+1)*stride))
  *   d_out/cap  : match records; records beyond cap are counted but not stored
  *   d_count    : device int64; incremented by the number of matches found
- *                (the caller zeroes it; order of records is unspecified).  The filter
- *                path keeps an internal candidate list sized for 1/8 of the probe
- *                positions; if a pathological key set overflows it, *d_count is set to
- *                -1: call acb_table_reserve_candidates(tb, 1) and scan again
- *                (acb_scan_host does this by itself).
+ *                (the caller zeroes it; order of records is unspecified).
  * One scan at a time per table: the table owns the scratch buffers of the scan.
  */
 int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t total_bytes,
                     const int64_t *d_offsets, int64_t n_hay, int64_t stride_bytes,
                     acb_match *d_out, int64_t cap, int64_t *d_count,
                     void *stream, int algo);
-
-/* worst_case != 0: size the candidate list for every probe position (never overflows) */
-int acb_table_reserve_candidates(acb_table *tb, int worst_case);
 
 /* Batch scan, HOST buffers: H2D copy of haystacks (+offsets), the kernel, and D2H of
  * the count and the records, all inside the call (this is what `e2e` times).

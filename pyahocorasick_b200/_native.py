@@ -10,7 +10,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ACB_LIB") or os.path.join(_PKG, "_native", "libacb200.so")   # ACB_LIB: experimental builds
 
-ABI_VERSION = 2            # ACB_ABI_VERSION of include/acb200.h this binding was written against
+ABI_VERSION = 3            # ACB_ABI_VERSION of include/acb200.h this binding was written against
 ACB_OK, ACB_ENOMEM, ACB_EINVAL, ACB_ESTATE, ACB_ECUDA, ACB_EOVERFLOW, ACB_ERANGE = 0, -1, -2, -3, -4, -5, -6
 ALGO_AUTO, ALGO_FILTER, ALGO_DFA, ALGO_LONG = 0, 1, 2, 3
 ALGOS = {"auto": ALGO_AUTO, "filter": ALGO_FILTER, "dfa": ALGO_DFA, "long": ALGO_LONG}
@@ -28,10 +28,8 @@ class FlatView(ctypes.Structure):
         ("key_of", ctypes.POINTER(ctypes.c_int32)), ("out_ptr", ctypes.POINTER(ctypes.c_int32)),
         ("out_idx", ctypes.POINTER(ctypes.c_int32)), ("key_len", ctypes.POINTER(ctypes.c_int32)),
         ("gram_bytes", ctypes.c_int32), ("stride", ctypes.c_int32),
-        ("log2_bits1", ctypes.c_int32), ("log2_bits2", ctypes.c_int32), ("log2_bits3", ctypes.c_int32),
-        ("log2_anchor_slots", ctypes.c_int32),
-        ("bitmap1", ctypes.POINTER(ctypes.c_uint32)), ("bitmap2", ctypes.POINTER(ctypes.c_uint32)),
-        ("bitmap3", ctypes.POINTER(ctypes.c_uint32)), ("anchors", ctypes.POINTER(ctypes.c_uint32)),
+        ("log2_bits1", ctypes.c_int32), ("log2_anchor_slots", ctypes.c_int32),
+        ("bitmap1", ctypes.POINTER(ctypes.c_uint32)), ("anchors", ctypes.POINTER(ctypes.c_uint32)),
         ("filter_flags", ctypes.c_int32),
     ]
 
@@ -79,7 +77,6 @@ def lib() -> ctypes.CDLL:
         "acb_table_upload": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp)]),
         "acb_table_free": (None, [vp]),
         "acb_table_device_bytes": (i64, [vp]),
-        "acb_table_reserve_candidates": (ctypes.c_int, [vp, ctypes.c_int]),
         "acb_scan_device": (ctypes.c_int, [vp, vp, i64, vp, i64, i64, vp, i64, vp, vp, ctypes.c_int]),
         "acb_scan_host": (ctypes.c_int, [vp, vp, i64, vp, i64, i64, vp, i64, pi64, ctypes.c_int, ctypes.c_int]),
         "acb_copy_records": (ctypes.c_int, [vp, vp, i64]),
@@ -108,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "acb_trie_find", "acb_trie_longest_prefix", "acb_trie_make_automaton", "acb_trie_kind",
     "acb_trie_count", "acb_trie_longest_word", "acb_trie_nodes", "acb_trie_links", "acb_trie_host_bytes", "acb_trie_flat_view",
     "acb_trie_export_nodes", "acb_trie_import_nodes", "acb_node_records_span",
-    "acb_device_count", "acb_table_upload", "acb_table_free", "acb_table_device_bytes", "acb_table_reserve_candidates",
+    "acb_device_count", "acb_table_upload", "acb_table_free", "acb_table_device_bytes",
     "acb_scan_device", "acb_scan_host", "acb_copy_records", "acb_take_records", "acb_release_records", "acb_sort_matches_device", "acb_launch_count", "acb_set_kernel_timing",
     "acb_last_kernel_ms", "acb_last_error", "acb_abi_version",
 ]

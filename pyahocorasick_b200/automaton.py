@@ -571,11 +571,9 @@ class Automaton:
             byte_class=arr(fv.byte_class, 256, np.uint8), goto_cm=arr(fv.goto_cm, K * S, np.int32).reshape(K, S),
             fail=arr(fv.fail, S, np.int32), letter_fail=arr(fv.letter_fail, S, np.int32), key_of=arr(fv.key_of, S, np.int32), out_ptr=arr(fv.out_ptr, S + 1, np.int32),
             out_idx=arr(fv.out_idx, n_out, np.int32), key_len=arr(fv.key_len, fv.n_keys, np.int32),
-            gram_bytes=fv.gram_bytes, stride=fv.stride, log2_bits1=fv.log2_bits1, log2_bits2=fv.log2_bits2,
-            log2_bits3=fv.log2_bits3, log2_anchor_slots=fv.log2_anchor_slots, filter_flags=fv.filter_flags,
-            bitmap3=arr(fv.bitmap3, (1 << (fv.log2_bits3 - 5)) if fv.log2_bits3 else 1, np.uint32),
-            bitmap1=arr(fv.bitmap1, 7 << (fv.log2_bits1 - 8), np.uint32),
-            bitmap2=arr(fv.bitmap2, 1 << (fv.log2_bits1 - 8), np.uint32),
+            gram_bytes=fv.gram_bytes, stride=fv.stride, log2_bits1=fv.log2_bits1,
+            log2_anchor_slots=fv.log2_anchor_slots, filter_flags=fv.filter_flags,
+            bitmap1=arr(fv.bitmap1, 1 << (fv.log2_bits1 - 5), np.uint32),
             anchors=arr(fv.anchors, 8 << fv.log2_anchor_slots, np.uint32).reshape(-1, 8))
 
     # ------------------------------------------------------------------ GPU scan plumbing
@@ -635,9 +633,6 @@ class Automaton:
                 N.check(self._lib.acb_scan_device(tb, t.data_ptr(), n * stride, None, n, stride, out.data_ptr(), cap,
                                                   cnt.data_ptr(), stream, N.ALGOS[algo]))
                 found = int(cnt.item())
-                if found == -1:                                   # internal candidate list overflowed: worst-case size, again
-                    N.check(self._lib.acb_table_reserve_candidates(tb, 1))
-                    continue
                 if found > cap:
                     cap = self._match_cap = found + 1024
                     continue

@@ -1,25 +1,26 @@
 /*
  * acb_device.cu -- sm_100a scan kernels and the device half of the C ABI (include/acb200.h).
  *
- * ACB_ALGO_FILTER (the fast path) is two launches per <= 2 GiB segment of the batch:
+ * ACB_ALGO_FILTER (the fast path) is ONE launch per <= 2 GiB segment of the batch:
  *
- *  acb_filter_kernel<NW,STRIDE,WIDE>   persistent, one CTA per SM; streams the haystack bytes once.
- *      Start-anchored search.  Every probe position is tested against the stage-1 gram filter in shared memory
- *      (a blocked Bloom filter, two bits per gram in one word).  The rare survivors are hashed a second time
- *      and tested against stage 2 (shared memory) and, for large key sets, stage 3 (global memory), then queued
- *      per warp.  Between work units a warp resolves its queue through the anchor table in global memory (one
- *      32-byte slot): a UNIQUE anchor carries the only key that can match there, which is compared with the
- *      text directly; a MULTI anchor (keys sharing that prefix) walks the trie through the column-major goto
- *      table.  No failure links are followed: an occurrence is found exactly once, from its first byte, so the
- *      result set equals what the reference produces by walking fail chains at every position
- *      (src/AutomatonSearchIter.c:157-197, src/Automaton.c:693-714).
- *  acb_verify_kernel                   resolves the candidates a warp had to spill to the global list because
- *      its queue was full (normally none), re-arms the counters, flags an overflowed list.
+ *  acb_stream_kernel<NW,STRIDE,MODE>   persistent, one CTA per SM, warp specialised.
+ *      A producer warp claims 16 KiB tiles of the flat haystack buffer from an atomic counter and moves them
+ *      into a 4-stage shared-memory ring with cp.async.bulk (the TMA engine) and mbarriers; sixteen consumer
+ *      warps read their 1 KiB slice of a stage (32 consecutive bytes per lane), hash the gram at every probe
+ *      position and test it against the gram bitmap held in shared memory (a blocked Bloom filter, two bits per
+ *      gram in one word; PAIR mode: one word serves two adjacent positions).  Start-anchored search: the rare
+ *      survivors get the second hash of their gram (read back from the stage, still resident) and are queued
+ *      per warp; between slices a warp resolves its queue, 32 candidates at a time, through the anchor table in
+ *      global memory (one 32-byte slot): a UNIQUE anchor carries the only key that can match there, which is
+ *      compared with the text directly; a MULTI anchor (keys sharing that prefix) walks the trie through the
+ *      column-major goto table.  No failure links are followed: an occurrence is found exactly once, from its
+ *      first byte, so the result set equals what the reference produces by walking fail chains at every
+ *      position (src/AutomatonSearchIter.c:157-197, src/Automaton.c:693-714).
  *
  *  acb_dfa_kernel                      (ACB_ALGO_DFA)
  *      The textbook automaton: goto, else fail until root (src/trie.c:177-194), outputs from CSR lists.  One
  *      lane per 64-byte span with a max_key-1 byte warm-up.  Slower (every byte is a dependent L2 lookup) but
- *      insensitive to key-set shape; also used to cross-check the filter kernel on the GPU.
+ *      insensitive to key-set shape; also used to cross-check the stream kernel on the GPU.
  *
  *  acb_long_kernel                     (ACB_ALGO_LONG)
  *      iter_long: the reference's longest-match walk (src/AutomatonSearchIterLong.c:89-153) replayed letter by
@@ -57,24 +58,32 @@
 
 namespace {
 
-constexpr int kThreads      = 1024;               /* filter kernel: one CTA per SM                 */
-constexpr int kWarps        = kThreads / 32;
-#ifndef ACB_BLOCK_BYTES
-#define ACB_BLOCK_BYTES 4096
+#ifndef ACB_CONSUMERS
+#define ACB_CONSUMERS 16
 #endif
-constexpr int kBlockBytes   = ACB_BLOCK_BYTES;    /* work unit per warp grab (filter kernel)       */
-constexpr int kQueueCap     = 128;                /* stage-1 survivors queued per warp (smem)      */
-constexpr int kStageCap     = 32;                 /* match records staged per warp (smem)          */
+#ifndef ACB_STAGES
+#define ACB_STAGES 4
+#endif
+constexpr int kConsumers    = ACB_CONSUMERS;          /* consumer warps of the stream kernel           */
+constexpr int kFThreads     = (kConsumers + 1) * 32;  /* + the producer warp                           */
+constexpr int kSliceBytes   = 1024;                   /* one warp iteration: 32 bytes per lane         */
+constexpr int kTileBytes    = kConsumers * kSliceBytes;
+constexpr int kLook         = 16;                     /* bytes copied past a tile (gram look-ahead)    */
+constexpr int kStageBytes   = kTileBytes + 128;       /* tile + look-ahead, stages stay 128 B aligned  */
+constexpr int kStages       = ACB_STAGES;
+constexpr int kClaimDepth   = 8;                      /* tile claims in flight per producer (multiple of kStages) */
+constexpr int kQueueCap     = 128;                    /* bitmap survivors queued per warp (smem)       */
+constexpr int kStageCap     = 32;                     /* match records staged per warp (smem)          */
 constexpr uint32_t kFull    = 0xffffffffu;
-constexpr int32_t  kTermBit = 0x40000000;         /* goto entry flag: child ends a key             */
+constexpr uint32_t kNoTile  = 0xffffffffu;
+constexpr int32_t  kTermBit = 0x40000000;             /* goto entry flag: child ends a key             */
 constexpr int32_t  kIdMask  = 0x3fffffff;
-constexpr long long kSegBytes = 1LL << 31;        /* candidates are uint32 offsets into a segment  */
+constexpr long long kSegBytes = 1LL << 31;            /* candidates are uint32 offsets into a segment  */
 
-constexpr int kVerThreads   = 256;
-constexpr int kVerWarps     = kVerThreads / 32;
-
-constexpr int kDfaSpan      = 64;                 /* bytes per lane in the DFA kernel              */
+constexpr int kDfaSpan      = 64;                     /* bytes per lane in the DFA kernel              */
 constexpr int kDfaThreads   = 256;
+
+enum { kModeNarrow = 0, kModeWide = 1, kModePair = 2 };   /* how a gram is placed in the bitmap (acb_hash.h) */
 
 std::atomic<long long> g_launches{0};
 thread_local float g_last_ms = 0.f;
@@ -98,28 +107,19 @@ struct ScanParams {
     int32_t L;
     int32_t gram;
     int32_t max_key_bytes;
-    const uint32_t *bm1;
-    const uint32_t *bm2;
-    const uint32_t *bm3;           /* stage 3, global memory; log3 == 0: unused */
+    const uint32_t *bm1;           /* gram bitmap, 2^(log1-5) words */
     const uint4 *anchors;          /* 2 x uint4 per slot */
-    int32_t log1, log2, log3, logA;
+    int32_t log1, logA;
     uint32_t mul1[ACB_MAX_WINDOWS];
     uint32_t mul2[ACB_MAX_WINDOWS];
     acb_match *out;
     long long cap;
     unsigned long long *count;
-    /* filter -> verify hand-over */
-    long long seg_begin, seg_end;  /* byte range of this launch pair */
-    long long n_blocks;            /* work units in the segment */
-    uint2 *cand;                   /* candidates: {probe position relative to seg_begin, hash2(gram)|1} */
-    unsigned long long cand_cap;
-    unsigned long long *cand_count;
-    unsigned int *work_ctr;        /* [0] next work unit, [1] filter CTAs done, [2] verify CTAs done */
+    long long seg_begin, seg_end;  /* byte range of this launch */
+    unsigned int n_tiles;          /* kTileBytes tiles in the segment */
+    unsigned int *work_ctr;        /* [0] next tile, [1] CTAs done */
     int stride_shift;              /* log2(stride_bytes) when it is a power of two, else -1 */
     int letter_shift;              /* log2(L) */
-    unsigned long long *timeline;  /* debug (ACB_TIMELINE=1): 6 globaltimer stamps per warp, else nullptr */
-    int inline_resolve;            /* 1: warps resolve their own candidates between work units; 0: all go to the list */
-    int filter_flags;              /* ACB_FILTER_* of the table */
 };
 
 /* ---------------------------------------------------------------- helpers */
@@ -230,31 +230,60 @@ __device__ __forceinline__ bool text_equals(const uint32_t (&w)[6], long long x,
     return diff == 0;
 }
 
-/* ------------------------------------------------------- the filter kernel */
-/* Stage 1.  Persistent CTAs; every warp grabs 4 KiB work units.  Per iteration a lane owns 32
- * consecutive bytes (two 16-byte loads, prefetched one iteration ahead), hashes the gram at
- * each probe position and tests it against the bitmap in shared memory.  Survivors are queued
- * per warp in shared memory together with hash2 of their gram (re-read through L1) and written,
- * 32 at a time, to the global candidate list.  Work units that lie completely inside the buffer
- * run a variant without any bounds check (GUARD = false). */
+/* ------------------------------------------------------- the stream kernel */
 
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
+__device__ __forceinline__ unsigned long long mul_wide(uint32_t a, uint32_t b) {
+    unsigned long long d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
+    return d;
 }
-#define ACB_STAMP(i) do { if (p.timeline && lane == 0) p.timeline[((size_t)blockIdx.x * kWarps + warp) * 6 + (i)] = gtime(); } while (0)
-
 __device__ __forceinline__ unsigned long long mad_wide(uint32_t a, uint32_t b, unsigned long long c) {
     unsigned long long d;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
     return d;
 }
-
-__device__ __forceinline__ uint32_t lds_word(uint32_t saddr) {
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+/* the bitmap never changes during a launch: a plain (non-volatile) load the compiler may schedule freely */
+__device__ __forceinline__ uint32_t lds_bitmap(uint32_t saddr) {
     uint32_t v;
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
+}
+
+/* mbarrier / bulk-copy (TMA engine) primitives: PTX ISA "mbarrier", "cp.async.bulk" */
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" :: "r"(bar), "r"(parity) : "memory");
+}
+/* global -> shared bulk copy, completion counted in bytes on `bar`; all of dst, src, bytes are multiples of 16 */
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void resolve(const ScanParams &p, const WarpStage &ws, uint2 c) {
@@ -295,283 +324,291 @@ __device__ __forceinline__ void resolve(const ScanParams &p, const WarpStage &ws
     }
 }
 
-/* per-warp state of the in-kernel stage 2/3 (all in shared memory except the ring positions) */
+/* per-warp state of the candidate path (all in shared memory except the ring positions) */
 struct WarpResolve {
-    uint2 *queue;      /* candidates {pos, tag} that passed both bitmaps, ring of kQueueCap */
+    uint2 *queue;      /* candidates {pos, tag} that passed the bitmap, ring of kQueueCap */
     WarpStage ws;
 };
 
-/* Resolve the warp's queued candidates (they passed both bitmaps) through the anchor table, 32 at a
- * time.  Called between work units, never from the probe loop, so that none of the probe loop's
- * registers are live across it.  While this warp waits on L2 the other warps keep filtering. */
-__device__ __noinline__ void drain_queue(const ScanParams &p, const WarpResolve &wr, int &qhead, int qtail,
+/* Resolve the warp's queued candidates through the anchor table, 32 at a time.  Called between slices, never
+ * from the probe loop, so that none of the probe loop's registers are live across it.  While this warp waits on
+ * L2 the other warps keep filtering. */
+__device__ __noinline__ void drain_queue(const ScanParams &p, const WarpResolve &wr, uint32_t &qhead, uint32_t qtail,
                                          bool final_flush, int lane) {
-    while (qtail - qhead >= 32 || (final_flush && qtail > qhead)) {
+    while (qtail - qhead >= 32u || (final_flush && qtail != qhead)) {
         __syncwarp();
-        const int n = (qtail - qhead >= 32) ? 32 : (qtail - qhead);
-        if (lane < n) resolve(p, wr.ws, wr.queue[(qhead + lane) & (kQueueCap - 1)]);
+        const uint32_t n = (qtail - qhead >= 32u) ? 32u : (qtail - qhead);
+        if ((uint32_t)lane < n) resolve(p, wr.ws, wr.queue[(qhead + lane) & (kQueueCap - 1)]);
         qhead += n;
         flush_stage(p, wr.ws, lane);
     }
 }
 
-struct FilterCtx {
-    const uint8_t *seg;        /* hay + seg_begin */
-    uint32_t seg_len;          /* bytes of this segment: positions >= seg_len belong to the next launch */
-    long long total_rel;       /* total - seg_begin: bytes that exist from seg onwards */
+/* what a consumer warp needs to probe a slice */
+struct ProbeCtx {
     uint32_t sbm;              /* shared-memory address of the bitmap */
-    uint32_t mul_word;         /* umulhi(h, mul_word) = stage-1 word index (7/8 of the words) */
-    const uint32_t *bm3;       /* stage-3 bitmap in global memory (large key sets), log3 == 0: unused */
-    int log3;
-    uint32_t sbm2;             /* shared-memory address of the stage-2 bitmap (last 1/8) */
-    int sh_word2, sh_bit2;     /* tag >> sh_word2 = stage-2 word index, tag >> sh_bit2 = its bit index */
-    uint32_t four;             /* == 4, opaque to the compiler so the address is one IMAD (FMA pipe) */
+    uint32_t n_words;          /* umulhi(h, n_words) = word index */
+    uint32_t four;             /* == 4, opaque to the compiler so the address is one IMAD (FMA pipe, which has room) */
     uint32_t two;              /* == 2, same trick for the hit accumulator */
-    int sh_bit;                /* h >> sh_bit: bit index (low 5 bits, wrap shift) */
-    uint32_t lt_mask;
-    int lane;
-    uint2 *queue;
-    uint2 *cand;
-    unsigned long long cand_cap;
-    unsigned long long *cand_count;
+    int sh_bit;                /* NARROW: h >> sh_bit supplies the first bit index (low 5 bits, wrap shift) */
 };
 
-/* move queued candidates to the global list, 32 at a time (all of them when `all` is set) */
-__device__ __forceinline__ void spill_queue(const FilterCtx &c, int &qhead, int qtail, bool all) {
-    while (qtail - qhead >= 32 || (all && qtail > qhead)) {
-        __syncwarp();
-        const int n = (qtail - qhead >= 32) ? 32 : (qtail - qhead);
-        unsigned long long g = 0;
-        if (c.lane == 0) g = atomicAdd(c.cand_count, (unsigned long long)n);
-        g = __shfl_sync(kFull, g, 0);
-        if (c.lane < n && g + c.lane < c.cand_cap) c.cand[g + c.lane] = c.queue[(qhead + c.lane) & (kQueueCap - 1)];
-        qhead += n;
-        __syncwarp();
-    }
-}
-
-template <bool GUARD>
-__device__ __forceinline__ uint4 ld_chunk(const FilterCtx &c, uint32_t rel) {
-    if (!GUARD || (long long)rel + 16 <= c.total_rel) return __ldg(reinterpret_cast<const uint4 *>(c.seg + rel));
-    uint32_t w[4] = {0, 0, 0, 0};
-    for (int i = 0; i < 16; i++) if ((long long)rel + i < c.total_rel) w[i >> 2] |= (uint32_t)c.seg[rel + i] << (8 * (i & 3));
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-template <bool GUARD>
-__device__ __forceinline__ uint32_t ld_word(const FilterCtx &c, uint32_t rel) {       /* rel % 4 == 0 */
-    if (!GUARD || (long long)rel + 4 <= c.total_rel) return __ldg(reinterpret_cast<const uint32_t *>(c.seg + rel));
-    uint32_t v = 0;
-    for (int b = 0; b < 4; b++) if ((long long)rel + b < c.total_rel) v |= (uint32_t)c.seg[rel + b] << (8 * b);
-    return v;
-}
-
-constexpr int kFChunk = 32;                       /* bytes per lane per iteration   */
-constexpr int kFWarpBytes = 32 * kFChunk;         /* 1 KiB per warp iteration       */
-constexpr int kFIters = kBlockBytes / kFWarpBytes;
-
-/* W[off + g] for g in 0..7 without dynamic register indexing: a 3-level select tree */
+/* window t of the lane's text: the 4 bytes at byte offset t of W[] (little endian) */
 template <int N>
-__device__ __forceinline__ uint32_t sel8(const uint32_t (&W)[N], int off, int g) {
-    const uint32_t a0 = (g & 1) ? W[off + 1] : W[off + 0], a1 = (g & 1) ? W[off + 3] : W[off + 2];
-    const uint32_t a2 = (g & 1) ? W[off + 5] : W[off + 4], a3 = (g & 1) ? W[off + 7] : W[off + 6];
-    const uint32_t b0 = (g & 2) ? a1 : a0, b1 = (g & 2) ? a3 : a2;
-    return (g & 4) ? b1 : b0;
+__device__ __forceinline__ uint32_t window(const uint32_t (&W)[N], int t) {
+    return ((t & 3) == 0) ? W[t >> 2] : __funnelshift_r(W[t >> 2], W[(t >> 2) + 1], (t & 3) * 8);
 }
 
-template <int NW, int STRIDE, bool WIDE, bool GUARD>
-__device__ __forceinline__ void filter_unit(const FilterCtx &c, const uint32_t (&mul)[NW], const uint32_t (&mul2)[NW],
-                                            uint32_t rel0, int &qhead, int &qtail) {
-    constexpr int kProbes = kFChunk / STRIDE;
-    const int lane = c.lane;
-    uint4 cur0 = ld_chunk<GUARD>(c, rel0 + lane * kFChunk);
-    uint4 cur1 = ld_chunk<GUARD>(c, rel0 + lane * kFChunk + 16);
-#pragma unroll 1
-    for (int it = 0; it < kFIters; ++it) {
-        const uint32_t pos0 = rel0 + it * kFWarpBytes + lane * kFChunk;
-        if (GUARD && rel0 + it * kFWarpBytes >= c.seg_len) break;                  /* warp-uniform */
-        /* prefetch the next iteration; past the unit only lane 0's first chunk is needed (look-ahead) */
-        uint4 nxt0 = make_uint4(0, 0, 0, 0), nxt1 = make_uint4(0, 0, 0, 0);
-        if (it + 1 < kFIters) {
-            nxt0 = ld_chunk<GUARD>(c, pos0 + kFWarpBytes);
-            nxt1 = ld_chunk<GUARD>(c, pos0 + kFWarpBytes + 16);
-        } else if (lane == 0) {
-            nxt0 = ld_chunk<GUARD>(c, pos0 + kFWarpBytes);
-        }
-        uint32_t W[8 + NW];
-        W[0] = cur0.x; W[1] = cur0.y; W[2] = cur0.z; W[3] = cur0.w;
-        W[4] = cur1.x; W[5] = cur1.y; W[6] = cur1.z; W[7] = cur1.w;
-        {   /* look-ahead words: the next lane's first chunk; lane 31 takes lane 0's next-iteration chunk */
-            const uint32_t cw[4] = {cur0.x, cur0.y, cur0.z, cur0.w};
-            const uint32_t nw[4] = {nxt0.x, nxt0.y, nxt0.z, nxt0.w};
-#pragma unroll
-            for (int k = 0; k < NW; k++) {
-                uint32_t a = __shfl_down_sync(kFull, cw[k], 1);
-                uint32_t b = __shfl_sync(kFull, nw[k], 0);
-                W[8 + k] = (lane == 31) ? b : a;
-            }
-        }
-        /* One bitmap probe per position.  The hit bit is shifted into `acc` with a multiply-add (FMA pipe, which
-           has room; c.two == 2 is opaque to the compiler), so probe i ends up in bit kProbes-1-i.  Blocked Bloom,
-           k = 2: both bits of the gram must be set in its word (wrap shifts use the low 5 bits of the hash). */
-        uint32_t acc = 0;
-#pragma unroll
-        for (int t = 0; t < kFChunk; t += STRIDE) {
-            uint32_t h = 0, ha;
-            if (WIDE) {                          /* 64-bit products: low half = hash1, high half -> first bit */
-                unsigned long long hw = 0;
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    const int wi = (t >> 2) + k;
-                    const uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
-                    hw = mad_wide(w, mul[k], hw);
-                }
-                h = (uint32_t)hw;
-                ha = (uint32_t)(hw >> 32);
-            } else {
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    const int wi = (t >> 2) + k;
-                    const uint32_t w = ((t & 3) == 0) ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], (t & 3) * 8);
-                    h += w * mul[k];
-                }
-                ha = h >> c.sh_bit;
-            }
-            const uint32_t word = lds_word(__umulhi(h, c.mul_word) * c.four + c.sbm);
-            const uint32_t both = __funnelshift_r(word, 0u, ha) & __funnelshift_r(word, 0u, h) & 1u;
-            acc = acc * c.two + both;
-        }
-        uint32_t hits = __brev(acc) >> (32 - kProbes);                             /* bit i = probe i */
-        if (GUARD && pos0 + kFChunk > c.seg_len) {                                 /* probes that start past the segment */
-            const int valid = (pos0 >= c.seg_len) ? 0 : ((int)(c.seg_len - pos0) + STRIDE - 1) / STRIDE;
-            hits = (valid <= 0) ? 0u : ((valid >= 32) ? hits : (hits & ((1u << valid) - 1u)));
-        }
-        /* queue the survivors (ballot-ranked append into the warp's ring) with hash2 of their gram */
-        unsigned any = __ballot_sync(kFull, hits != 0);
-        while (any) {
-            bool keep = false;
-            uint2 cand = make_uint2(0, 0);
-            if (hits) {
-                const int t = (__ffs(hits) - 1) * STRIDE;                          /* byte offset inside the lane's 32 */
-                const uint32_t x = pos0 + t;
-                hits &= hits - 1;
-                /* hash2 of the gram, from the words still in registers (8-way select on t / 4) */
-                const int g = t >> 2, sh = (t & 3) * 8;
-                uint32_t tag = 0, w0 = sel8(W, 0, g);
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    const uint32_t w1 = sel8(W, k + 1, g);
-                    tag += __funnelshift_r(w0, w1, sh) * mul2[k];
-                    w0 = w1;
-                }
-                tag |= 1u;
-                /* stage 2: second bitmap (hash2), also in shared memory; only its survivors are queued */
-                const uint32_t word2 = lds_word((tag >> c.sh_word2) * 4u + c.sbm2);
-                keep = (__funnelshift_r(word2, 0u, tag >> c.sh_bit2) & 1u) != 0;
-                if (keep && c.log3) {                                              /* stage 3 (large key sets only): bitmap in L2 */
-                    const uint32_t i3 = (tag * ACB_S3_MIX) >> (32 - c.log3);
-                    keep = ((__ldg(c.bm3 + (i3 >> 5)) >> (i3 & 31)) & 1u) != 0;
-                }
-                cand = make_uint2(x, tag);
-            }
-            const unsigned km = __ballot_sync(kFull, keep);
-            if (keep) c.queue[(qtail + __popc(km & c.lt_mask)) & (kQueueCap - 1)] = cand;
-            qtail += __popc(km);
-            if (qtail - qhead > kQueueCap - 32) {                                  /* ring nearly full: spill 32 to the global list */
-                __syncwarp();
-                unsigned long long g = 0;
-                if (lane == 0) g = atomicAdd(c.cand_count, 32ULL);
-                g = __shfl_sync(kFull, g, 0);
-                if (g + lane < c.cand_cap) c.cand[g + lane] = c.queue[(qhead + lane) & (kQueueCap - 1)];
-                qhead += 32;
-                __syncwarp();
-            }
-            any = __ballot_sync(kFull, hits != 0);
-        }
-        cur0 = nxt0;
-        cur1 = nxt1;
-    }
-}
-
+/* One bitmap probe per STRIDE-th position of the lane's 32 bytes; returns bit i = probe i passed.  The hit bit is
+ * shifted into `acc` with a multiply-add (FMA pipe; c.two == 2 is opaque to the compiler).  Blocked Bloom, k = 2:
+ * both bits of the gram must be set in its word (wrap shifts use the low 5 bits of their amount).
+ * WIDE (g % 4 == 0): 64-bit products, low half = hash1 (word index, second bit), high half -> first bit. */
 template <int NW, int STRIDE, bool WIDE>
-__global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_constant__ ScanParams p) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    const int nwords = 1 << (p.log1 - 5);
-    uint32_t *s_bm = smem;
-    uint2 *s_queue = reinterpret_cast<uint2 *>(s_bm + nwords);           /* kWarps * kQueueCap */
-    acb_match *s_stage = reinterpret_cast<acb_match *>(s_queue + kWarps * kQueueCap);   /* kWarps * kStageCap */
-    int *s_cnt = reinterpret_cast<int *>(s_stage + kWarps * kStageCap);  /* kWarps */
+__device__ __forceinline__ uint32_t probe_single(const ProbeCtx &c, const uint32_t (&W)[8 + NW], const uint32_t (&mul)[NW]) {
+    constexpr int kProbes = 32 / STRIDE;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int t = 0; t < 32; t += STRIDE) {
+        uint32_t h = 0, ha;
+        if (WIDE) {
+            unsigned long long hw = 0;
+#pragma unroll
+            for (int k = 0; k < NW; k++) hw = mad_wide(window(W, t + 4 * k), mul[k], hw);
+            h = (uint32_t)hw;
+            ha = (uint32_t)(hw >> 32);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NW; k++) h += window(W, t + 4 * k) * mul[k];
+            ha = h >> c.sh_bit;
+        }
+        const uint32_t word = lds_bitmap(__umulhi(h, c.n_words) * c.four + c.sbm);
+        const uint32_t both = __funnelshift_r(word, 0u, ha) & __funnelshift_r(word, 0u, h) & 1u;
+        acc = acc * c.two + both;
+    }
+    return __brev(acc) >> (32 - kProbes);
+}
 
+/* PAIR placement (acb_hash.h): positions x (even) and x+1 test two bits each in ONE word selected by the three
+ * bytes their grams share -- one shared-memory load per two positions.  Bit y of the result = position y. */
+template <int N>
+__device__ __forceinline__ uint32_t probe_pair(const ProbeCtx &c, const uint32_t (&W)[N], uint32_t mulp) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int x = 0; x < 32; x += 2) {
+        const uint32_t w0 = window(W, x), w1 = window(W, x + 1);
+        /* a register whose low 5 bits are those of text byte x+4 (the byte of gram x+1 outside the common three) */
+        const int tb = x + 4;
+        const uint32_t wb = ((tb & 3) == 0) ? W[tb >> 2] : (tb < 32 ? window(W, tb) : (W[tb >> 2] >> ((tb & 3) * 8)));
+        const uint32_t a0 = __umulhi(w0, mulp);
+        const unsigned long long p1 = mul_wide(w1, mulp);
+        const uint32_t word = lds_bitmap(__umulhi((uint32_t)p1, c.n_words) * c.four + c.sbm);
+        const uint32_t r0 = __funnelshift_r(word, 0u, a0) & __funnelshift_r(word, 0u, w0) & 1u;
+        const uint32_t r1 = __funnelshift_r(word, 0u, (uint32_t)(p1 >> 32)) & __funnelshift_r(word, 0u, wb) & 1u;
+        acc = acc * c.two + r0;
+        acc = acc * c.two + r1;
+    }
+    return __brev(acc);
+}
+
+/* shared-memory carve-up of the stream kernel (host and device agree through this one function) */
+struct StreamSmem {
+    uint32_t bitmap, stages, queue, stage_rec, stage_cnt, bars, tiles, next, total;
+};
+__host__ __device__ inline StreamSmem stream_smem(int log1) {
+    StreamSmem s;
+    uint32_t o = 0;
+    s.bitmap = o;    o += 1u << (log1 - 3);                       o = (o + 127u) & ~127u;
+    s.stages = o;    o += (uint32_t)kStages * kStageBytes;
+    s.queue = o;     o += (uint32_t)kConsumers * kQueueCap * (uint32_t)sizeof(uint2);
+    s.stage_rec = o; o += (uint32_t)kConsumers * kStageCap * (uint32_t)sizeof(acb_match);
+    s.stage_cnt = o; o += (uint32_t)kConsumers * 4u;              o = (o + 15u) & ~15u;
+    s.bars = o;      o += 2u * kStages * 8u;                      /* full[kStages], empty[kStages] */
+    s.tiles = o;     o += (uint32_t)kStages * 4u;
+    s.next = o;      o += 4u;
+    s.total = (o + 15u) & ~15u;
+    return s;
+}
+
+template <int NW, int STRIDE, int MODE>
+__global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const StreamSmem lay = stream_smem(p.log1);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    ACB_STAMP(0);
-    {   /* both bitmaps -> shared memory (stage 1 in the first 7/8 of the words, stage 2 in the last 1/8), with
-           cp.async so that all of a thread's 16-byte pieces are in flight at once instead of one L2 round trip each */
-        const int n1 = 7 * (nwords / 8);
-        const uint4 *src1 = reinterpret_cast<const uint4 *>(p.bm1), *src2 = reinterpret_cast<const uint4 *>(p.bm2);
-        const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(s_bm);
-        for (int i = tid; i < n1 / 4; i += kThreads)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sdst + 16u * i), "l"(src1 + i));
-        for (int i = tid; i < (nwords - n1) / 4; i += kThreads)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sdst + 16u * (n1 / 4 + i)), "l"(src2 + i));
+    const uint32_t bar_full = sbase + lay.bars, bar_empty = bar_full + 8u * kStages;
+    volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem_raw + lay.tiles);
+
+    {   /* the bitmap -> shared memory with cp.async, so that all of a thread's 16-byte pieces are in flight at once */
+        const int n16 = 1 << (p.log1 - 7);
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.bm1);
+        for (int i = tid; i < n16; i += kFThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + lay.bitmap + 16u * i), "l"(src + i));
         asm volatile("cp.async.commit_group;");
-        if (tid < kWarps) s_cnt[tid] = 0;
+        if (tid < kConsumers) reinterpret_cast<int *>(smem_raw + lay.stage_cnt)[tid] = 0;
+        if (tid == 0) *reinterpret_cast<unsigned int *>(smem_raw + lay.next) = 0u;
+        if (tid == 0) {
+            for (int s = 0; s < kStages; s++) {
+                mbar_init(bar_full + 8u * s, 1);                 /* the producer's arrive(.expect_tx) */
+                mbar_init(bar_empty + 8u * s, kConsumers);       /* one arrive per consumer warp */
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    ACB_STAMP(1);
-    WarpResolve wr;
-    wr.queue = s_queue + warp * kQueueCap;
-    wr.ws.buf = s_stage + warp * kStageCap;
-    wr.ws.cnt = s_cnt + warp;
 
-    FilterCtx c;
-    c.seg = p.hay + p.seg_begin;
-    c.seg_len = (uint32_t)(p.seg_end - p.seg_begin);                     /* <= 2^31 */
-    c.total_rel = p.total - p.seg_begin;
-    c.sbm = (uint32_t)__cvta_generic_to_shared(s_bm);
-    c.mul_word = 7u << (p.log1 - 8);
-    c.bm3 = p.bm3;
-    c.log3 = p.log3;
-    c.sbm2 = c.sbm + 4u * (7u << (p.log1 - 8));
-    c.sh_word2 = 40 - p.log1;
-    c.sh_bit2 = 35 - p.log1;
-    c.four = 4u + (uint32_t)(p.log1 >> 8);                               /* always 4 */
-    c.two = 2u + (uint32_t)(p.log1 >> 8);                                /* always 2 */
-    c.sh_bit = 32 - p.log1;
-    c.lt_mask = (1u << lane) - 1u;
-    c.lane = lane;
-    c.queue = s_queue + warp * kQueueCap;
-    c.cand = p.cand;
-    c.cand_cap = p.cand_cap;
-    c.cand_count = p.cand_count;
-    uint32_t mul[NW], mul2[NW];
+    const uint32_t seg_len = (uint32_t)(p.seg_end - p.seg_begin);        /* <= 2^31 */
+
+    if (warp == kConsumers) {
+        /* ---------------- producer warp: claim a tile, wait for a free stage, start the bulk copy */
+        const uint8_t *seg = p.hay + p.seg_begin;
+        const long long exist = p.total - p.seg_begin;                   /* bytes that exist from seg onwards */
+        /* Tiles come from one global counter.  A claim is a ~1 us round trip to L2, so kClaimDepth of them are kept
+           in flight: claim[k] serves fills k, k + kClaimDepth, ... and is re-issued as soon as it has been read (one
+           register per slot, so that reading a slot never waits for a younger atomic). */
+        unsigned int claim[kClaimDepth];
 #pragma unroll
-    for (int k = 0; k < NW; k++) { mul[k] = p.mul1[k]; mul2[k] = p.mul2[k]; }
-    int qhead = 0, qtail = 0;                    /* ring positions; the queue persists across work units */
-    /* units below this index need no bounds checks: unit, look-ahead and gram re-reads stay inside both
-       the segment and the buffer */
-    long long interior_end = c.total_rel - 64 < (long long)c.seg_len ? c.total_rel - 64 : (long long)c.seg_len;
-    const long long n_interior = interior_end < kBlockBytes ? 0 : interior_end / kBlockBytes;
-
-    bool first_unit = true;
-    for (;;) {
-        unsigned int blk = 0;
-        if (lane == 0) blk = atomicAdd(p.work_ctr, 1u);
-        blk = __shfl_sync(kFull, blk, 0);
-        if ((long long)blk >= p.n_blocks) break;
-        if (first_unit) { ACB_STAMP(2); first_unit = false; }
-        const uint32_t rel0 = blk * (uint32_t)kBlockBytes;
-        if ((long long)blk < n_interior) filter_unit<NW, STRIDE, WIDE, false>(c, mul, mul2, rel0, qhead, qtail);
-        else filter_unit<NW, STRIDE, WIDE, true>(c, mul, mul2, rel0, qhead, qtail);
-        if (qtail - qhead >= 32) {
-            if (p.inline_resolve) drain_queue(p, wr, qhead, qtail, false, lane);
-            else spill_queue(c, qhead, qtail, false);
+        for (int k = 0; k < kClaimDepth; k++) claim[k] = (lane == 0) ? atomicAdd(p.work_ctr, 1u) : 0u;
+        bool more = true;
+        for (uint32_t base = 0; more; base += kClaimDepth) {
+#pragma unroll
+            for (int k = 0; k < kClaimDepth; k++) {
+                if (!more) break;
+                const uint32_t fill = base + k;
+                const uint32_t stage = fill % kStages;
+                const unsigned int tile = __shfl_sync(kFull, claim[k], 0);
+                if (lane == 0 && tile < p.n_tiles) claim[k] = atomicAdd(p.work_ctr, 1u);
+                if (fill >= (uint32_t)kStages) mbar_wait(bar_empty + 8u * stage, ((fill / kStages) - 1u) & 1u);
+                if (tile >= p.n_tiles) {                                 /* out of work: one sentinel fill ends every consumer */
+                    if (lane == 0) { s_tile[stage] = kNoTile; mbar_arrive(bar_full + 8u * stage); }
+                    more = false;
+                    break;
+                }
+                const long long off = (long long)tile * kTileBytes;
+                const long long avail = exist - off;                     /* > 0 */
+                const uint32_t want = kTileBytes + kLook;
+                const uint32_t bulk = avail >= (long long)want ? want : (uint32_t)(avail & ~15LL);
+                uint8_t *dst = smem_raw + lay.stages + (size_t)stage * kStageBytes;
+                if (avail < (long long)want) {
+                    /* last tile of the buffer: the bytes past the last whole 16 are copied by hand, and the rest of the
+                       slice they end in (plus look-ahead) is zero filled so that no lane reads stale shared memory */
+                    const uint32_t a = (uint32_t)avail;
+                    uint32_t zend = ((a + (uint32_t)kSliceBytes - 1u) & ~((uint32_t)kSliceBytes - 1u)) + kLook;
+                    if (zend > want) zend = want;
+                    for (uint32_t i = bulk + lane; i < zend; i += 32) dst[i] = i < a ? seg[off + i] : (uint8_t)0;
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    s_tile[stage] = tile;
+                    if (bulk) {
+                        mbar_arrive_expect_tx(bar_full + 8u * stage, bulk);
+                        bulk_load(sbase + lay.stages + stage * (uint32_t)kStageBytes, seg + off, bulk, bar_full + 8u * stage);
+                    } else {
+                        mbar_arrive(bar_full + 8u * stage);
+                    }
+                }
+            }
         }
+    } else {
+        /* ---------------- consumer warps */
+        WarpResolve wr;
+        wr.queue = reinterpret_cast<uint2 *>(smem_raw + lay.queue) + warp * kQueueCap;
+        wr.ws.buf = reinterpret_cast<acb_match *>(smem_raw + lay.stage_rec) + warp * kStageCap;
+        wr.ws.cnt = reinterpret_cast<int *>(smem_raw + lay.stage_cnt) + warp;
+        ProbeCtx c;
+        c.sbm = sbase + lay.bitmap;
+        c.n_words = 1u << (p.log1 - 5);
+        c.four = 4u + (uint32_t)(p.log1 >> 8);                           /* always 4 */
+        c.two = 2u + (uint32_t)(p.log1 >> 8);                            /* always 2 */
+        c.sh_bit = 32 - p.log1;
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        uint32_t mul[NW], mul2[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) { mul[k] = p.mul1[k]; mul2[k] = p.mul2[k]; }
+        const uint32_t mulp = acb_pair_mul() + (uint32_t)(p.log1 >> 8);  /* a register, not an immediate per use */
+        uint32_t qhead = 0, qtail = 0;                                   /* ring positions; the queue persists across slices */
+
+        /* Slices are handed out dynamically: slice g is slice g % kConsumers of fill g / kConsumers.  A warp that is
+           busy resolving candidates simply takes fewer slices; with exactly kConsumers warps and one slice held per warp
+           a waiter can never be a whole ring turn ahead of the barrier phase it waits for. */
+        volatile unsigned int *s_next = reinterpret_cast<volatile unsigned int *>(smem_raw + lay.next);
+        for (;;) {
+            unsigned int g = 0;
+            if (lane == 0) g = atomicAdd(const_cast<unsigned int *>(s_next), 1u);
+            g = __shfl_sync(kFull, g, 0);
+            const uint32_t fill = g / kConsumers, slice_off = (g % kConsumers) * (uint32_t)kSliceBytes;
+            const uint32_t stage = fill % kStages;
+            mbar_wait(bar_full + 8u * stage, (fill / kStages) & 1u);
+            const uint32_t tile = s_tile[stage];
+            if (tile == kNoTile) break;
+            const uint32_t tile_off = tile * (uint32_t)kTileBytes;       /* relative to the segment */
+            const uint32_t n_valid = (seg_len - tile_off < (uint32_t)kTileBytes) ? seg_len - tile_off : (uint32_t)kTileBytes;
+            if (slice_off < n_valid) {                                   /* warp-uniform */
+                const uint32_t saddr = sbase + lay.stages + stage * (uint32_t)kStageBytes + slice_off + (uint32_t)lane * 32u;
+                const uint4 c0 = lds128(saddr), c1 = lds128(saddr + 16u);
+                uint32_t W[8 + NW];
+                W[0] = c0.x; W[1] = c0.y; W[2] = c0.z; W[3] = c0.w;
+                W[4] = c1.x; W[5] = c1.y; W[6] = c1.z; W[7] = c1.w;
+                {   /* look-ahead words: the next lane's first words; lane 31 reads past its slice (next slice / tile pad) */
+                    const uint32_t cw[4] = {c0.x, c0.y, c0.z, c0.w};
+#pragma unroll
+                    for (int k = 0; k < NW; k++) W[8 + k] = __shfl_down_sync(kFull, cw[k], 1);
+                    if (lane == 31) {
+#pragma unroll
+                        for (int k = 0; k < NW; k++) W[8 + k] = lds32(saddr + 32u + 4u * k);
+                    }
+                }
+                uint32_t hits;
+#ifdef ACB_EXP_NOPROBE
+                hits = (W[0] ^ W[3] ^ W[5] ^ W[8]) == 0x12345678u ? 1u : 0u;     /* timing experiment: the stream skeleton alone */
+#else
+                if constexpr (MODE == kModePair) hits = probe_pair(c, W, mulp);
+                else hits = probe_single<NW, STRIDE, MODE == kModeWide>(c, W, mul);
+#endif
+                if (n_valid - slice_off < (uint32_t)kSliceBytes) {       /* last slice of the segment: probes that start past it */
+                    const int v = (int)(n_valid - slice_off) - lane * 32;
+                    const int valid = (MODE == kModePair) ? v : (v + STRIDE - 1) / STRIDE;
+                    hits = (valid <= 0) ? 0u : ((valid >= 32) ? hits : (hits & ((1u << valid) - 1u)));
+                }
+                /* queue the survivors (ballot-ranked append into the warp's ring) with hash2 of their gram, which is
+                   read back from the stage: it stays ours until the arrive below */
+#ifdef ACB_EXP_NOSURV
+                if (hits == 0x9e3779b9u) qtail += 1u;                    /* timing experiment: probes only, survivors dropped */
+                hits = 0;
+#endif
+                unsigned any = __ballot_sync(kFull, hits != 0);
+                while (any) {
+                    const bool has = hits != 0;
+                    uint2 cand = make_uint2(0, 0);
+                    if (has) {
+                        const uint32_t t = (uint32_t)(__ffs(hits) - 1) * (MODE == kModePair ? 1u : (uint32_t)STRIDE);
+                        hits &= hits - 1;
+                        const uint32_t ga = saddr + t, wa = ga & ~3u, sh = (ga & 3u) * 8u;
+                        uint32_t tag = 0, w0 = lds32(wa);
+#pragma unroll
+                        for (int k = 0; k < NW; k++) {
+                            const uint32_t w1 = lds32(wa + 4u * (k + 1));
+                            tag += __funnelshift_r(w0, w1, sh) * mul2[k];
+                            w0 = w1;
+                        }
+                        cand = make_uint2(tile_off + slice_off + (uint32_t)lane * 32u + t, tag | 1u);
+                    }
+                    if (has) wr.queue[(qtail + __popc(any & lt_mask)) & (kQueueCap - 1)] = cand;
+#ifdef ACB_EXP_NODRAIN
+                    if (cand.y == 0x9e3779b9u) qtail += 1u;              /* timing experiment: survivors hashed, then dropped */
+#else
+                    qtail += __popc(any);
+#endif
+                    if (qtail - qhead > (uint32_t)(kQueueCap - 32)) drain_queue(p, wr, qhead, qtail, false, lane);
+                    any = __ballot_sync(kFull, hits != 0);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8u * stage);          /* this warp is done with the stage */
+            if (qtail - qhead >= 32u) drain_queue(p, wr, qhead, qtail, false, lane);
+        }
+        drain_queue(p, wr, qhead, qtail, true, lane);                    /* leftovers */
     }
-    ACB_STAMP(3);
-    if (p.inline_resolve) drain_queue(p, wr, qhead, qtail, true, lane);  /* leftovers */
-    else spill_queue(c, qhead, qtail, true);
-    ACB_STAMP(4);
     /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
     __syncthreads();
     if (tid == 0) {
@@ -580,44 +617,6 @@ __global__ void __launch_bounds__(kThreads, 1) acb_filter_kernel(const __grid_co
         if (done == gridDim.x - 1) {
             p.work_ctr[0] = 0u;
             p.work_ctr[1] = 0u;
-            __threadfence();
-        }
-    }
-    ACB_STAMP(5);
-}
-
-/* ------------------------------------------------------- the verify kernel */
-/* Overflow path of stage 3: resolves the candidates that warps had to spill to the global list
- * (normally none).  Each candidate is resolved through the anchor table (open addressing, 32-byte slots):
- * UNIQUE anchor -> the single key that can match is compared with the text;
- * MULTI anchor  -> exact gram compare, then a trie walk from the root. */
-
-__global__ void __launch_bounds__(kVerThreads) acb_verify_kernel(const __grid_constant__ ScanParams p) {
-    __shared__ acb_match s_stage[kVerWarps * kStageCap];
-    __shared__ int s_cnt[kVerWarps];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < kVerWarps) s_cnt[tid] = 0;
-    __syncthreads();
-    WarpStage ws;
-    ws.buf = s_stage + warp * kStageCap;
-    ws.cnt = s_cnt + warp;
-    const unsigned long long found = *p.cand_count;
-    const unsigned long long n = found < p.cand_cap ? found : p.cand_cap;
-    const unsigned long long gwarp = (unsigned long long)blockIdx.x * kVerWarps + warp;
-    const unsigned long long nwarps = (unsigned long long)gridDim.x * kVerWarps;
-    for (unsigned long long w0 = gwarp * 32; w0 < n; w0 += nwarps * 32) {
-        if (w0 + lane < n) resolve(p, ws, p.cand[w0 + lane]);
-        flush_stage(p, ws, lane);
-    }
-    /* last CTA out: re-arm the candidate counter; flag an overflowed candidate list in *count */
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        unsigned int done = atomicAdd(p.work_ctr + 2, 1u);
-        if (done == gridDim.x - 1) {
-            if (found > p.cand_cap) *p.count = ~0ULL;       /* results incomplete: caller must retry */
-            *p.cand_count = 0ULL;
-            p.work_ctr[2] = 0u;
             __threadfence();
         }
     }
@@ -740,18 +739,14 @@ __global__ void __launch_bounds__(kDfaThreads) acb_long_kernel(const __grid_cons
 struct acb_table {
     int device = 0;
     int sm_count = 0;
-    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log2 = 15, log3 = 0, logA = 10, filter_flags = 0;
+    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, logA = 10, filter_flags = 0;
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     uint8_t *d_cls = nullptr;
     int32_t *d_lfail = nullptr;
     int32_t *d_goto = nullptr, *d_fail = nullptr, *d_keyof = nullptr, *d_outptr = nullptr, *d_outidx = nullptr, *d_keylen = nullptr;
-    uint32_t *d_bm1 = nullptr, *d_bm2 = nullptr, *d_bm3 = nullptr, *d_anchors = nullptr;
+    uint32_t *d_bm1 = nullptr, *d_anchors = nullptr;
     unsigned int *d_work = nullptr;
-    uint2 *d_cand = nullptr;                 /* candidate list (filter -> verify) */
-    unsigned long long cand_cap = 0;
-    unsigned long long *d_cand_count = nullptr;
-    bool cand_worst_case = false;
     long long dev_bytes = 0;
     std::vector<int32_t> key_len;            /* host copy, for sorting records */
     /* workspace of acb_scan_host */
@@ -790,8 +785,8 @@ extern "C" void acb_table_free(acb_table *tb) {
     if (!tb) return;
     cudaSetDevice(tb->device);
     cudaFree(tb->d_lfail); cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
-    cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_bm2); cudaFree(tb->d_bm3); cudaFree(tb->d_anchors);
-    cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->d_cand_count); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
+    cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_anchors);
+    cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
     if (tb->h_count) cudaFreeHost(tb->h_count);
     if (tb->h_out) cudaFreeHost(tb->h_out);
     if (tb->ev0) cudaEventDestroy(tb->ev0);
@@ -820,7 +815,7 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { acb_set_error("cudaGetDeviceProperties failed"); rc = ACB_ECUDA; break; }
         tb->sm_count = prop.multiProcessorCount;
         tb->S = f.n_states; tb->K = f.n_classes; tb->L = f.letter_bytes; tb->n_keys = f.n_keys;
-        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log2 = f.log2_bits2; tb->log3 = f.log2_bits3; tb->logA = f.log2_anchor_slots; tb->filter_flags = f.filter_flags;
+        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->logA = f.log2_anchor_slots; tb->filter_flags = f.filter_flags;
         tb->min_key_bytes = f.min_key_bytes; tb->max_key_bytes = f.max_key_bytes;
         acb_hash_multipliers(tb->gram, 1, tb->mul1);
         acb_hash_multipliers(tb->gram, 2, tb->mul2);
@@ -846,14 +841,10 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if ((rc = upload(&tb->d_outptr, f.out_ptr, (size_t)f.n_states + 1, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_outidx, f.out_idx, (size_t)f.out_ptr[f.n_states], tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_keylen, f.key_len, (size_t)f.n_keys, tb->dev_bytes))) break;
-        if ((rc = upload(&tb->d_bm1, f.bitmap1, (size_t)7 << (f.log2_bits1 - 8), tb->dev_bytes))) break;
-        if ((rc = upload(&tb->d_bm2, f.bitmap2, (size_t)1 << (f.log2_bits1 - 8), tb->dev_bytes))) break;
-        if ((rc = upload(&tb->d_bm3, f.bitmap3, f.log2_bits3 ? ((size_t)1 << (f.log2_bits3 - 5)) : 1, tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_bm1, f.bitmap1, (size_t)1 << (f.log2_bits1 - 5), tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_anchors, f.anchors, (size_t)8 << f.log2_anchor_slots, tb->dev_bytes))) break;
         unsigned int zero[4] = {0, 0, 0, 0};   /* work counters, re-armed by the kernels themselves */
         if ((rc = upload(&tb->d_work, zero, 4, tb->dev_bytes))) break;
-        unsigned long long zero64 = 0;
-        if ((rc = upload(&tb->d_cand_count, &zero64, 1, tb->dev_bytes))) break;
     } while (0);
     if (rc != ACB_OK) { acb_table_free(tb); return rc; }
     *out = tb;
@@ -861,77 +852,63 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
 }
 
 extern "C" int64_t acb_table_device_bytes(const acb_table *tb) { return tb ? tb->dev_bytes : 0; }
-extern "C" int acb_table_reserve_candidates(acb_table *tb, int worst_case) {
-    if (!tb) return ACB_EINVAL;
-    tb->cand_worst_case = worst_case != 0;
-    return ACB_OK;
-}
 extern "C" int64_t acb_launch_count(void) { return g_launches.load(); }
 extern "C" int acb_set_kernel_timing(int enabled) { g_timing.store(enabled ? 1 : 0); return ACB_OK; }
 extern "C" float acb_last_kernel_ms(void) { return g_last_ms; }
 
 /* ------------------------------------------------------------- launching */
 
-static size_t filter_smem_bytes(int log1) {
-    return ((size_t)1 << (log1 - 3)) + (size_t)kWarps * kQueueCap * sizeof(uint2) +
-           (size_t)kWarps * kStageCap * sizeof(acb_match) + (size_t)kWarps * sizeof(int);
-}
-
-template <int NW, int STRIDE, bool WIDE>
-static int launch_filter_w(const ScanParams &p, int grid, cudaStream_t s) {
-    auto kern = acb_filter_kernel<NW, STRIDE, WIDE>;
-    const size_t smem = filter_smem_bytes(p.log1);
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, s>>>(p);
+template <int NW, int STRIDE, int MODE>
+static int launch_stream_m(const ScanParams &p, int grid, cudaStream_t s) {
+    auto kern = acb_stream_kernel<NW, STRIDE, MODE>;
+    const size_t smem = stream_smem(p.log1).total;
+    static std::atomic<size_t> opted{0};                     /* per instantiation: the largest size opted into so far */
+    if (opted.load(std::memory_order_relaxed) < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opted.store(smem, std::memory_order_relaxed);
+    }
+    kern<<<grid, kFThreads, smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     return ACB_OK;
 }
 
-/* WIDE follows from the gram length (acb_hash_is_wide) */
+/* the placement mode follows from the table's filter_flags */
 template <int NW, int STRIDE>
-static int launch_filter_t(const ScanParams &p, int grid, cudaStream_t s) {
-    if (p.filter_flags & ACB_FILTER_WIDE) {
-        if (p.gram != 4 * NW) { acb_set_error("WIDE filter with gram %d", p.gram); return ACB_EINVAL; }
-        return launch_filter_w<NW, STRIDE, true>(p, grid, s);
+static int launch_stream_t(const ScanParams &p, int flags, int grid, cudaStream_t s) {
+    if (flags & ACB_FILTER_PAIR) {
+        if (NW != 1 || STRIDE != 1 || p.gram != 4 || p.L != 1) { acb_set_error("PAIR filter needs gram 4, stride 1, 1-byte letters"); return ACB_EINVAL; }
+        return launch_stream_m<1, 1, kModePair>(p, grid, s);
     }
-    return launch_filter_w<NW, STRIDE, false>(p, grid, s);
+    if (flags & ACB_FILTER_WIDE) {
+        if (p.gram != 4 * NW) { acb_set_error("WIDE filter with gram %d", p.gram); return ACB_EINVAL; }
+        return launch_stream_m<NW, STRIDE, kModeWide>(p, grid, s);
+    }
+    return launch_stream_m<NW, STRIDE, kModeNarrow>(p, grid, s);
 }
 
 template <int NW>
-static int launch_filter_s(const ScanParams &p, int stride, int grid, cudaStream_t s) {
+static int launch_stream_s(const ScanParams &p, int flags, int stride, int grid, cudaStream_t s) {
     switch (stride) {
-        case 1:  return launch_filter_t<NW, 1>(p, grid, s);
-        case 2:  return launch_filter_t<NW, 2>(p, grid, s);
-        case 4:  return launch_filter_t<NW, 4>(p, grid, s);
-        case 8:  return launch_filter_t<NW, 8>(p, grid, s);
-        case 16: return launch_filter_t<NW, 16>(p, grid, s);
+        case 1:  return launch_stream_t<NW, 1>(p, flags, grid, s);
+        case 2:  return launch_stream_t<NW, 2>(p, flags, grid, s);
+        case 4:  return launch_stream_t<NW, 4>(p, flags, grid, s);
+        case 8:  return launch_stream_t<NW, 8>(p, flags, grid, s);
+        case 16: return launch_stream_t<NW, 16>(p, flags, grid, s);
     }
     acb_set_error("unsupported filter stride %d", stride);
     return ACB_EINVAL;
 }
 
-static int launch_filter(const ScanParams &p, int stride, int grid, cudaStream_t s) {
+static int launch_stream(const ScanParams &p, int flags, int stride, int grid, cudaStream_t s) {
     switch ((p.gram + 3) / 4) {
-        case 1: return launch_filter_s<1>(p, stride, grid, s);
-        case 2: return launch_filter_s<2>(p, stride, grid, s);
-        case 3: return launch_filter_s<3>(p, stride, grid, s);
-        case 4: return launch_filter_s<4>(p, stride, grid, s);
+        case 1: return launch_stream_s<1>(p, flags, stride, grid, s);
+        case 2: return launch_stream_s<2>(p, flags, stride, grid, s);
+        case 3: return launch_stream_s<3>(p, flags, stride, grid, s);
+        case 4: return launch_stream_s<4>(p, flags, stride, grid, s);
     }
     acb_set_error("unsupported gram length %d", p.gram);
     return ACB_EINVAL;
-}
-
-/* candidate list capacity for a segment of `seg` bytes: 1/8 of the probe positions by default,
- * every probe position once a scan has reported an overflow (acb_scan_host retries that way) */
-static int ensure_candidates(acb_table *tb, long long seg, bool worst_case) {
-    unsigned long long probes = (unsigned long long)(seg / tb->stride + 1);
-    unsigned long long want = worst_case ? probes : std::max<unsigned long long>(1ULL << 20, probes / 8);
-    if (tb->d_cand && tb->cand_cap >= want) return ACB_OK;
-    if (tb->d_cand) { cudaFree(tb->d_cand); tb->d_cand = nullptr; tb->cand_cap = 0; }
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_cand), (size_t)want * sizeof(uint2)));
-    tb->cand_cap = want;
-    return ACB_OK;
 }
 
 extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t total_bytes,
@@ -957,9 +934,9 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     p.n_hay = n_hay; p.stride_bytes = stride_bytes;
     p.cls = tb->d_cls; p.gto = tb->d_goto; p.fail = tb->d_fail; p.letter_fail = tb->d_lfail; p.key_of = tb->d_keyof;
     p.out_ptr = tb->d_outptr; p.out_idx = tb->d_outidx; p.key_len = tb->d_keylen;
-    p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.filter_flags = tb->filter_flags; p.max_key_bytes = tb->max_key_bytes;
-    p.bm1 = tb->d_bm1; p.bm2 = tb->d_bm2; p.bm3 = tb->d_bm3; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
-    p.log1 = tb->log1; p.log2 = tb->log2; p.log3 = tb->log3; p.logA = tb->logA;
+    p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.max_key_bytes = tb->max_key_bytes;
+    p.bm1 = tb->d_bm1; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
+    p.log1 = tb->log1; p.logA = tb->logA;
     memcpy(p.mul1, tb->mul1, sizeof(p.mul1));
     memcpy(p.mul2, tb->mul2, sizeof(p.mul2));
     p.out = d_out; p.cap = cap; p.count = reinterpret_cast<unsigned long long *>(d_count);
@@ -967,11 +944,6 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     p.stride_shift = -1;
     if (!d_offsets) for (int b = 0; b < 62; b++) if ((1LL << b) == stride_bytes) p.stride_shift = b;
     p.letter_shift = tb->L == 4 ? 2 : (tb->L == 2 ? 1 : 0);
-    {
-        static int inl = -1;
-        if (inl < 0) { const char *e = getenv("ACB_INLINE_RESOLVE"); inl = e ? atoi(e) : 1; }
-        p.inline_resolve = inl;
-    }
 
     if (algo == ACB_ALGO_AUTO) algo = ACB_ALGO_FILTER;
     if (tb->n_keys == 0) return ACB_OK;                     /* empty key set: nothing can match */
@@ -981,53 +953,13 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
         CUDA_TRY(cudaEventRecord(tb->ev0, s));
     }
     if (algo == ACB_ALGO_FILTER) {
-        int rc = ensure_candidates(tb, std::min<long long>(total_bytes, kSegBytes), tb->cand_worst_case);
-        if (rc != ACB_OK) return rc;
-        p.cand = tb->d_cand; p.cand_cap = tb->cand_cap; p.cand_count = tb->d_cand_count;
         for (long long seg = 0; seg < total_bytes; seg += kSegBytes) {
             p.seg_begin = seg;
             p.seg_end = std::min<long long>(seg + kSegBytes, total_bytes);
-            p.n_blocks = (p.seg_end - p.seg_begin + kBlockBytes - 1) / kBlockBytes;
-            int grid = (int)std::min<long long>(tb->sm_count, p.n_blocks);
-            unsigned long long *d_tl = nullptr;
-            const size_t n_tl = (size_t)grid * kWarps * 6;
-            if (getenv("ACB_TIMELINE")) {                       /* diagnostic: per-warp phase timestamps */
-                cudaMalloc(reinterpret_cast<void **>(&d_tl), n_tl * 8);
-                cudaMemset(d_tl, 0, n_tl * 8);
-                p.timeline = d_tl;
-            }
-            rc = launch_filter(p, tb->stride, grid, s);
+            p.n_tiles = (unsigned int)((p.seg_end - p.seg_begin + kTileBytes - 1) / kTileBytes);
+            const int grid = (int)std::min<long long>(tb->sm_count, p.n_tiles);
+            int rc = launch_stream(p, tb->filter_flags, tb->stride, grid, s);
             if (rc != ACB_OK) return rc;
-            if (d_tl) {
-                std::vector<unsigned long long> tl(n_tl);
-                cudaStreamSynchronize(s);
-                cudaMemcpy(tl.data(), d_tl, n_tl * 8, cudaMemcpyDeviceToHost);
-                cudaFree(d_tl);
-                p.timeline = nullptr;
-                unsigned long long t0 = ~0ULL;
-                for (size_t w = 0; w < n_tl / 6; w++) if (tl[w * 6]) t0 = std::min(t0, tl[w * 6]);
-                const char *nm[6] = {"start", "bitmap ready", "first unit claimed", "stream done", "drained", "exit"};
-                for (int k = 0; k < 6; k++) {
-                    std::vector<double> v;
-                    for (size_t w = 0; w < n_tl / 6; w++) if (tl[w * 6 + k]) v.push_back((double)(tl[w * 6 + k] - t0) / 1000.0);
-                    if (v.empty()) continue;
-                    std::sort(v.begin(), v.end());
-                    fprintf(stderr, "[timeline] %-20s n=%6zu  min %8.2f  p50 %8.2f  p90 %8.2f  max %8.2f us\n", nm[k], v.size(),
-                            v.front(), v[v.size() / 2], v[v.size() * 9 / 10], v.back());
-                }
-            }
-            if (getenv("ACB_DEBUG")) {                          /* diagnostic: size of the spilled candidate list */
-                unsigned long long cc = 0, mc = 0;
-                cudaStreamSynchronize(s);
-                cudaMemcpy(&cc, tb->d_cand_count, sizeof(cc), cudaMemcpyDeviceToHost);
-                cudaMemcpy(&mc, p.count, sizeof(mc), cudaMemcpyDeviceToHost);
-                fprintf(stderr, "[acb_scan_device] segment %lld..%lld: %llu candidates spilled (cap %llu), %llu matches so far, gram %d stride %d log3 %d\n",
-                        p.seg_begin, p.seg_end, cc, (unsigned long long)p.cand_cap, mc, p.gram, tb->stride, p.log3);
-            }
-            acb_verify_kernel<<<p.inline_resolve ? tb->sm_count : tb->sm_count * 6, kVerThreads, 0, s>>>(p);
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) { acb_set_error("verify kernel launch failed: %s", cudaGetErrorString(e)); return ACB_ECUDA; }
-            g_launches.fetch_add(1);
         }
     } else if (algo == ACB_ALGO_DFA) {
         long long spans = (total_bytes + kDfaSpan - 1) / kDfaSpan;
@@ -1199,11 +1131,6 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
     CUDA_TRY(cudaStreamSynchronize(s));
     if (trace) t2 = now();
     unsigned long long n = *tb->h_count;
-    if (n == ~0ULL) {                                           /* candidate list overflowed: redo with room for every probe */
-        if (tb->cand_worst_case) { acb_set_error("candidate list overflow even at worst-case capacity"); return ACB_ECUDA; }
-        tb->cand_worst_case = true;
-        return acb_scan_host(tb, hay, total_bytes, offsets, n_hay, stride_bytes, out, cap, n_found, algo, sort);
-    }
     *n_found = (int64_t)n;
     if (n > (unsigned long long)cap) {
         acb_set_error("match buffer too small: %llu matches, capacity %lld", n, (long long)cap);
@@ -1248,3 +1175,4 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
     }
     return ACB_OK;
 }
+

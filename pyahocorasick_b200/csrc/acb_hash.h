@@ -11,7 +11,7 @@
  *      h  = sum_k  w_k * mul[k]      (mod 2^32)
  *      bit index = h >> (32 - log2_bits)
  *
- * Stage 1 (shared-memory bitmap) and stage 2 (global bitmap) use different odd
+ * The shared-memory bitmap (hash 1) and the anchor table (hash 2, the "tag") use different odd
  * multiplier sets so that their false positives are independent.
  */
 #ifndef ACB_HASH_H_INCLUDED
@@ -37,7 +37,6 @@
 #define ACB_S2_M1 0xD3A2646Du
 #define ACB_S2_M2 0xFD7046C5u
 #define ACB_S2_M3 0xB55A4F09u
-#define ACB_S3_MIX 0x9E3779B1u   /* stage 3 (global bitmap): bit index = (tag * ACB_S3_MIX) >> (32 - log2_bits3) */
 
 /* fill mul[0..3] for a gram of g bytes; stage = 1 or 2 */
 ACB_HD void acb_hash_multipliers(int g, int stage, uint32_t mul[ACB_MAX_WINDOWS]) {
@@ -102,5 +101,28 @@ ACB_HD uint32_t acb_stage1_bit_a(uint64_t hw, int g, int log2_bits) {
     return acb_hash_is_wide(g) ? ((uint32_t)(hw >> 32) & 31u) : (((uint32_t)hw >> (32 - log2_bits)) & 31u);
 }
 ACB_HD uint32_t acb_stage1_bit_b(uint64_t hw) { return (uint32_t)hw & 31u; }
+
+/* ---- PAIR placement (gram 4, stride 1, 1-byte letters) --------------------------------------------------
+ * Positions x (even) and x+1 share ONE bitmap word, selected by the three bytes their 4-byte grams have in
+ * common, so the probe loop needs one shared-memory load per two positions.  With mulp = ACB_PAIR_M << 8 and
+ * G the gram read as a little-endian word:   P = (uint64)G * mulp
+ *      low half  : depends on bytes 0..2 of G only (the top byte is shifted out)  -> word index of the pair in
+ *                  which G plays role 1 (G starts at the odd position x+1; its bytes 0..2 are the common ones)
+ *      high half : low 5 bits = bit `a` of G, depends on all four bytes
+ * Role 0 (G starts at the even position x; the common bytes are its bytes 1..3): the word is selected by the low
+ * half of (G >> 8) * mulp.  The second bit of a gram is the low 5 bits of its one byte OUTSIDE the common three:
+ * byte 0 in role 0, byte 3 in role 1.  Every key gram is entered under both roles (a key may start anywhere). */
+#define ACB_PAIR_M 0x9E3779B1u
+ACB_HD uint32_t acb_pair_mul(void) { return ACB_PAIR_M << 8; }
+/* role 0 / 1 placement of gram G: *word = index into n_words words, *bits = the two bits to set / test */
+ACB_HD void acb_pair_place(uint32_t G, int role, uint32_t n_words, uint32_t *word, uint32_t *bits) {
+    const uint32_t mulp = ACB_PAIR_M << 8;
+    const uint32_t a = (uint32_t)(((uint64_t)G * mulp) >> 32) & 31u;
+    const uint32_t common = role ? G : (G >> 8);
+    const uint32_t lo = (uint32_t)((uint64_t)common * mulp);
+    const uint32_t b = (role ? (G >> 24) : G) & 31u;
+    *word = (uint32_t)(((uint64_t)lo * n_words) >> 32);
+    *bits = (1u << a) | (1u << b);
+}
 
 #endif

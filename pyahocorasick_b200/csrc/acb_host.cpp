@@ -104,8 +104,8 @@ struct Flat {
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint8_t byte_class[256];
     std::vector<int32_t> goto_cm, fail, letter_fail, key_of, out_ptr, out_idx, key_len;
-    int32_t gram = 0, stride = 0, log1 = 0, log2 = 0, log3 = 0, logA = 0, filter_flags = 0;
-    std::vector<uint32_t> bm1, bm2, bm3, anchors;
+    int32_t gram = 0, stride = 0, log1 = 0, logA = 0, filter_flags = 0;
+    std::vector<uint32_t> bm1, anchors;
 };
 
 } // namespace
@@ -388,13 +388,27 @@ static void build_filter(acb_trie *t, Flat &f) {
         }
     }
     pt.lap("filter: prefixes");
-    int forced_g = 0, forced_s = 0, forced_l1 = 0;
-    if (const char *env = getenv("ACB_FILTER")) sscanf(env, "%d,%d,%d", &forced_g, &forced_s, &forced_l1);
+    int forced_g = 0, forced_s = 0, forced_l1 = 0, forced_mode = -1;     /* ACB_FILTER=g,s,log1,mode (0 single, 1 pair) */
+    if (const char *env = getenv("ACB_FILTER")) sscanf(env, "%d,%d,%d,%d", &forced_g, &forced_s, &forced_l1, &forced_mode);
 
+    /* Pick gram length g, probe stride s and the placement (single / pair) by a small cost model, in issue
+     * cycles per text byte of one SM sub-partition: a single-position probe is bound by the
+     * bank conflicts of its shared-memory load (about 17 cycles per position and warp), a pair probe by the ALU
+     * pipe (about 9); every survivor of the bitmap costs an anchor-table visit in L2 and a divergent round. */
     const double Kb = std::max(1, f.K - 1);
     FilterChoice best;
+    int best_pair = 0;
     std::vector<Gram16> best_grams;
     std::vector<uint64_t> scratch;
+    auto pass_rate = [](double lambda) {                 /* blocked Bloom, k = 2: P(both bits of a foreign gram are set) */
+        double pass = 0, pn = std::exp(-lambda);         /* Poisson(n; lambda) entries in the word */
+        for (int n = 1; n <= 64; n++) {
+            pn *= lambda / n;
+            const double bits = 32.0 * (1.0 - std::pow(1.0 - 1.0 / 32.0, 2.0 * n));   /* distinct bits set by n entries */
+            pass += pn * std::min(1.0, bits * (bits - 1.0) / (32.0 * 31.0));
+        }
+        return pass;
+    };
     for (int s = L; s <= 16; s *= 2) {
         if (forced_s && s != forced_s) continue;
         int gmax = std::min(ACB_MAX_GRAM, m - s + L);
@@ -408,15 +422,20 @@ static void build_filter(acb_trie *t, Flat &f) {
             const double E = (double)count_grams(prefixes, g, s, L, scratch);
             int log1 = std::min(20, std::max(13, ceil_log2_u64((uint64_t)(E * 64.0) + 1)));
             if (forced_l1) log1 = forced_l1;
-            double space = std::pow(Kb, (double)g);
-            double p_true = std::min(1.0, E / space);
-            double fill1 = std::min(1.0, E / (0.875 * std::pow(2.0, log1)));
-            int nw = (g + 3) / 4;
-            double pass1 = p_true + (1 - p_true) * fill1;
-            /* per byte: probe instructions + anchor lookups for stage-1 survivors + key compares */
-            double cost = ((4.0 + 3.0 * nw) + pass1 * 40.0 + p_true * (s / L) * 40.0) / s;
-            if (cost < best.cost) {
-                best.g = g; best.s = s; best.log1 = log1; best.cost = cost;
+            const double words = std::pow(2.0, log1 - 5);
+            const double space = std::pow(Kb, (double)g);
+            const double p_true = std::min(1.0, E / space);
+            const int nw = (g + 3) / 4;
+            for (int pair = 0; pair <= 1; pair++) {
+                if (pair && !(L == 1 && s == 1 && g == 4)) continue;
+                if (forced_mode >= 0 && pair != forced_mode) continue;
+                const double pass1 = p_true + (1 - p_true) * pass_rate((pair ? 2.0 : 1.0) * E / words);
+                const double probe = pair ? 9.0 : std::max(17.0, 5.0 + 3.0 * nw);
+                const double cost = (probe + pass1 * 120.0 + p_true * (s / L) * 40.0) / s;
+                if (cost < best.cost) {
+                    best.g = g; best.s = s; best.log1 = log1; best.cost = cost;
+                    best_pair = pair;
+                }
             }
         }
     }
@@ -426,26 +445,31 @@ static void build_filter(acb_trie *t, Flat &f) {
     f.gram = g;
     f.stride = s;
     f.log1 = best.log1;
-    /* The 2^log1 bits of shared memory are split 7/8 : 1/8 between the stage-1 bitmap (probed at
-     * every position, indexed by hash1) and the stage-2 bitmap (probed only by stage-1 survivors,
-     * indexed by hash2):  word1 = umulhi(hash1, 7 << (log1-8)), bits acb_stage1_bit_a AND acb_stage1_bit_b (acb_hash.h);
-     *                     word2 = hash2 >> (40-log1),           bit2 = (hash2 >> (35-log1)) & 31. */
-    const uint32_t mulw1 = 7u << (best.log1 - 8);
-    f.bm1.assign((size_t)7 << (best.log1 - 8), 0);
-    f.bm2.assign((size_t)1 << (best.log1 - 8), 0);
-    f.log2 = best.log1 - 3;
+    /* The bitmap: 2^log1 bits of shared memory, 2^(log1-5) words.  A gram sets two bits of ONE word (a blocked
+     * Bloom filter with k = 2: the probe costs one shared-memory load, and a random gram has to find BOTH bits set).
+     *   single: word = umulhi(hash1, n_words), bits acb_stage1_bit_a AND acb_stage1_bit_b (acb_hash.h);
+     *   pair  : acb_pair_place, every gram once per role. */
+    const uint32_t n_words = 1u << (best.log1 - 5);
+    f.bm1.assign((size_t)n_words, 0);
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     acb_hash_multipliers(g, 1, mul1);
     acb_hash_multipliers(g, 2, mul2);
-    f.filter_flags = acb_hash_is_wide(g) ? ACB_FILTER_WIDE : 0;
+    f.filter_flags = best_pair ? ACB_FILTER_PAIR : (acb_hash_is_wide(g) ? ACB_FILTER_WIDE : 0);
     for (const auto &gr : best_grams) {
-        const uint64_t hw = acb_hash_bytes_wide(gr.data(), g, mul1);
-        uint32_t h1 = (uint32_t)hw, h2 = acb_hash_bytes(gr.data(), g, mul2) | 1u;
-        /* two bits per gram inside one word (a blocked Bloom filter with k = 2): the probe costs one
-           shared-memory load either way, and a random gram now has to find BOTH bits set */
-        const uint32_t bits = (1u << acb_stage1_bit_a(hw, g, best.log1)) | (1u << acb_stage1_bit_b(hw));
-        f.bm1[(size_t)(((uint64_t)h1 * mulw1) >> 32)] |= bits;
-        f.bm2[h2 >> (40 - best.log1)] |= 1u << ((h2 >> (35 - best.log1)) & 31);
+        if (best_pair) {
+            const uint8_t *b = gr.data();
+            const uint32_t G = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+            for (int role = 0; role < 2; role++) {
+                uint32_t word, bits;
+                acb_pair_place(G, role, n_words, &word, &bits);
+                f.bm1[word] |= bits;
+            }
+        } else {
+            const uint64_t hw = acb_hash_bytes_wide(gr.data(), g, mul1);
+            const uint32_t h1 = (uint32_t)hw;
+            const uint32_t bits = (1u << acb_stage1_bit_a(hw, g, best.log1)) | (1u << acb_stage1_bit_b(hw));
+            f.bm1[(size_t)(((uint64_t)h1 * n_words) >> 32)] |= bits;
+        }
     }
 
     pt.lap("filter: bitmaps");
@@ -543,20 +567,6 @@ static void build_filter(acb_trie *t, Flat &f) {
         a = b;
     }
     pt.lap("filter: anchor entries");
-    /* stage 3: a bitmap in global memory over a re-mix of the tag, 64 bits per distinct tag.  Only used
-     * when the shared-memory bitmaps are too full to reject much (large key sets): it keeps the flood of
-     * survivors away from the anchor table at the price of one L2 access each. */
-    {
-        const double fill2 = (double)best_grams.size() / std::pow(2.0, best.log1 - 3);
-        f.log3 = 0;
-        f.bm3.assign(1, 0);
-        if (fill2 > 0.25) {
-            int log3 = std::min(30, std::max(16, ceil_log2_u64((uint64_t)entries.size() * 64 + 1)));
-            f.log3 = log3;
-            f.bm3.assign((size_t)1 << (log3 - 5), 0);
-            for (const Entry &e : entries) set_bit(f.bm3, (e.w[0] * ACB_S3_MIX) >> (32 - log3));
-        }
-    }
     int logA = std::max(10, ceil_log2_u64((uint64_t)entries.size() * 4 + 1));     /* load factor <= 1/4 */
     if (logA > 28) logA = 28;
     while (((size_t)1 << logA) < entries.size() + entries.size() / 4 + 1) logA++;
@@ -573,7 +583,7 @@ static void build_filter(acb_trie *t, Flat &f) {
         while (f.anchors[i * 8] != 0) i = (i + 1) & mask;
         memcpy(&f.anchors[i * 8], e.w, sizeof(e.w));
     }
-    pt.lap("filter: stage 3 + anchor table");
+    pt.lap("filter: anchor table");
 }
 
 /* ----------------------------------------------- make_automaton + flatten */
@@ -692,12 +702,9 @@ extern "C" int acb_trie_make_automaton(acb_trie *t, int32_t *built) {
         pt.lap("goto / fail / outputs");
         if (f.n_keys > 0) build_filter(t, f);
         else {                                               /* nothing can ever match */
-            f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.log2 = 10; f.logA = 10;
+            f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.logA = 10;
             f.filter_flags = acb_hash_is_wide(f.gram) ? ACB_FILTER_WIDE : 0;
-            f.bm1.assign((size_t)7 << (13 - 8), 0);
-            f.bm2.assign((size_t)1 << (13 - 8), 0);
-            f.log3 = 0;
-            f.bm3.assign(1, 0);
+            f.bm1.assign((size_t)1 << (13 - 5), 0);
             f.anchors.assign(((size_t)1 << 10) * 8, 0);
         }
         f.valid = true;
@@ -737,12 +744,8 @@ extern "C" int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out) {
     out->gram_bytes = f.gram;
     out->stride = f.stride;
     out->log2_bits1 = f.log1;
-    out->log2_bits2 = f.log2;
-    out->log2_bits3 = f.log3;
     out->log2_anchor_slots = f.logA;
-    out->bitmap3 = f.bm3.data();
     out->bitmap1 = f.bm1.data();
-    out->bitmap2 = f.bm2.data();
     out->anchors = f.anchors.data();
     out->filter_flags = f.filter_flags;
     return ACB_OK;

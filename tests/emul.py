@@ -3,7 +3,7 @@ flattened tables produced by the host core.  It exists so that the CPU test-suit
 exercise the host logic (filter construction, flattening, the Python API layer) without
 a GPU; it is never imported by the product.
 
-emul_filter() restates acb_filter_kernel: stage-1 bitmap probe at every `stride`-th byte,
+emul_filter() restates acb_stream_kernel: the gram-bitmap probe at every `stride`-th byte (single or pair placement),
 then the anchor table (UNIQUE anchors compare the key, MULTI anchors walk the trie).  emul_dfa() restates
 acb_dfa_kernel (goto / fail / CSR outputs).  Both return records sorted the way
 acb_scan_host sorts them.
@@ -63,6 +63,7 @@ def hash_bytes_wide(buf, q, g, mul):
 
 
 FILTER_WIDE = 1
+FILTER_PAIR = 2
 
 
 def _bit(bm, idx):
@@ -101,11 +102,49 @@ def _entry_bytes(e, n):
     return raw[:n]
 
 
+PAIR_M = 0x9E3779B1
+
+
+def pair_place(G, role, n_words):
+    """acb_pair_place (csrc/acb_hash.h): word index and the two bits of gram G (little-endian u32) in one role"""
+    mulp = (PAIR_M << 8) & M32
+    a = ((G * mulp) >> 32) & 31
+    common = G if role else (G >> 8)
+    lo = (common * mulp) & M32
+    b = ((G >> 24) if role else G) & 31
+    return (lo * n_words) >> 32, (1 << a) | (1 << b)
+
+
+def _u32_at(buf, q):
+    """little-endian word at q, zero filled past the end of buf (the kernel may see other bytes there: they can
+    only add survivors that the anchor compare rejects)"""
+    n = len(buf)
+    return sum(int(buf[q + i]) << (8 * i) for i in range(4) if q + i < n)
+
+
+def _passes_bitmap(f, buf, q):
+    """the shared-memory bitmap test of acb_stream_kernel at probe position q"""
+    g, l1, flags = f["gram_bytes"], f["log2_bits1"], f["filter_flags"]
+    n_words = 1 << (l1 - 5)
+    if flags & FILTER_PAIR:
+        assert g == 4 and f["stride"] == 1 and f["letter_bytes"] == 1
+        role = q & 1                                   # x even: role 0 of pair (x, x+1); x odd: role 1 of (x-1, x)
+        word, bits = pair_place(_u32_at(buf, q), role, n_words)
+        return (int(f["bitmap1"][word]) & bits) == bits
+    mul1 = multipliers(g, 1)
+    hw = hash_bytes_wide(buf, q, g, mul1)
+    h1 = hw & M32
+    assert bool(flags & FILTER_WIDE) == (g % 4 == 0)
+    bit_a = ((hw >> 32) & 31) if flags & FILTER_WIDE else ((h1 >> (32 - l1)) & 31)
+    w1 = int(f["bitmap1"][(h1 * n_words) >> 32])
+    return bool((w1 >> bit_a) & (w1 >> (h1 & 31)) & 1)
+
+
 def emul_filter(f, buf, offsets=None, stride_bytes=0):
-    """stage 1 bitmap -> anchor table (UNIQUE: direct key compare, MULTI: trie walk)"""
+    """gram bitmap -> anchor table (UNIQUE: direct key compare, MULTI: trie walk)"""
     L, g, s = f["letter_bytes"], f["gram_bytes"], f["stride"]
-    mul1, mul2 = multipliers(g, 1), multipliers(g, 2)
-    l1, lA = f["log2_bits1"], f["log2_anchor_slots"]
+    mul2 = multipliers(g, 2)
+    lA = f["log2_anchor_slots"]
     anchors = f["anchors"]
     amask = (1 << lA) - 1
     total = len(buf)
@@ -115,22 +154,11 @@ def emul_filter(f, buf, offsets=None, stride_bytes=0):
     if f["n_keys"] == 0:
         return recs
     for q in range(0, total, s):
-        hw = hash_bytes_wide(buf, q, g, mul1)
-        h1 = hw & M32
-        flags = f["filter_flags"]
-        assert bool(flags & FILTER_WIDE) == (g % 4 == 0)
-        bit_a = ((hw >> 32) & 31) if flags & FILTER_WIDE else ((h1 >> (32 - l1)) & 31)
-        w1 = int(f["bitmap1"][(h1 * (7 << (l1 - 8))) >> 32])
-        if not ((w1 >> bit_a) & (w1 >> (h1 & 31)) & 1):
+        if not _passes_bitmap(f, buf, q):
             continue
         if q + g > total:
             continue
         tag = hash_bytes(buf, q, g, mul2) | 1
-        if not (int(f["bitmap2"][tag >> (40 - l1)]) >> ((tag >> (35 - l1)) & 31)) & 1:
-            continue
-        l3 = f["log2_bits3"]
-        if l3 and not _bit(f["bitmap3"], ((tag * 0x9E3779B1) & M32) >> (32 - l3)):
-            continue
         slot = tag >> (32 - lA)
         bounds = None
         while True:
