@@ -59,21 +59,32 @@
 namespace {
 
 #ifndef ACB_CONSUMERS
-#define ACB_CONSUMERS 16
+#define ACB_CONSUMERS 24
+#endif
+#ifndef ACB_RESOLVERS
+#define ACB_RESOLVERS 7
 #endif
 #ifndef ACB_STAGES
-#define ACB_STAGES 4
+#define ACB_STAGES 3
+#endif
+#ifndef ACB_LANE_BYTES
+#define ACB_LANE_BYTES 32
 #endif
 constexpr int kConsumers    = ACB_CONSUMERS;          /* consumer warps of the stream kernel           */
-constexpr int kFThreads     = (kConsumers + 1) * 32;  /* + the producer warp                           */
-constexpr int kSliceBytes   = 1024;                   /* one warp iteration: 32 bytes per lane         */
+constexpr int kResolvers    = ACB_RESOLVERS;          /* warps that resolve candidates through L2      */
+constexpr int kFThreads     = (kConsumers + kResolvers + 1) * 32;   /* + the producer warp             */
+constexpr int kLaneBytes    = ACB_LANE_BYTES;         /* text bytes per lane and iteration (16 or 32)  */
+constexpr int kLaneWords    = kLaneBytes / 4;
+constexpr int kSliceBytes   = 32 * kLaneBytes;        /* one warp iteration                            */
 constexpr int kTileBytes    = kConsumers * kSliceBytes;
 constexpr int kLook         = 16;                     /* bytes copied past a tile (gram look-ahead)    */
 constexpr int kStageBytes   = kTileBytes + 128;       /* tile + look-ahead, stages stay 128 B aligned  */
 constexpr int kStages       = ACB_STAGES;
-constexpr int kClaimDepth   = 8;                      /* tile claims in flight per producer (multiple of kStages) */
-constexpr int kQueueCap     = 128;                    /* bitmap survivors queued per warp (smem)       */
-constexpr int kStageCap     = 32;                     /* match records staged per warp (smem)          */
+constexpr int kClaimDepth   = 8;                      /* tile claims in flight per producer            */
+constexpr int kCandCap      = 1024;                   /* candidate ring of a CTA (smem), power of two  */
+constexpr int kBatch        = 64;                     /* candidates a resolver warp takes at a time    */
+constexpr int kStageCap     = 64;                     /* match records staged per resolver warp (smem) */
+static_assert(kFThreads <= 1024 && kTileBytes % 16 == 0 && (kCandCap & (kCandCap - 1)) == 0 && kBatch % 32 == 0, "stream kernel shape");
 constexpr uint32_t kFull    = 0xffffffffu;
 constexpr uint32_t kNoTile  = 0xffffffffu;
 constexpr int32_t  kTermBit = 0x40000000;             /* goto entry flag: child ends a key             */
@@ -161,7 +172,8 @@ __device__ __forceinline__ void emit(const ScanParams &p, const WarpStage &ws, i
     m.hay_id = h;
     m.end_index = e;
     m.key_id = k;
-    int slot = atomicAdd(ws.cnt, 1);
+    int slot;                                 /* ws.cnt is shared memory: a shared-space atomic, not a generic one */
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"((uint32_t)__cvta_generic_to_shared(ws.cnt)) : "memory");
     if (slot < kStageCap) {
         ws.buf[slot] = m;
     } else {                                  /* staging full: straight to global */
@@ -179,7 +191,9 @@ __device__ __forceinline__ void flush_stage(const ScanParams &p, const WarpStage
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(p.count, (unsigned long long)n);
         base = __shfl_sync(kFull, base, 0);
-        if (lane < n && base + lane < (unsigned long long)p.cap) p.out[base + lane] = ws.buf[lane];
+#pragma unroll
+        for (int i = lane; i < kStageCap; i += 32)
+            if (i < n && base + i < (unsigned long long)p.cap) p.out[base + i] = ws.buf[i];
     }
     __syncwarp();
     if (lane == 0) *ws.cnt = 0;
@@ -286,19 +300,35 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void resolve(const ScanParams &p, const WarpStage &ws, uint2 c) {
-    const long long q = p.seg_begin + (long long)c.x;
-    const uint32_t tag = c.y;
+/* hash2 (the anchor tag) of the gram at byte position q, from the aligned words load_text(q) returned */
+template <int NW>
+__device__ __forceinline__ uint32_t tag_of(const uint32_t (&tq)[6], long long q, const uint32_t (&mul2)[NW]) {
+    const int sh = (int)(q & 3) * 8;
+    uint32_t tag = 0;
+#pragma unroll
+    for (int k = 0; k < NW; k++) tag += __funnelshift_r(tq[k], tq[k + 1], sh) * mul2[k];
+    return tag | 1u;
+}
+
+/* Follow the anchor chain of `tag` for the candidate at q, starting with the slot (e0, e1) already loaded.
+ * Three ways out, in the order of their frequency on sparse-match text: an empty slot (the bitmap let a foreign
+ * gram through); ONE entry that is the last of its tag, UNIQUE and anchored at its first byte (every such lane of
+ * the warp runs the same straight-line compare); anything else takes the general loop. */
+__device__ __forceinline__ void resolve_chain(const ScanParams &p, const WarpStage &ws, long long q, uint32_t tag,
+                                              const uint32_t (&tq)[6], uint4 e0, uint4 e1) {
+    if (e0.x == 0u) return;
+    long long h = -1, hs = 0, he = 0;
+    if (e0.x == tag && (int32_t)e0.y >= 0 && (e0.z & 0x100ffu) == 0x10000u) {
+        const uint32_t kw[5] = {e0.w, e1.x, e1.y, e1.z, e1.w};
+        const int len = (int)((e0.z >> 8) & 0xffu);
+        find_haystack(p, q, h, hs, he);
+        if (q + len <= he && text_equals(tq, q, len, kw))
+            emit(p, ws, (int32_t)h, (int32_t)(((q + len - hs) >> p.letter_shift) - 1), (int32_t)e0.y);
+        return;
+    }
     const uint32_t amask = (1u << p.logA) - 1u;
     uint32_t slot = tag >> (32 - p.logA);
-    long long h = -1, hs = 0, he = 0;
-    /* the text at the probe position is fetched together with the anchor slot, not after it: for stride-1
-       filters (j == 0) that is the text every entry compares with, so the two L2 round trips overlap */
-    uint32_t tq[6];
-    load_text(p, q, tq);
     for (;;) {
-        const uint4 e0 = __ldg(p.anchors + 2 * (size_t)slot);             /* both halves of the 32-byte slot at once */
-        const uint4 e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
         if (e0.x == 0u) break;                                 /* empty slot ends the probe sequence */
         if (e0.x == tag) {
             const uint32_t kw[5] = {e0.w, e1.x, e1.y, e1.z, e1.w};
@@ -321,27 +351,20 @@ __device__ __forceinline__ void resolve(const ScanParams &p, const WarpStage &ws
             if (e0.z & 0x10000u) break;                        /* no further entry carries this tag */
         }
         slot = (slot + 1) & amask;
+        e0 = __ldg(p.anchors + 2 * (size_t)slot);
+        e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
     }
 }
 
-/* per-warp state of the candidate path (all in shared memory except the ring positions) */
-struct WarpResolve {
-    uint2 *queue;      /* candidates {pos, tag} that passed the bitmap, ring of kQueueCap */
-    WarpStage ws;
-};
-
-/* Resolve the warp's queued candidates through the anchor table, 32 at a time.  Called between slices, never
- * from the probe loop, so that none of the probe loop's registers are live across it.  While this warp waits on
- * L2 the other warps keep filtering. */
-__device__ __noinline__ void drain_queue(const ScanParams &p, const WarpResolve &wr, uint32_t &qhead, uint32_t qtail,
-                                         bool final_flush, int lane) {
-    while (qtail - qhead >= 32u || (final_flush && qtail != qhead)) {
-        __syncwarp();
-        const uint32_t n = (qtail - qhead >= 32u) ? 32u : (qtail - qhead);
-        if ((uint32_t)lane < n) resolve(p, wr.ws, wr.queue[(qhead + lane) & (kQueueCap - 1)]);
-        qhead += n;
-        flush_stage(p, wr.ws, lane);
-    }
+/* one candidate position, start to end (used for the second and later hits of a lane's 32 bytes) */
+template <int NW>
+__device__ __forceinline__ void resolve_one(const ScanParams &p, const WarpStage &ws, long long q, const uint32_t (&mul2)[NW]) {
+    uint32_t tq[6];
+    load_text(p, q, tq);
+    const uint32_t tag = tag_of<NW>(tq, q, mul2);
+    const uint32_t slot = tag >> (32 - p.logA);
+    const uint4 e0 = __ldg(p.anchors + 2 * (size_t)slot), e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
+    resolve_chain(p, ws, q, tag, tq, e0, e1);
 }
 
 /* what a consumer warp needs to probe a slice */
@@ -359,16 +382,16 @@ __device__ __forceinline__ uint32_t window(const uint32_t (&W)[N], int t) {
     return ((t & 3) == 0) ? W[t >> 2] : __funnelshift_r(W[t >> 2], W[(t >> 2) + 1], (t & 3) * 8);
 }
 
-/* One bitmap probe per STRIDE-th position of the lane's 32 bytes; returns bit i = probe i passed.  The hit bit is
- * shifted into `acc` with a multiply-add (FMA pipe; c.two == 2 is opaque to the compiler).  Blocked Bloom, k = 2:
- * both bits of the gram must be set in its word (wrap shifts use the low 5 bits of their amount).
+/* One bitmap probe per STRIDE-th position of the lane's kLaneBytes bytes; returns bit i = probe i passed.  The hit
+ * bit is shifted into `acc` with a multiply-add (FMA pipe; c.two == 2 is opaque to the compiler).  Blocked Bloom,
+ * k = 2: both bits of the gram must be set in its word (wrap shifts use the low 5 bits of their amount).
  * WIDE (g % 4 == 0): 64-bit products, low half = hash1 (word index, second bit), high half -> first bit. */
 template <int NW, int STRIDE, bool WIDE>
-__device__ __forceinline__ uint32_t probe_single(const ProbeCtx &c, const uint32_t (&W)[8 + NW], const uint32_t (&mul)[NW]) {
-    constexpr int kProbes = 32 / STRIDE;
+__device__ __forceinline__ uint32_t probe_single(const ProbeCtx &c, const uint32_t (&W)[kLaneWords + NW], const uint32_t (&mul)[NW]) {
+    constexpr int kProbes = kLaneBytes / STRIDE;
     uint32_t acc = 0;
 #pragma unroll
-    for (int t = 0; t < 32; t += STRIDE) {
+    for (int t = 0; t < kLaneBytes; t += STRIDE) {
         uint32_t h = 0, ha;
         if (WIDE) {
             unsigned long long hw = 0;
@@ -391,44 +414,61 @@ __device__ __forceinline__ uint32_t probe_single(const ProbeCtx &c, const uint32
 /* PAIR placement (acb_hash.h): positions x (even) and x+1 test two bits each in ONE word selected by the three
  * bytes their grams share -- one shared-memory load per two positions.  Bit y of the result = position y. */
 template <int N>
-__device__ __forceinline__ uint32_t probe_pair(const ProbeCtx &c, const uint32_t (&W)[N], uint32_t mulp) {
+__device__ __forceinline__ uint32_t probe_pair(const ProbeCtx &c, const uint32_t (&W)[N], uint32_t mulp, uint32_t mulq) {
     uint32_t acc = 0;
 #pragma unroll
-    for (int x = 0; x < 32; x += 2) {
+    for (int x = 0; x < kLaneBytes; x += 2) {
         const uint32_t w0 = window(W, x), w1 = window(W, x + 1);
-        /* a register whose low 5 bits are those of text byte x+4 (the byte of gram x+1 outside the common three) */
-        const int tb = x + 4;
-        const uint32_t wb = ((tb & 3) == 0) ? W[tb >> 2] : (tb < 32 ? window(W, tb) : (W[tb >> 2] >> ((tb & 3) * 8)));
-        const uint32_t a0 = __umulhi(w0, mulp);
+        const uint32_t a0 = __umulhi(w0, mulp), b0 = __umulhi(w0, mulq);
         const unsigned long long p1 = mul_wide(w1, mulp);
+        const uint32_t b1 = __umulhi(w1, mulq);
         const uint32_t word = lds_bitmap(__umulhi((uint32_t)p1, c.n_words) * c.four + c.sbm);
-        const uint32_t r0 = __funnelshift_r(word, 0u, a0) & __funnelshift_r(word, 0u, w0) & 1u;
-        const uint32_t r1 = __funnelshift_r(word, 0u, (uint32_t)(p1 >> 32)) & __funnelshift_r(word, 0u, wb) & 1u;
+        const uint32_t r0 = __funnelshift_r(word, 0u, a0) & __funnelshift_r(word, 0u, b0) & 1u;
+        const uint32_t r1 = __funnelshift_r(word, 0u, (uint32_t)(p1 >> 32)) & __funnelshift_r(word, 0u, b1) & 1u;
         acc = acc * c.two + r0;
         acc = acc * c.two + r1;
     }
-    return __brev(acc);
+    return __brev(acc) >> (32 - kLaneBytes);
 }
+
+#ifdef ACB_EXP_WATCHDOG
+#define ACB_SPIN_GUARD(n, what, a, b) do { if (++(n) > 4000000u) { printf("[acb watchdog] %s cta %d warp %d lane %d: %u %u (tail %u head %u done %u)\n", what, (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), (unsigned)(a), (unsigned)(b), s_ctl[0], s_ctl[1], s_ctl[2]); __trap(); } } while (0)
+#else
+#define ACB_SPIN_GUARD(n, what, a, b) do { } while (0)
+#endif
 
 /* shared-memory carve-up of the stream kernel (host and device agree through this one function) */
 struct StreamSmem {
-    uint32_t bitmap, stages, queue, stage_rec, stage_cnt, bars, tiles, next, total;
+    uint32_t bitmap, stages, cand, stage_rec, stage_cnt, bars, tiles, ctl, total;
 };
 __host__ __device__ inline StreamSmem stream_smem(int log1) {
     StreamSmem s;
     uint32_t o = 0;
     s.bitmap = o;    o += 1u << (log1 - 3);                       o = (o + 127u) & ~127u;
     s.stages = o;    o += (uint32_t)kStages * kStageBytes;
-    s.queue = o;     o += (uint32_t)kConsumers * kQueueCap * (uint32_t)sizeof(uint2);
-    s.stage_rec = o; o += (uint32_t)kConsumers * kStageCap * (uint32_t)sizeof(acb_match);
-    s.stage_cnt = o; o += (uint32_t)kConsumers * 4u;              o = (o + 15u) & ~15u;
+    s.cand = o;      o += (uint32_t)kCandCap * (uint32_t)sizeof(uint2);
+    s.stage_rec = o; o += (uint32_t)kResolvers * kStageCap * (uint32_t)sizeof(acb_match);
+    s.stage_cnt = o; o += (uint32_t)kResolvers * 4u;              o = (o + 15u) & ~15u;
     s.bars = o;      o += 2u * kStages * 8u;                      /* full[kStages], empty[kStages] */
     s.tiles = o;     o += (uint32_t)kStages * 4u;
-    s.next = o;      o += 4u;
+    s.ctl = o;       o += 16u;                                    /* candidate ring: tail, head, consumers done */
     s.total = (o + 15u) & ~15u;
     return s;
 }
 
+/* The three roles of the stream kernel's warps:
+ *   producer  (1 warp)          claims tiles, prefetches them into L2, keeps the shared-memory ring full
+ *                               (cp.async.bulk + mbarrier)
+ *   consumers (kConsumers)      probe their slice of every tile; a lane whose 32 bytes hold a survivor of the bitmap
+ *                               puts {position of its bytes, hit mask} into the candidate ring
+ *   resolvers (kResolvers)      take entries off the ring, kBatch at a time, and resolve every hit through the anchor
+ *                               table in L2 (text and anchors come from global memory, never from the stage)
+ * so that the warps that stream never wait for L2 and release their stage as soon as its bytes are in registers.
+ * The candidate ring is one CTA-wide ring in shared memory: consumers reserve slots with one atomicAdd per slice,
+ * resolvers claim kBatch slots with another.  Reservations may run many laps ahead of the resolvers, so a slot says
+ * whose turn it is: a free slot holds {next index, 0} and only the consumer that reserved exactly that index may fill
+ * it; a filled slot holds {position | lap parity << 31, mask != 0} and is taken by the resolver that claimed the index
+ * of that lap, which then frees it for index + kCandCap. */
 template <int NW, int STRIDE, int MODE>
 __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -437,6 +477,8 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t bar_full = sbase + lay.bars, bar_empty = bar_full + 8u * kStages;
     volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem_raw + lay.tiles);
+    volatile unsigned int *s_ctl = reinterpret_cast<volatile unsigned int *>(smem_raw + lay.ctl);   /* [0] tail [1] head [2] done */
+    volatile unsigned long long *s_cand = reinterpret_cast<volatile unsigned long long *>(smem_raw + lay.cand);
 
     {   /* the bitmap -> shared memory with cp.async, so that all of a thread's 16-byte pieces are in flight at once */
         const int n16 = 1 << (p.log1 - 7);
@@ -444,8 +486,9 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         for (int i = tid; i < n16; i += kFThreads)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + lay.bitmap + 16u * i), "l"(src + i));
         asm volatile("cp.async.commit_group;");
-        if (tid < kConsumers) reinterpret_cast<int *>(smem_raw + lay.stage_cnt)[tid] = 0;
-        if (tid == 0) *reinterpret_cast<unsigned int *>(smem_raw + lay.next) = 0u;
+        for (int i = tid; i < kCandCap; i += kFThreads) s_cand[i] = (unsigned long long)i;       /* free for index i */
+        if (tid < kResolvers) reinterpret_cast<int *>(smem_raw + lay.stage_cnt)[tid] = 0;
+        if (tid < 4) s_ctl[tid] = 0u;
         if (tid == 0) {
             for (int s = 0; s < kStages; s++) {
                 mbar_init(bar_full + 8u * s, 1);                 /* the producer's arrive(.expect_tx) */
@@ -459,25 +502,36 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
 
     const uint32_t seg_len = (uint32_t)(p.seg_end - p.seg_begin);        /* <= 2^31 */
 
-    if (warp == kConsumers) {
-        /* ---------------- producer warp: claim a tile, wait for a free stage, start the bulk copy */
+    if (warp == kConsumers + kResolvers) {
+        /* ---------------- producer warp.  A tile goes through three steps, kClaimDepth loop turns apart: it is claimed
+           from the global counter (a ~1 us round trip, so kClaimDepth claims are in flight, one register each so that
+           reading one never waits for a younger atomic), then its lines are prefetched into L2 by the 32 lanes, then a
+           bulk copy moves it into the next free stage. */
         const uint8_t *seg = p.hay + p.seg_begin;
         const long long exist = p.total - p.seg_begin;                   /* bytes that exist from seg onwards */
-        /* Tiles come from one global counter.  A claim is a ~1 us round trip to L2, so kClaimDepth of them are kept
-           in flight: claim[k] serves fills k, k + kClaimDepth, ... and is re-issued as soon as it has been read (one
-           register per slot, so that reading a slot never waits for a younger atomic). */
-        unsigned int claim[kClaimDepth];
+        unsigned int claim[kClaimDepth], ready[kClaimDepth];
 #pragma unroll
-        for (int k = 0; k < kClaimDepth; k++) claim[k] = (lane == 0) ? atomicAdd(p.work_ctr, 1u) : 0u;
+        for (int k = 0; k < kClaimDepth; k++) { claim[k] = (lane == 0) ? atomicAdd(p.work_ctr, 1u) : 0u; ready[k] = kNoTile; }
         bool more = true;
-        for (uint32_t base = 0; more; base += kClaimDepth) {
+        uint32_t fill = 0;
+        for (uint32_t turn = 0; more; ++turn) {
 #pragma unroll
             for (int k = 0; k < kClaimDepth; k++) {
                 if (!more) break;
-                const uint32_t fill = base + k;
+                const unsigned int t_pf = __shfl_sync(kFull, claim[k], 0);
+                const unsigned int tile = ready[k];
+                ready[k] = t_pf;
+                if (t_pf < p.n_tiles) {
+                    if (lane == 0) claim[k] = atomicAdd(p.work_ctr, 1u);
+#ifndef ACB_NO_L2_PREFETCH
+                    const long long off = (long long)t_pf * kTileBytes;
+                    const long long end = (exist - off < (long long)kTileBytes) ? exist - off : (long long)kTileBytes;
+                    for (long long i = (long long)lane * 128; i < end; i += 32 * 128)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(seg + off + i));
+#endif
+                }
+                if (turn == 0) continue;                                 /* nothing prefetched yet */
                 const uint32_t stage = fill % kStages;
-                const unsigned int tile = __shfl_sync(kFull, claim[k], 0);
-                if (lane == 0 && tile < p.n_tiles) claim[k] = atomicAdd(p.work_ctr, 1u);
                 if (fill >= (uint32_t)kStages) mbar_wait(bar_empty + 8u * stage, ((fill / kStages) - 1u) & 1u);
                 if (tile >= p.n_tiles) {                                 /* out of work: one sentinel fill ends every consumer */
                     if (lane == 0) { s_tile[stage] = kNoTile; mbar_arrive(bar_full + 8u * stage); }
@@ -507,14 +561,17 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
                         mbar_arrive(bar_full + 8u * stage);
                     }
                 }
+                ++fill;
             }
         }
-    } else {
-        /* ---------------- consumer warps */
-        WarpResolve wr;
-        wr.queue = reinterpret_cast<uint2 *>(smem_raw + lay.queue) + warp * kQueueCap;
-        wr.ws.buf = reinterpret_cast<acb_match *>(smem_raw + lay.stage_rec) + warp * kStageCap;
-        wr.ws.cnt = reinterpret_cast<int *>(smem_raw + lay.stage_cnt) + warp;
+        {   /* every claim still in flight must have landed before this CTA reports itself done (the last CTA re-arms the counter) */
+            unsigned int sink = 0;
+#pragma unroll
+            for (int k = 0; k < kClaimDepth; k++) sink |= claim[k];
+            if (sink == 0x7fffffffu) s_ctl[3] = sink;
+        }
+    } else if (warp < kConsumers) {
+        /* ---------------- consumer warps: slice `warp` of every fill */
         ProbeCtx c;
         c.sbm = sbase + lay.bitmap;
         c.n_words = 1u << (p.log1 - 5);
@@ -522,92 +579,144 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         c.two = 2u + (uint32_t)(p.log1 >> 8);                            /* always 2 */
         c.sh_bit = 32 - p.log1;
         const uint32_t lt_mask = (1u << lane) - 1u;
-        uint32_t mul[NW], mul2[NW];
+        uint32_t mul[NW];
 #pragma unroll
-        for (int k = 0; k < NW; k++) { mul[k] = p.mul1[k]; mul2[k] = p.mul2[k]; }
-        const uint32_t mulp = acb_pair_mul() + (uint32_t)(p.log1 >> 8);  /* a register, not an immediate per use */
-        uint32_t qhead = 0, qtail = 0;                                   /* ring positions; the queue persists across slices */
+        for (int k = 0; k < NW; k++) mul[k] = p.mul1[k];
+        const uint32_t mulp = acb_pair_mul() + (uint32_t)(p.log1 >> 8);  /* registers, not immediates per use */
+        const uint32_t mulq = acb_pair_mul_b() + (uint32_t)(p.log1 >> 8);
+        const uint32_t slice_off = (uint32_t)warp * kSliceBytes;
 
-        /* Slices are handed out dynamically: slice g is slice g % kConsumers of fill g / kConsumers.  A warp that is
-           busy resolving candidates simply takes fewer slices; with exactly kConsumers warps and one slice held per warp
-           a waiter can never be a whole ring turn ahead of the barrier phase it waits for. */
-        volatile unsigned int *s_next = reinterpret_cast<volatile unsigned int *>(smem_raw + lay.next);
-        for (;;) {
-            unsigned int g = 0;
-            if (lane == 0) g = atomicAdd(const_cast<unsigned int *>(s_next), 1u);
-            g = __shfl_sync(kFull, g, 0);
-            const uint32_t fill = g / kConsumers, slice_off = (g % kConsumers) * (uint32_t)kSliceBytes;
+        for (uint32_t fill = 0;; ++fill) {
             const uint32_t stage = fill % kStages;
             mbar_wait(bar_full + 8u * stage, (fill / kStages) & 1u);
             const uint32_t tile = s_tile[stage];
             if (tile == kNoTile) break;
             const uint32_t tile_off = tile * (uint32_t)kTileBytes;       /* relative to the segment */
             const uint32_t n_valid = (seg_len - tile_off < (uint32_t)kTileBytes) ? seg_len - tile_off : (uint32_t)kTileBytes;
-            if (slice_off < n_valid) {                                   /* warp-uniform */
-                const uint32_t saddr = sbase + lay.stages + stage * (uint32_t)kStageBytes + slice_off + (uint32_t)lane * 32u;
-                const uint4 c0 = lds128(saddr), c1 = lds128(saddr + 16u);
-                uint32_t W[8 + NW];
-                W[0] = c0.x; W[1] = c0.y; W[2] = c0.z; W[3] = c0.w;
-                W[4] = c1.x; W[5] = c1.y; W[6] = c1.z; W[7] = c1.w;
-                {   /* look-ahead words: the next lane's first words; lane 31 reads past its slice (next slice / tile pad) */
-                    const uint32_t cw[4] = {c0.x, c0.y, c0.z, c0.w};
+            const bool live = slice_off < n_valid;                       /* warp-uniform */
+            uint32_t W[kLaneWords + NW];
+            if (live) {
+                const uint32_t saddr = sbase + lay.stages + stage * (uint32_t)kStageBytes + slice_off + (uint32_t)lane * kLaneBytes;
 #pragma unroll
-                    for (int k = 0; k < NW; k++) W[8 + k] = __shfl_down_sync(kFull, cw[k], 1);
-                    if (lane == 31) {
-#pragma unroll
-                        for (int k = 0; k < NW; k++) W[8 + k] = lds32(saddr + 32u + 4u * k);
-                    }
+                for (int i = 0; i < kLaneWords; i += 4) {
+                    const uint4 v = lds128(saddr + 4u * i);
+                    W[i] = v.x; W[i + 1] = v.y; W[i + 2] = v.z; W[i + 3] = v.w;
                 }
-                uint32_t hits;
-#ifdef ACB_EXP_NOPROBE
-                hits = (W[0] ^ W[3] ^ W[5] ^ W[8]) == 0x12345678u ? 1u : 0u;     /* timing experiment: the stream skeleton alone */
-#else
-                if constexpr (MODE == kModePair) hits = probe_pair(c, W, mulp);
-                else hits = probe_single<NW, STRIDE, MODE == kModeWide>(c, W, mul);
-#endif
-                if (n_valid - slice_off < (uint32_t)kSliceBytes) {       /* last slice of the segment: probes that start past it */
-                    const int v = (int)(n_valid - slice_off) - lane * 32;
-                    const int valid = (MODE == kModePair) ? v : (v + STRIDE - 1) / STRIDE;
-                    hits = (valid <= 0) ? 0u : ((valid >= 32) ? hits : (hits & ((1u << valid) - 1u)));
-                }
-                /* queue the survivors (ballot-ranked append into the warp's ring) with hash2 of their gram, which is
-                   read back from the stage: it stays ours until the arrive below */
-#ifdef ACB_EXP_NOSURV
-                if (hits == 0x9e3779b9u) qtail += 1u;                    /* timing experiment: probes only, survivors dropped */
-                hits = 0;
-#endif
-                unsigned any = __ballot_sync(kFull, hits != 0);
-                while (any) {
-                    const bool has = hits != 0;
-                    uint2 cand = make_uint2(0, 0);
-                    if (has) {
-                        const uint32_t t = (uint32_t)(__ffs(hits) - 1) * (MODE == kModePair ? 1u : (uint32_t)STRIDE);
-                        hits &= hits - 1;
-                        const uint32_t ga = saddr + t, wa = ga & ~3u, sh = (ga & 3u) * 8u;
-                        uint32_t tag = 0, w0 = lds32(wa);
+                /* look-ahead words: the next lane's first words; lane 31 reads past its slice (next slice / tile pad) */
 #pragma unroll
-                        for (int k = 0; k < NW; k++) {
-                            const uint32_t w1 = lds32(wa + 4u * (k + 1));
-                            tag += __funnelshift_r(w0, w1, sh) * mul2[k];
-                            w0 = w1;
-                        }
-                        cand = make_uint2(tile_off + slice_off + (uint32_t)lane * 32u + t, tag | 1u);
-                    }
-                    if (has) wr.queue[(qtail + __popc(any & lt_mask)) & (kQueueCap - 1)] = cand;
-#ifdef ACB_EXP_NODRAIN
-                    if (cand.y == 0x9e3779b9u) qtail += 1u;              /* timing experiment: survivors hashed, then dropped */
-#else
-                    qtail += __popc(any);
-#endif
-                    if (qtail - qhead > (uint32_t)(kQueueCap - 32)) drain_queue(p, wr, qhead, qtail, false, lane);
-                    any = __ballot_sync(kFull, hits != 0);
+                for (int k = 0; k < NW; k++) W[kLaneWords + k] = __shfl_down_sync(kFull, W[k], 1);
+                if (lane == 31) {
+#pragma unroll
+                    for (int k = 0; k < NW; k++) W[kLaneWords + k] = lds32(saddr + kLaneBytes + 4u * k);
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8u * stage);          /* this warp is done with the stage */
-            if (qtail - qhead >= 32u) drain_queue(p, wr, qhead, qtail, false, lane);
+            if (lane == 0) mbar_arrive(bar_empty + 8u * stage);          /* the slice is in registers: the stage is free */
+            if (!live) continue;
+            uint32_t hits;
+#ifdef ACB_EXP_NOPROBE
+            hits = (W[0] ^ W[3] ^ W[kLaneWords]) == 0x12345678u ? 1u : 0u;      /* timing experiment: the stream skeleton alone */
+#else
+            if constexpr (MODE == kModePair) hits = probe_pair(c, W, mulp, mulq);
+            else hits = probe_single<NW, STRIDE, MODE == kModeWide>(c, W, mul);
+#endif
+            if (n_valid - slice_off < (uint32_t)kSliceBytes) {           /* last slice of the segment: probes that start past it */
+                const int v = (int)(n_valid - slice_off) - lane * kLaneBytes;
+                const int valid = (MODE == kModePair) ? v : (v + STRIDE - 1) / STRIDE;
+                hits = (valid <= 0) ? 0u : ((valid >= 32) ? hits : (hits & ((1u << valid) - 1u)));
+            }
+#ifdef ACB_EXP_NOSURV
+            if (hits == 0x9e3779b9u) s_ctl[3] = 1u;                      /* timing experiment: probes only, survivors dropped */
+            hits = 0;
+#endif
+            /* lanes with survivors: {where the lane's bytes are, which probes passed} -> the candidate ring */
+            const unsigned any = __ballot_sync(kFull, hits != 0);
+            if (any) {
+                unsigned int idx = 0;
+                if (lane == 0) idx = atomicAdd(const_cast<unsigned int *>(s_ctl), (unsigned int)__popc(any));
+                idx = __shfl_sync(kFull, idx, 0) + __popc(any & lt_mask);
+                if (hits) {
+                    volatile unsigned long long *slot = s_cand + (idx & (kCandCap - 1));
+                    unsigned int spins = 0;
+                    while (*slot != (unsigned long long)idx) { __nanosleep(64); ACB_SPIN_GUARD(spins, "consumer: slot busy", idx, (uint32_t)(*slot >> 32)); }   /* ring full: wait for our turn */
+                    const uint32_t lap = (idx / kCandCap) & 1u;
+                    *slot = ((unsigned long long)hits << 32) | ((tile_off + slice_off + (uint32_t)lane * kLaneBytes) | (lap << 31));
+                }
+            }
         }
-        drain_queue(p, wr, qhead, qtail, true, lane);                    /* leftovers */
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(const_cast<unsigned int *>(s_ctl + 2), 1u);   /* this consumer has pushed its last entry */
+    } else {
+        /* ---------------- resolver warps */
+        WarpStage ws;
+        ws.buf = reinterpret_cast<acb_match *>(smem_raw + lay.stage_rec) + (warp - kConsumers) * kStageCap;
+        ws.cnt = reinterpret_cast<int *>(smem_raw + lay.stage_cnt) + (warp - kConsumers);
+        uint32_t mul2[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) mul2[k] = p.mul2[k];
+        constexpr int kPer = kBatch / 32;                                /* entries per lane and batch */
+        constexpr uint32_t kStep = (MODE == kModePair) ? 1u : (uint32_t)STRIDE;   /* bytes per mask bit */
+        for (;;) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(const_cast<unsigned int *>(s_ctl + 1), (unsigned int)kBatch);
+            base = __shfl_sync(kFull, base, 0);
+            long long q[kPer];
+            uint32_t rest[kPer];                                         /* hits of the entry beyond the first */
+            bool got[kPer];
+            bool past_end = false;
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {
+                const unsigned int idx = base + 32u * j + lane;
+                volatile unsigned long long *slot = s_cand + (idx & (kCandCap - 1));
+                const uint32_t lap = (idx / kCandCap) & 1u;
+                got[j] = false; rest[j] = 0; q[j] = 0;
+                unsigned int spins = 0;
+                for (;;) {
+                    const unsigned long long e = *slot;
+                    if ((uint32_t)(e >> 32) != 0u && (((uint32_t)e) >> 31) == lap) {
+                        *slot = (unsigned long long)(idx + (unsigned int)kCandCap);   /* free for the next lap */
+                        const uint32_t mask = (uint32_t)(e >> 32);
+                        q[j] = p.seg_begin + (long long)((uint32_t)e & 0x7fffffffu) + (long long)((uint32_t)(__ffs(mask) - 1) * kStep);
+                        rest[j] = mask & (mask - 1);
+                        got[j] = true;
+                        break;
+                    }
+                    if (s_ctl[2] == (unsigned int)kConsumers) {          /* every consumer is done: the tail is final */
+                        __threadfence_block();
+                        if (idx >= s_ctl[0]) { past_end = true; break; }
+                    }
+                    __nanosleep(100);
+                    ACB_SPIN_GUARD(spins, "resolver: slot empty", idx, (uint32_t)(*slot >> 32));
+                }
+            }
+            /* first hit of every entry: all text loads, then all anchor loads, then the compares */
+            uint32_t tq[kPer][6], tag[kPer];
+            uint4 e0[kPer], e1[kPer];
+#pragma unroll
+            for (int j = 0; j < kPer; j++) if (got[j]) load_text(p, q[j], tq[j]);
+#pragma unroll
+            for (int j = 0; j < kPer; j++) if (got[j]) {
+                tag[j] = tag_of<NW>(tq[j], q[j], mul2);
+                const uint32_t slot = tag[j] >> (32 - p.logA);
+                e0[j] = __ldg(p.anchors + 2 * (size_t)slot);
+                e1[j] = __ldg(p.anchors + 2 * (size_t)slot + 1);
+            }
+#pragma unroll
+            for (int j = 0; j < kPer; j++) if (got[j]) resolve_chain(p, ws, q[j], tag[j], tq[j], e0[j], e1[j]);
+            /* further hits in the same 32 bytes (rare on sparse-match text) */
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {
+                uint32_t m = rest[j];
+                const long long q0 = q[j] & ~(long long)(kLaneBytes - 1);
+                while (m) {
+                    resolve_one<NW>(p, ws, q0 + (long long)((uint32_t)(__ffs(m) - 1) * kStep), mul2);
+                    m &= m - 1;
+                }
+            }
+            flush_stage(p, ws, lane);
+            if (__all_sync(kFull, past_end)) break;                      /* nothing at or after this batch will ever come */
+        }
     }
     /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
     __syncthreads();

@@ -110,17 +110,21 @@ ACB_HD uint32_t acb_stage1_bit_b(uint64_t hw) { return (uint32_t)hw & 31u; }
  *                  which G plays role 1 (G starts at the odd position x+1; its bytes 0..2 are the common ones)
  *      high half : low 5 bits = bit `a` of G, depends on all four bytes
  * Role 0 (G starts at the even position x; the common bytes are its bytes 1..3): the word is selected by the low
- * half of (G >> 8) * mulp.  The second bit of a gram is the low 5 bits of its one byte OUTSIDE the common three:
- * byte 0 in role 0, byte 3 in role 1.  Every key gram is entered under both roles (a key may start anywhere). */
+ * half of (G >> 8) * mulp.  The second bit `b` of a gram comes from the high half of G * mulq, a second
+ * multiplier (one more IMAD.HI per position on the FMA pipe, which has room; taking it from a raw text byte
+ * instead tripled the false positives on alphanumeric text).  Every key gram is entered under both roles (a key
+ * may start at an even or an odd position). */
 #define ACB_PAIR_M 0x9E3779B1u
+#define ACB_PAIR_Q 0x85EBCA77u
 ACB_HD uint32_t acb_pair_mul(void) { return ACB_PAIR_M << 8; }
+ACB_HD uint32_t acb_pair_mul_b(void) { return ACB_PAIR_Q << 8; }
 /* role 0 / 1 placement of gram G: *word = index into n_words words, *bits = the two bits to set / test */
 ACB_HD void acb_pair_place(uint32_t G, int role, uint32_t n_words, uint32_t *word, uint32_t *bits) {
     const uint32_t mulp = ACB_PAIR_M << 8;
     const uint32_t a = (uint32_t)(((uint64_t)G * mulp) >> 32) & 31u;
     const uint32_t common = role ? G : (G >> 8);
     const uint32_t lo = (uint32_t)((uint64_t)common * mulp);
-    const uint32_t b = (role ? (G >> 24) : G) & 31u;
+    const uint32_t b = (uint32_t)(((uint64_t)G * (ACB_PAIR_Q << 8)) >> 32) & 31u;
     *word = (uint32_t)(((uint64_t)lo * n_words) >> 32);
     *bits = (1u << a) | (1u << b);
 }

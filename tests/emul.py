@@ -103,6 +103,7 @@ def _entry_bytes(e, n):
 
 
 PAIR_M = 0x9E3779B1
+PAIR_Q = 0x85EBCA77
 
 
 def pair_place(G, role, n_words):
@@ -111,7 +112,7 @@ def pair_place(G, role, n_words):
     a = ((G * mulp) >> 32) & 31
     common = G if role else (G >> 8)
     lo = (common * mulp) & M32
-    b = ((G >> 24) if role else G) & 31
+    b = ((G * ((PAIR_Q << 8) & M32)) >> 32) & 31
     return (lo * n_words) >> 32, (1 << a) | (1 << b)
 
 
