@@ -59,32 +59,28 @@
 namespace {
 
 #ifndef ACB_CONSUMERS
-#define ACB_CONSUMERS 24
-#endif
-#ifndef ACB_RESOLVERS
-#define ACB_RESOLVERS 7
+#define ACB_CONSUMERS 31
 #endif
 #ifndef ACB_STAGES
-#define ACB_STAGES 3
+#define ACB_STAGES 6
 #endif
 #ifndef ACB_LANE_BYTES
-#define ACB_LANE_BYTES 32
+#define ACB_LANE_BYTES 16
 #endif
 constexpr int kConsumers    = ACB_CONSUMERS;          /* consumer warps of the stream kernel           */
-constexpr int kResolvers    = ACB_RESOLVERS;          /* warps that resolve candidates through L2      */
-constexpr int kFThreads     = (kConsumers + kResolvers + 1) * 32;   /* + the producer warp             */
+constexpr int kFThreads     = (kConsumers + 1) * 32;  /* + the producer warp                           */
 constexpr int kLaneBytes    = ACB_LANE_BYTES;         /* text bytes per lane and iteration (16 or 32)  */
 constexpr int kLaneWords    = kLaneBytes / 4;
 constexpr int kSliceBytes   = 32 * kLaneBytes;        /* one warp iteration                            */
 constexpr int kTileBytes    = kConsumers * kSliceBytes;
 constexpr int kLook         = 16;                     /* bytes copied past a tile (gram look-ahead)    */
-constexpr int kStageBytes   = kTileBytes + 128;       /* tile + look-ahead, stages stay 128 B aligned  */
+constexpr int kStageBytes   = (kTileBytes + kLook + 127) / 128 * 128;   /* tile + look-ahead, stages stay 128 B aligned */
 constexpr int kStages       = ACB_STAGES;
 constexpr int kClaimDepth   = 8;                      /* tile claims in flight per producer            */
-constexpr int kCandCap      = 1024;                   /* candidate ring of a CTA (smem), power of two  */
-constexpr int kBatch        = 64;                     /* candidates a resolver warp takes at a time    */
-constexpr int kStageCap     = 64;                     /* match records staged per resolver warp (smem) */
-static_assert(kFThreads <= 1024 && kTileBytes % 16 == 0 && (kCandCap & (kCandCap - 1)) == 0 && kBatch % 32 == 0, "stream kernel shape");
+constexpr int kResThreads   = 256;                    /* resolve kernel: threads per CTA               */
+constexpr int kResPerRegion = 4;                      /* resolve kernel: CTAs per candidate region     */
+constexpr int kStageCap     = 64;                     /* match records staged per warp of the resolve kernel (smem) */
+static_assert(kFThreads <= 1024 && kTileBytes % 16 == 0, "stream kernel shape");
 constexpr uint32_t kFull    = 0xffffffffu;
 constexpr uint32_t kNoTile  = 0xffffffffu;
 constexpr int32_t  kTermBit = 0x40000000;             /* goto entry flag: child ends a key             */
@@ -128,7 +124,14 @@ struct ScanParams {
     unsigned long long *count;
     long long seg_begin, seg_end;  /* byte range of this launch */
     unsigned int n_tiles;          /* kTileBytes tiles in the segment */
-    unsigned int *work_ctr;        /* [0] next tile, [1] CTAs done */
+    unsigned int *work_ctr;        /* [0] next tile, [1] stream CTAs done, [2] resolve CTAs done, [3] sticky overflow flag */
+    /* stream -> resolve hand-over: one region of the candidate list per stream CTA */
+    uint2 *cand;                   /* region r = cand[r * region_cap ...]: {position of 16/32 text bytes in the segment, hit mask} */
+    unsigned int region_cap;       /* entries per region */
+    unsigned int *region_count;    /* entries written per region (capped at region_cap) */
+    int n_regions;                 /* = grid of the stream kernel */
+    int static_tiles;              /* 1: tiles are assigned round-robin instead of claimed (bounds a CTA's share of the candidates) */
+    int last_segment;              /* the resolve launch of the last segment reports a sticky overflow in *count */
     int stride_shift;              /* log2(stride_bytes) when it is a power of two, else -1 */
     int letter_shift;              /* log2(L) */
 };
@@ -373,7 +376,7 @@ struct ProbeCtx {
     uint32_t n_words;          /* umulhi(h, n_words) = word index */
     uint32_t four;             /* == 4, opaque to the compiler so the address is one IMAD (FMA pipe, which has room) */
     uint32_t two;              /* == 2, same trick for the hit accumulator */
-    int sh_bit;                /* NARROW: h >> sh_bit supplies the first bit index (low 5 bits, wrap shift) */
+    int sh_bit;                /* NARROW: h >> sh_bit supplies the first bit index (low 5 bits, wrap shift); PAIR: the word index */
 };
 
 /* window t of the lane's text: the 4 bytes at byte offset t of W[] (little endian) */
@@ -413,62 +416,52 @@ __device__ __forceinline__ uint32_t probe_single(const ProbeCtx &c, const uint32
 
 /* PAIR placement (acb_hash.h): positions x (even) and x+1 test two bits each in ONE word selected by the three
  * bytes their grams share -- one shared-memory load per two positions.  Bit y of the result = position y. */
+__device__ __forceinline__ uint32_t dp4a_u32(uint32_t x, uint32_t c) {
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(c), "r"(0u));
+    return d;
+}
+
 template <int N>
-__device__ __forceinline__ uint32_t probe_pair(const ProbeCtx &c, const uint32_t (&W)[N], uint32_t mulp, uint32_t mulq) {
+__device__ __forceinline__ uint32_t probe_pair(const ProbeCtx &c, const uint32_t (&W)[N], uint32_t mulp, uint32_t ca, uint32_t cb) {
     uint32_t acc = 0;
 #pragma unroll
     for (int x = 0; x < kLaneBytes; x += 2) {
         const uint32_t w0 = window(W, x), w1 = window(W, x + 1);
-        const uint32_t a0 = __umulhi(w0, mulp), b0 = __umulhi(w0, mulq);
-        const unsigned long long p1 = mul_wide(w1, mulp);
-        const uint32_t b1 = __umulhi(w1, mulq);
-        const uint32_t word = lds_bitmap(__umulhi((uint32_t)p1, c.n_words) * c.four + c.sbm);
-        const uint32_t r0 = __funnelshift_r(word, 0u, a0) & __funnelshift_r(word, 0u, b0) & 1u;
-        const uint32_t r1 = __funnelshift_r(word, 0u, (uint32_t)(p1 >> 32)) & __funnelshift_r(word, 0u, b1) & 1u;
-        acc = acc * c.two + r0;
-        acc = acc * c.two + r1;
+        const uint32_t word = lds_bitmap(((w1 * mulp) >> c.sh_bit) * c.four + c.sbm);     /* sh_bit = 32 - log2(words) */
+        const uint32_t r0 = __funnelshift_r(word, 0u, dp4a_u32(w0, ca)) & __funnelshift_r(word, 0u, dp4a_u32(w0, cb)) & 1u;
+        const uint32_t r1 = __funnelshift_r(word, 0u, dp4a_u32(w1, ca)) & __funnelshift_r(word, 0u, dp4a_u32(w1, cb)) & 1u;
+        acc = acc + acc + r0;                                     /* plain adds: they issue on either pipe */
+        acc = acc + acc + r1;
     }
     return __brev(acc) >> (32 - kLaneBytes);
 }
 
-#ifdef ACB_EXP_WATCHDOG
-#define ACB_SPIN_GUARD(n, what, a, b) do { if (++(n) > 4000000u) { printf("[acb watchdog] %s cta %d warp %d lane %d: %u %u (tail %u head %u done %u)\n", what, (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), (unsigned)(a), (unsigned)(b), s_ctl[0], s_ctl[1], s_ctl[2]); __trap(); } } while (0)
-#else
-#define ACB_SPIN_GUARD(n, what, a, b) do { } while (0)
-#endif
-
 /* shared-memory carve-up of the stream kernel (host and device agree through this one function) */
 struct StreamSmem {
-    uint32_t bitmap, stages, cand, stage_rec, stage_cnt, bars, tiles, ctl, total;
+    uint32_t bitmap, stages, bars, tiles, ctl, total;
 };
 __host__ __device__ inline StreamSmem stream_smem(int log1) {
     StreamSmem s;
     uint32_t o = 0;
     s.bitmap = o;    o += 1u << (log1 - 3);                       o = (o + 127u) & ~127u;
     s.stages = o;    o += (uint32_t)kStages * kStageBytes;
-    s.cand = o;      o += (uint32_t)kCandCap * (uint32_t)sizeof(uint2);
-    s.stage_rec = o; o += (uint32_t)kResolvers * kStageCap * (uint32_t)sizeof(acb_match);
-    s.stage_cnt = o; o += (uint32_t)kResolvers * 4u;              o = (o + 15u) & ~15u;
     s.bars = o;      o += 2u * kStages * 8u;                      /* full[kStages], empty[kStages] */
     s.tiles = o;     o += (uint32_t)kStages * 4u;
-    s.ctl = o;       o += 16u;                                    /* candidate ring: tail, head, consumers done */
+    s.ctl = o;       o += 16u;                                    /* [0] entries pushed into this CTA's candidate region */
     s.total = (o + 15u) & ~15u;
     return s;
 }
 
-/* The three roles of the stream kernel's warps:
- *   producer  (1 warp)          claims tiles, prefetches them into L2, keeps the shared-memory ring full
+/* acb_stream_kernel: the HBM stream.  Persistent, one CTA per SM, warp specialised:
+ *   producer  (1 warp)          claims tiles from a global counter and keeps the shared-memory ring full
  *                               (cp.async.bulk + mbarrier)
- *   consumers (kConsumers)      probe their slice of every tile; a lane whose 32 bytes hold a survivor of the bitmap
- *                               puts {position of its bytes, hit mask} into the candidate ring
- *   resolvers (kResolvers)      take entries off the ring, kBatch at a time, and resolve every hit through the anchor
- *                               table in L2 (text and anchors come from global memory, never from the stage)
- * so that the warps that stream never wait for L2 and release their stage as soon as its bytes are in registers.
- * The candidate ring is one CTA-wide ring in shared memory: consumers reserve slots with one atomicAdd per slice,
- * resolvers claim kBatch slots with another.  Reservations may run many laps ahead of the resolvers, so a slot says
- * whose turn it is: a free slot holds {next index, 0} and only the consumer that reserved exactly that index may fill
- * it; a filled slot holds {position | lap parity << 31, mask != 0} and is taken by the resolver that claimed the index
- * of that lap, which then frees it for index + kCandCap. */
+ *   consumers (kConsumers)      slice `warp` of every tile: the lane's bytes go to registers, the stage is released at
+ *                               once, every probe position is tested against the gram bitmap in shared memory; a lane
+ *                               whose bytes hold a survivor appends {position of its bytes, hit mask} to the CTA's own
+ *                               region of the candidate list in global memory (a shared-memory cursor, no global atomic,
+ *                               a plain store nobody waits for)
+ * The warps that stream never wait for L2: everything that needs the anchor table is left to acb_resolve_kernel. */
 template <int NW, int STRIDE, int MODE>
 __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -477,8 +470,7 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t bar_full = sbase + lay.bars, bar_empty = bar_full + 8u * kStages;
     volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem_raw + lay.tiles);
-    volatile unsigned int *s_ctl = reinterpret_cast<volatile unsigned int *>(smem_raw + lay.ctl);   /* [0] tail [1] head [2] done */
-    volatile unsigned long long *s_cand = reinterpret_cast<volatile unsigned long long *>(smem_raw + lay.cand);
+    volatile unsigned int *s_ctl = reinterpret_cast<volatile unsigned int *>(smem_raw + lay.ctl);
 
     {   /* the bitmap -> shared memory with cp.async, so that all of a thread's 16-byte pieces are in flight at once */
         const int n16 = 1 << (p.log1 - 7);
@@ -486,8 +478,6 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         for (int i = tid; i < n16; i += kFThreads)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + lay.bitmap + 16u * i), "l"(src + i));
         asm volatile("cp.async.commit_group;");
-        for (int i = tid; i < kCandCap; i += kFThreads) s_cand[i] = (unsigned long long)i;       /* free for index i */
-        if (tid < kResolvers) reinterpret_cast<int *>(smem_raw + lay.stage_cnt)[tid] = 0;
         if (tid < 4) s_ctl[tid] = 0u;
         if (tid == 0) {
             for (int s = 0; s < kStages; s++) {
@@ -502,36 +492,25 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
 
     const uint32_t seg_len = (uint32_t)(p.seg_end - p.seg_begin);        /* <= 2^31 */
 
-    if (warp == kConsumers + kResolvers) {
-        /* ---------------- producer warp.  A tile goes through three steps, kClaimDepth loop turns apart: it is claimed
-           from the global counter (a ~1 us round trip, so kClaimDepth claims are in flight, one register each so that
-           reading one never waits for a younger atomic), then its lines are prefetched into L2 by the 32 lanes, then a
-           bulk copy moves it into the next free stage. */
+    if (warp == kConsumers) {
+        /* ---------------- producer warp.  Tiles come from one global counter.  A claim is a ~1 us round trip to L2, so
+           kClaimDepth of them are kept in flight: claim[k] serves fills k, k + kClaimDepth, ... and is re-issued as soon
+           as it has been read (one register per slot, so that reading a slot never waits for a younger atomic). */
         const uint8_t *seg = p.hay + p.seg_begin;
         const long long exist = p.total - p.seg_begin;                   /* bytes that exist from seg onwards */
-        unsigned int claim[kClaimDepth], ready[kClaimDepth];
+        unsigned int claim[kClaimDepth];
 #pragma unroll
-        for (int k = 0; k < kClaimDepth; k++) { claim[k] = (lane == 0) ? atomicAdd(p.work_ctr, 1u) : 0u; ready[k] = kNoTile; }
+        for (int k = 0; k < kClaimDepth; k++) claim[k] = (lane == 0 && !p.static_tiles) ? atomicAdd(p.work_ctr, 1u) : 0u;
         bool more = true;
-        uint32_t fill = 0;
-        for (uint32_t turn = 0; more; ++turn) {
+        for (uint32_t base = 0; more; base += kClaimDepth) {
 #pragma unroll
             for (int k = 0; k < kClaimDepth; k++) {
                 if (!more) break;
-                const unsigned int t_pf = __shfl_sync(kFull, claim[k], 0);
-                const unsigned int tile = ready[k];
-                ready[k] = t_pf;
-                if (t_pf < p.n_tiles) {
-                    if (lane == 0) claim[k] = atomicAdd(p.work_ctr, 1u);
-#ifndef ACB_NO_L2_PREFETCH
-                    const long long off = (long long)t_pf * kTileBytes;
-                    const long long end = (exist - off < (long long)kTileBytes) ? exist - off : (long long)kTileBytes;
-                    for (long long i = (long long)lane * 128; i < end; i += 32 * 128)
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(seg + off + i));
-#endif
-                }
-                if (turn == 0) continue;                                 /* nothing prefetched yet */
+                const uint32_t fill = base + k;
                 const uint32_t stage = fill % kStages;
+                /* static_tiles (the worst-case retry): tile f of CTA b is b + f * grid, so that a CTA's share is bounded */
+                const unsigned int tile = p.static_tiles ? blockIdx.x + fill * gridDim.x : __shfl_sync(kFull, claim[k], 0);
+                if (lane == 0 && !p.static_tiles && tile < p.n_tiles) claim[k] = atomicAdd(p.work_ctr, 1u);
                 if (fill >= (uint32_t)kStages) mbar_wait(bar_empty + 8u * stage, ((fill / kStages) - 1u) & 1u);
                 if (tile >= p.n_tiles) {                                 /* out of work: one sentinel fill ends every consumer */
                     if (lane == 0) { s_tile[stage] = kNoTile; mbar_arrive(bar_full + 8u * stage); }
@@ -561,7 +540,6 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
                         mbar_arrive(bar_full + 8u * stage);
                     }
                 }
-                ++fill;
             }
         }
         {   /* every claim still in flight must have landed before this CTA reports itself done (the last CTA re-arms the counter) */
@@ -570,21 +548,22 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
             for (int k = 0; k < kClaimDepth; k++) sink |= claim[k];
             if (sink == 0x7fffffffu) s_ctl[3] = sink;
         }
-    } else if (warp < kConsumers) {
+    } else {
         /* ---------------- consumer warps: slice `warp` of every fill */
         ProbeCtx c;
         c.sbm = sbase + lay.bitmap;
         c.n_words = 1u << (p.log1 - 5);
         c.four = 4u + (uint32_t)(p.log1 >> 8);                           /* always 4 */
         c.two = 2u + (uint32_t)(p.log1 >> 8);                            /* always 2 */
-        c.sh_bit = 32 - p.log1;
+        c.sh_bit = (MODE == kModePair) ? 37 - p.log1 : 32 - p.log1;     /* PAIR: hash >> sh_bit = word index */
         const uint32_t lt_mask = (1u << lane) - 1u;
         uint32_t mul[NW];
 #pragma unroll
         for (int k = 0; k < NW; k++) mul[k] = p.mul1[k];
         const uint32_t mulp = acb_pair_mul() + (uint32_t)(p.log1 >> 8);  /* registers, not immediates per use */
-        const uint32_t mulq = acb_pair_mul_b() + (uint32_t)(p.log1 >> 8);
+        const uint32_t ca = ACB_PAIR_CA + (uint32_t)(p.log1 >> 8), cb = ACB_PAIR_CB + (uint32_t)(p.log1 >> 8);
         const uint32_t slice_off = (uint32_t)warp * kSliceBytes;
+        uint2 *region = p.cand + (size_t)blockIdx.x * p.region_cap;
 
         for (uint32_t fill = 0;; ++fill) {
             const uint32_t stage = fill % kStages;
@@ -617,7 +596,7 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
 #ifdef ACB_EXP_NOPROBE
             hits = (W[0] ^ W[3] ^ W[kLaneWords]) == 0x12345678u ? 1u : 0u;      /* timing experiment: the stream skeleton alone */
 #else
-            if constexpr (MODE == kModePair) hits = probe_pair(c, W, mulp, mulq);
+            if constexpr (MODE == kModePair) hits = probe_pair(c, W, mulp, ca, cb);
             else hits = probe_single<NW, STRIDE, MODE == kModeWide>(c, W, mul);
 #endif
             if (n_valid - slice_off < (uint32_t)kSliceBytes) {           /* last slice of the segment: probes that start past it */
@@ -629,103 +608,105 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
             if (hits == 0x9e3779b9u) s_ctl[3] = 1u;                      /* timing experiment: probes only, survivors dropped */
             hits = 0;
 #endif
-            /* lanes with survivors: {where the lane's bytes are, which probes passed} -> the candidate ring */
+            /* lanes with survivors: {where the lane's bytes are, which probes passed} -> this CTA's candidate region */
             const unsigned any = __ballot_sync(kFull, hits != 0);
             if (any) {
                 unsigned int idx = 0;
                 if (lane == 0) idx = atomicAdd(const_cast<unsigned int *>(s_ctl), (unsigned int)__popc(any));
                 idx = __shfl_sync(kFull, idx, 0) + __popc(any & lt_mask);
-                if (hits) {
-                    volatile unsigned long long *slot = s_cand + (idx & (kCandCap - 1));
-                    unsigned int spins = 0;
-                    while (*slot != (unsigned long long)idx) { __nanosleep(64); ACB_SPIN_GUARD(spins, "consumer: slot busy", idx, (uint32_t)(*slot >> 32)); }   /* ring full: wait for our turn */
-                    const uint32_t lap = (idx / kCandCap) & 1u;
-                    *slot = ((unsigned long long)hits << 32) | ((tile_off + slice_off + (uint32_t)lane * kLaneBytes) | (lap << 31));
-                }
+                if (hits && idx < p.region_cap) region[idx] = make_uint2(tile_off + slice_off + (uint32_t)lane * kLaneBytes, hits);
             }
-        }
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) atomicAdd(const_cast<unsigned int *>(s_ctl + 2), 1u);   /* this consumer has pushed its last entry */
-    } else {
-        /* ---------------- resolver warps */
-        WarpStage ws;
-        ws.buf = reinterpret_cast<acb_match *>(smem_raw + lay.stage_rec) + (warp - kConsumers) * kStageCap;
-        ws.cnt = reinterpret_cast<int *>(smem_raw + lay.stage_cnt) + (warp - kConsumers);
-        uint32_t mul2[NW];
-#pragma unroll
-        for (int k = 0; k < NW; k++) mul2[k] = p.mul2[k];
-        constexpr int kPer = kBatch / 32;                                /* entries per lane and batch */
-        constexpr uint32_t kStep = (MODE == kModePair) ? 1u : (uint32_t)STRIDE;   /* bytes per mask bit */
-        for (;;) {
-            unsigned int base = 0;
-            if (lane == 0) base = atomicAdd(const_cast<unsigned int *>(s_ctl + 1), (unsigned int)kBatch);
-            base = __shfl_sync(kFull, base, 0);
-            long long q[kPer];
-            uint32_t rest[kPer];                                         /* hits of the entry beyond the first */
-            bool got[kPer];
-            bool past_end = false;
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                const unsigned int idx = base + 32u * j + lane;
-                volatile unsigned long long *slot = s_cand + (idx & (kCandCap - 1));
-                const uint32_t lap = (idx / kCandCap) & 1u;
-                got[j] = false; rest[j] = 0; q[j] = 0;
-                unsigned int spins = 0;
-                for (;;) {
-                    const unsigned long long e = *slot;
-                    if ((uint32_t)(e >> 32) != 0u && (((uint32_t)e) >> 31) == lap) {
-                        *slot = (unsigned long long)(idx + (unsigned int)kCandCap);   /* free for the next lap */
-                        const uint32_t mask = (uint32_t)(e >> 32);
-                        q[j] = p.seg_begin + (long long)((uint32_t)e & 0x7fffffffu) + (long long)((uint32_t)(__ffs(mask) - 1) * kStep);
-                        rest[j] = mask & (mask - 1);
-                        got[j] = true;
-                        break;
-                    }
-                    if (s_ctl[2] == (unsigned int)kConsumers) {          /* every consumer is done: the tail is final */
-                        __threadfence_block();
-                        if (idx >= s_ctl[0]) { past_end = true; break; }
-                    }
-                    __nanosleep(100);
-                    ACB_SPIN_GUARD(spins, "resolver: slot empty", idx, (uint32_t)(*slot >> 32));
-                }
-            }
-            /* first hit of every entry: all text loads, then all anchor loads, then the compares */
-            uint32_t tq[kPer][6], tag[kPer];
-            uint4 e0[kPer], e1[kPer];
-#pragma unroll
-            for (int j = 0; j < kPer; j++) if (got[j]) load_text(p, q[j], tq[j]);
-#pragma unroll
-            for (int j = 0; j < kPer; j++) if (got[j]) {
-                tag[j] = tag_of<NW>(tq[j], q[j], mul2);
-                const uint32_t slot = tag[j] >> (32 - p.logA);
-                e0[j] = __ldg(p.anchors + 2 * (size_t)slot);
-                e1[j] = __ldg(p.anchors + 2 * (size_t)slot + 1);
-            }
-#pragma unroll
-            for (int j = 0; j < kPer; j++) if (got[j]) resolve_chain(p, ws, q[j], tag[j], tq[j], e0[j], e1[j]);
-            /* further hits in the same 32 bytes (rare on sparse-match text) */
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                uint32_t m = rest[j];
-                const long long q0 = q[j] & ~(long long)(kLaneBytes - 1);
-                while (m) {
-                    resolve_one<NW>(p, ws, q0 + (long long)((uint32_t)(__ffs(m) - 1) * kStep), mul2);
-                    m &= m - 1;
-                }
-            }
-            flush_stage(p, ws, lane);
-            if (__all_sync(kFull, past_end)) break;                      /* nothing at or after this batch will ever come */
         }
     }
-    /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
+    /* hand the region over: its entry count (an overflow sets the sticky flag: the host repeats the scan with room for
+       every lane); the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
     __syncthreads();
     if (tid == 0) {
+        const unsigned int n = s_ctl[0];
+        p.region_count[blockIdx.x] = n < p.region_cap ? n : p.region_cap;
+        if (n > p.region_cap) atomicOr(p.work_ctr + 3, 1u);
         __threadfence();
         unsigned int done = atomicAdd(p.work_ctr + 1, 1u);
         if (done == gridDim.x - 1) {
             p.work_ctr[0] = 0u;
             p.work_ctr[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+/* acb_resolve_kernel: every hit of every candidate entry through the anchor table.  kResPerRegion CTAs share one
+ * region; a thread takes one entry at a time: the text at the hit (L2 / HBM), hash2 of its gram, the anchor slot the
+ * tag hashes to (L2), the compare.  Three dependent round trips per hit, hidden by occupancy (1536 threads per SM)
+ * instead of by the streaming warps.  Match records are staged per warp and appended with one atomicAdd per flush. */
+template <int NW>
+__global__ void __launch_bounds__(kResThreads, 4) acb_resolve_kernel(const __grid_constant__ ScanParams p, int step) {
+    __shared__ acb_match s_stage[(kResThreads / 32) * kStageCap];
+    __shared__ int s_cnt[kResThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < kResThreads / 32) s_cnt[tid] = 0;
+    __syncthreads();
+    WarpStage ws;
+    ws.buf = s_stage + warp * kStageCap;
+    ws.cnt = s_cnt + warp;
+    uint32_t mul2[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) mul2[k] = p.mul2[k];
+    const int r = blockIdx.x / kResPerRegion, sub = blockIdx.x % kResPerRegion;
+    const unsigned int n = __ldcg(p.region_count + r);
+    const uint2 *region = p.cand + (size_t)r * p.region_cap;
+    /* Two entries per lane and turn, their loads issued together: the entries, then the text at their first hits, then
+       the anchor slots -- three round trips per turn instead of six.  The trip count is warp-uniform. */
+    constexpr int kPer = 2;
+    const unsigned int turn = kResPerRegion * kResThreads * kPer;
+    for (unsigned int i0 = (unsigned int)((sub * kResThreads + warp * 32) * kPer); i0 < n; i0 += turn) {
+        uint2 e[kPer];
+        bool got[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            const unsigned int i = i0 + 32u * j + lane;
+            got[j] = i < n;
+            e[j] = got[j] ? __ldcg(region + i) : make_uint2(0u, 0u);
+        }
+        long long q[kPer];
+        uint32_t tq[kPer][6], tag[kPer];
+        uint4 a0[kPer], a1[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) if (got[j]) {
+            q[j] = p.seg_begin + (long long)e[j].x + (long long)((uint32_t)(__ffs(e[j].y) - 1) * (uint32_t)step);
+            load_text(p, q[j], tq[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; j++) if (got[j]) {
+            tag[j] = tag_of<NW>(tq[j], q[j], mul2);
+            const uint32_t slot = tag[j] >> (32 - p.logA);
+            a0[j] = __ldg(p.anchors + 2 * (size_t)slot);
+            a1[j] = __ldg(p.anchors + 2 * (size_t)slot + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; j++) if (got[j]) resolve_chain(p, ws, q[j], tag[j], tq[j], a0[j], a1[j]);
+        /* further hits in the same bytes (rare on sparse-match text) */
+#pragma unroll
+        for (int j = 0; j < kPer; j++) if (got[j]) {
+            const long long q0 = p.seg_begin + (long long)e[j].x;
+            uint32_t m = e[j].y & (e[j].y - 1);
+            while (m) {
+                resolve_one<NW>(p, ws, q0 + (long long)((uint32_t)(__ffs(m) - 1) * (uint32_t)step), mul2);
+                m &= m - 1;
+            }
+        }
+        __syncwarp();
+        if (*reinterpret_cast<volatile int *>(ws.cnt) >= kStageCap / 2) flush_stage(p, ws, lane);    /* warp-uniform */
+    }
+    flush_stage(p, ws, lane);
+    /* the last CTA of the last segment's launch turns a sticky overflow into *count = -1 and clears it */
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        unsigned int done = atomicAdd(p.work_ctr + 2, 1u);
+        if (done == gridDim.x - 1) {
+            p.work_ctr[2] = 0u;
+            if (p.last_segment && p.work_ctr[3]) { *p.count = ~0ULL; p.work_ctr[3] = 0u; }
             __threadfence();
         }
     }
@@ -856,6 +837,10 @@ struct acb_table {
     int32_t *d_goto = nullptr, *d_fail = nullptr, *d_keyof = nullptr, *d_outptr = nullptr, *d_outidx = nullptr, *d_keylen = nullptr;
     uint32_t *d_bm1 = nullptr, *d_anchors = nullptr;
     unsigned int *d_work = nullptr;
+    uint2 *d_cand = nullptr;                 /* candidate list (stream -> resolve), one region per stream CTA */
+    size_t cand_entries = 0;
+    unsigned int *d_region_count = nullptr;
+    bool cand_worst_case = false;
     long long dev_bytes = 0;
     std::vector<int32_t> key_len;            /* host copy, for sorting records */
     /* workspace of acb_scan_host */
@@ -895,7 +880,7 @@ extern "C" void acb_table_free(acb_table *tb) {
     cudaSetDevice(tb->device);
     cudaFree(tb->d_lfail); cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
     cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_anchors);
-    cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
+    cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->d_region_count); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
     if (tb->h_count) cudaFreeHost(tb->h_count);
     if (tb->h_out) cudaFreeHost(tb->h_out);
     if (tb->ev0) cudaEventDestroy(tb->ev0);
@@ -961,11 +946,24 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
 }
 
 extern "C" int64_t acb_table_device_bytes(const acb_table *tb) { return tb ? tb->dev_bytes : 0; }
+extern "C" int acb_table_reserve_candidates(acb_table *tb, int worst_case) {
+    if (!tb) return ACB_EINVAL;
+    tb->cand_worst_case = worst_case != 0;
+    return ACB_OK;
+}
 extern "C" int64_t acb_launch_count(void) { return g_launches.load(); }
 extern "C" int acb_set_kernel_timing(int enabled) { g_timing.store(enabled ? 1 : 0); return ACB_OK; }
 extern "C" float acb_last_kernel_ms(void) { return g_last_ms; }
 
 /* ------------------------------------------------------------- launching */
+
+template <int NW>
+static int launch_resolve(const ScanParams &p, int step, cudaStream_t s) {
+    acb_resolve_kernel<NW><<<p.n_regions * kResPerRegion, kResThreads, 0, s>>>(p, step);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return ACB_OK;
+}
 
 template <int NW, int STRIDE, int MODE>
 static int launch_stream_m(const ScanParams &p, int grid, cudaStream_t s) {
@@ -979,7 +977,7 @@ static int launch_stream_m(const ScanParams &p, int grid, cudaStream_t s) {
     kern<<<grid, kFThreads, smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
-    return ACB_OK;
+    return launch_resolve<NW>(p, MODE == kModePair ? 1 : STRIDE, s);
 }
 
 /* the placement mode follows from the table's filter_flags */
@@ -1018,6 +1016,29 @@ static int launch_stream(const ScanParams &p, int flags, int stride, int grid, c
     }
     acb_set_error("unsupported gram length %d", p.gram);
     return ACB_EINVAL;
+}
+
+/* The candidate list of one segment launch: one region per stream CTA.  By default a region has room for a quarter
+ * of the lanes an even share of the tiles holds (a lane = kLaneBytes of text = one possible entry); a scan that
+ * overflows any region sets a sticky flag, reports *count = -1, and is repeated with static tile assignment and
+ * room for every lane (acb_table_reserve_candidates; acb_scan_host does this by itself). */
+static int ensure_candidates(acb_table *tb, ScanParams &p, int grid) {
+    const size_t tile_lanes = kTileBytes / kLaneBytes;
+    const size_t share = ((size_t)p.n_tiles + grid - 1) / grid * tile_lanes;         /* lanes of an even share of the tiles */
+    const size_t cap = tb->cand_worst_case ? share : std::max<size_t>(4096, share / 4);
+    const size_t need = cap * (size_t)grid;
+    if (!tb->d_cand || tb->cand_entries < need) {
+        if (tb->d_cand) { cudaFree(tb->d_cand); tb->d_cand = nullptr; tb->cand_entries = 0; }
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_cand), need * sizeof(uint2)));
+        tb->cand_entries = need;
+    }
+    if (!tb->d_region_count) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_region_count), 1024 * sizeof(unsigned int)));
+    p.cand = tb->d_cand;
+    p.region_cap = (unsigned int)cap;
+    p.region_count = tb->d_region_count;
+    p.n_regions = grid;
+    p.static_tiles = tb->cand_worst_case ? 1 : 0;
+    return ACB_OK;
 }
 
 extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t total_bytes,
@@ -1067,7 +1088,10 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
             p.seg_end = std::min<long long>(seg + kSegBytes, total_bytes);
             p.n_tiles = (unsigned int)((p.seg_end - p.seg_begin + kTileBytes - 1) / kTileBytes);
             const int grid = (int)std::min<long long>(tb->sm_count, p.n_tiles);
-            int rc = launch_stream(p, tb->filter_flags, tb->stride, grid, s);
+            int rc = ensure_candidates(tb, p, grid);
+            if (rc != ACB_OK) return rc;
+            p.last_segment = p.seg_end == total_bytes;
+            rc = launch_stream(p, tb->filter_flags, tb->stride, grid, s);
             if (rc != ACB_OK) return rc;
         }
     } else if (algo == ACB_ALGO_DFA) {
@@ -1240,6 +1264,11 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
     CUDA_TRY(cudaStreamSynchronize(s));
     if (trace) t2 = now();
     unsigned long long n = *tb->h_count;
+    if (n == ~0ULL) {                                           /* a candidate region overflowed: redo with room for every lane */
+        if (tb->cand_worst_case) { acb_set_error("candidate list overflow even at worst-case capacity"); return ACB_ECUDA; }
+        tb->cand_worst_case = true;
+        return acb_scan_host(tb, hay, total_bytes, offsets, n_hay, stride_bytes, out, cap, n_found, algo, sort);
+    }
     *n_found = (int64_t)n;
     if (n > (unsigned long long)cap) {
         acb_set_error("match buffer too small: %llu matches, capacity %lld", n, (long long)cap);

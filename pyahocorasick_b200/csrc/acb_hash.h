@@ -104,29 +104,30 @@ ACB_HD uint32_t acb_stage1_bit_b(uint64_t hw) { return (uint32_t)hw & 31u; }
 
 /* ---- PAIR placement (gram 4, stride 1, 1-byte letters) --------------------------------------------------
  * Positions x (even) and x+1 share ONE bitmap word, selected by the three bytes their 4-byte grams have in
- * common, so the probe loop needs one shared-memory load per two positions.  With mulp = ACB_PAIR_M << 8 and
- * G the gram read as a little-endian word:   P = (uint64)G * mulp
- *      low half  : depends on bytes 0..2 of G only (the top byte is shifted out)  -> word index of the pair in
- *                  which G plays role 1 (G starts at the odd position x+1; its bytes 0..2 are the common ones)
- *      high half : low 5 bits = bit `a` of G, depends on all four bytes
- * Role 0 (G starts at the even position x; the common bytes are its bytes 1..3): the word is selected by the low
- * half of (G >> 8) * mulp.  The second bit `b` of a gram comes from the high half of G * mulq, a second
- * multiplier (one more IMAD.HI per position on the FMA pipe, which has room; taking it from a raw text byte
- * instead tripled the false positives on alphanumeric text).  Every key gram is entered under both roles (a key
- * may start at an even or an odd position). */
-#define ACB_PAIR_M 0x9E3779B1u
-#define ACB_PAIR_Q 0x85EBCA77u
+ * common, so the probe loop needs one shared-memory load per two positions.  With G the gram read as a
+ * little-endian word:
+ *      word   : top bits of ((common three bytes) * ACB_PAIR_M << 8) mod 2^32 -- a plain 32-bit multiply; the shifted
+ *               multiplier drops the fourth byte of the register the kernel happens to have (the window at x+1)
+ *      bits   : a = dp4a(G, ACB_PAIR_CA) & 31,  b = dp4a(G, ACB_PAIR_CB) & 31 -- byte-wise dot products with odd
+ *               coefficients: their LOW five bits are already mixed over all four bytes, so they feed a wrap shift
+ *               directly (no extraction), and IDP.4A issues at the rate of a 32-bit multiply (mul.hi / mul.wide, which
+ *               the first version used for these bits, issue at half of it: measured, tools/ubench/pipes.cu)
+ * Role 0 = G starts at the even position x (its bytes 1..3 are the common ones), role 1 = G starts at x+1 (bytes
+ * 0..2).  Every key gram is entered under both roles (a key may start at an even or an odd position). */
+#define ACB_PAIR_M  0x9E3779B1u
+#define ACB_PAIR_CA 0x1B0D0701u   /* bytes  1,  7, 13, 27 */
+#define ACB_PAIR_CB 0x1F091503u   /* bytes  3, 21,  9, 31 */
 ACB_HD uint32_t acb_pair_mul(void) { return ACB_PAIR_M << 8; }
-ACB_HD uint32_t acb_pair_mul_b(void) { return ACB_PAIR_Q << 8; }
-/* role 0 / 1 placement of gram G: *word = index into n_words words, *bits = the two bits to set / test */
-ACB_HD void acb_pair_place(uint32_t G, int role, uint32_t n_words, uint32_t *word, uint32_t *bits) {
-    const uint32_t mulp = ACB_PAIR_M << 8;
-    const uint32_t a = (uint32_t)(((uint64_t)G * mulp) >> 32) & 31u;
+ACB_HD uint32_t acb_dp4a(uint32_t x, uint32_t c) {
+    return (x & 0xffu) * (c & 0xffu) + ((x >> 8) & 0xffu) * ((c >> 8) & 0xffu) +
+           ((x >> 16) & 0xffu) * ((c >> 16) & 0xffu) + (x >> 24) * (c >> 24);
+}
+/* role 0 / 1 placement of gram G: *word = index into 2^log2_words words, *bits = the two bits to set / test */
+ACB_HD void acb_pair_place(uint32_t G, int role, int log2_words, uint32_t *word, uint32_t *bits) {
     const uint32_t common = role ? G : (G >> 8);
-    const uint32_t lo = (uint32_t)((uint64_t)common * mulp);
-    const uint32_t b = (uint32_t)(((uint64_t)G * (ACB_PAIR_Q << 8)) >> 32) & 31u;
-    *word = (uint32_t)(((uint64_t)lo * n_words) >> 32);
-    *bits = (1u << a) | (1u << b);
+    const uint32_t lo = common * (ACB_PAIR_M << 8);
+    *word = lo >> (32 - log2_words);
+    *bits = (1u << (acb_dp4a(G, ACB_PAIR_CA) & 31u)) | (1u << (acb_dp4a(G, ACB_PAIR_CB) & 31u));
 }
 
 #endif

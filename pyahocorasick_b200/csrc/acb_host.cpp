@@ -461,7 +461,7 @@ static void build_filter(acb_trie *t, Flat &f) {
             const uint32_t G = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
             for (int role = 0; role < 2; role++) {
                 uint32_t word, bits;
-                acb_pair_place(G, role, n_words, &word, &bits);
+                acb_pair_place(G, role, best.log1 - 5, &word, &bits);
                 f.bm1[word] |= bits;
             }
         } else {

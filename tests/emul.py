@@ -103,17 +103,19 @@ def _entry_bytes(e, n):
 
 
 PAIR_M = 0x9E3779B1
-PAIR_Q = 0x85EBCA77
+PAIR_CA = (1, 7, 13, 27)
+PAIR_CB = (3, 21, 9, 31)
 
 
-def pair_place(G, role, n_words):
+def _dp4a(G, c):
+    return sum(((G >> (8 * i)) & 0xFF) * c[i] for i in range(4))
+
+
+def pair_place(G, role, log2_words):
     """acb_pair_place (csrc/acb_hash.h): word index and the two bits of gram G (little-endian u32) in one role"""
-    mulp = (PAIR_M << 8) & M32
-    a = ((G * mulp) >> 32) & 31
     common = G if role else (G >> 8)
-    lo = (common * mulp) & M32
-    b = ((G * ((PAIR_Q << 8) & M32)) >> 32) & 31
-    return (lo * n_words) >> 32, (1 << a) | (1 << b)
+    lo = (common * ((PAIR_M << 8) & M32)) & M32
+    return lo >> (32 - log2_words), (1 << (_dp4a(G, PAIR_CA) & 31)) | (1 << (_dp4a(G, PAIR_CB) & 31))
 
 
 def _u32_at(buf, q):
@@ -130,7 +132,7 @@ def _passes_bitmap(f, buf, q):
     if flags & FILTER_PAIR:
         assert g == 4 and f["stride"] == 1 and f["letter_bytes"] == 1
         role = q & 1                                   # x even: role 0 of pair (x, x+1); x odd: role 1 of (x-1, x)
-        word, bits = pair_place(_u32_at(buf, q), role, n_words)
+        word, bits = pair_place(_u32_at(buf, q), role, l1 - 5)
         return (int(f["bitmap1"][word]) & bits) == bits
     mul1 = multipliers(g, 1)
     hw = hash_bytes_wide(buf, q, g, mul1)
