@@ -197,20 +197,13 @@ enum {
  *                when every haystack is `stride_bytes` long (haystack h = [h*stride, (h+1)*stride))
  *   d_out/cap  : match records; records beyond cap are counted but not stored
  *   d_count    : device int64; incremented by the number of matches found
- *                (the caller zeroes it; order of records is unspecified).  The filter
- *                path hands its bitmap survivors to a second kernel through a candidate list
- *                sized for a quarter of the text lanes; if a pathological key set overflows
- *                it, *d_count is set to -1: call acb_table_reserve_candidates(tb, 1) and scan
- *                again (acb_scan_host does this by itself).
+ *                (the caller zeroes it; order of records is unspecified).
  * One scan at a time per table: the table owns the scratch buffers of the scan.
  */
 int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t total_bytes,
                     const int64_t *d_offsets, int64_t n_hay, int64_t stride_bytes,
                     acb_match *d_out, int64_t cap, int64_t *d_count,
                     void *stream, int algo);
-
-/* worst_case != 0: size the candidate list for every lane of the text (never overflows) */
-int acb_table_reserve_candidates(acb_table *tb, int worst_case);
 
 /* Batch scan, HOST buffers: H2D copy of haystacks (+offsets), the kernel, and D2H of
  * the count and the records, all inside the call (this is what `e2e` times).

@@ -633,9 +633,6 @@ class Automaton:
                 N.check(self._lib.acb_scan_device(tb, t.data_ptr(), n * stride, None, n, stride, out.data_ptr(), cap,
                                                   cnt.data_ptr(), stream, N.ALGOS[algo]))
                 found = int(cnt.item())
-                if found == -1:                                   # a candidate region overflowed: worst-case size, again
-                    N.check(self._lib.acb_table_reserve_candidates(tb, 1))
-                    continue
                 if found > cap:
                     cap = self._match_cap = found + 1024
                     continue

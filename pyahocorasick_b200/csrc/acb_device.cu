@@ -62,10 +62,13 @@ namespace {
 #define ACB_CONSUMERS 31
 #endif
 #ifndef ACB_STAGES
-#define ACB_STAGES 6
+#define ACB_STAGES 5
 #endif
 #ifndef ACB_LANE_BYTES
 #define ACB_LANE_BYTES 16
+#endif
+#ifndef ACB_PHASE_FILLS
+#define ACB_PHASE_FILLS 32
 #endif
 constexpr int kConsumers    = ACB_CONSUMERS;          /* consumer warps of the stream kernel           */
 constexpr int kFThreads     = (kConsumers + 1) * 32;  /* + the producer warp                           */
@@ -77,10 +80,11 @@ constexpr int kLook         = 16;                     /* bytes copied past a til
 constexpr int kStageBytes   = (kTileBytes + kLook + 127) / 128 * 128;   /* tile + look-ahead, stages stay 128 B aligned */
 constexpr int kStages       = ACB_STAGES;
 constexpr int kClaimDepth   = 8;                      /* tile claims in flight per producer            */
-constexpr int kResThreads   = 256;                    /* resolve kernel: threads per CTA               */
-constexpr int kResPerRegion = 4;                      /* resolve kernel: CTAs per candidate region     */
-constexpr int kStageCap     = 64;                     /* match records staged per warp of the resolve kernel (smem) */
-static_assert(kFThreads <= 1024 && kTileBytes % 16 == 0, "stream kernel shape");
+constexpr int kPhaseFills   = ACB_PHASE_FILLS;        /* a consumer warp resolves its candidates every kPhaseFills slices,
+                                                         while their text is still in L2 (kPhaseFills tiles per SM)  */
+constexpr int kWarpCand     = kPhaseFills * 32;       /* candidate entries a warp can collect between two phases: every lane of every slice */
+constexpr int kStageCap     = 32;                     /* match records staged per consumer warp (smem) */
+static_assert(kFThreads <= 1024 && kTileBytes % 16 == 0 && (kPhaseFills & (kPhaseFills - 1)) == 0, "stream kernel shape");
 constexpr uint32_t kFull    = 0xffffffffu;
 constexpr uint32_t kNoTile  = 0xffffffffu;
 constexpr int32_t  kTermBit = 0x40000000;             /* goto entry flag: child ends a key             */
@@ -124,14 +128,9 @@ struct ScanParams {
     unsigned long long *count;
     long long seg_begin, seg_end;  /* byte range of this launch */
     unsigned int n_tiles;          /* kTileBytes tiles in the segment */
-    unsigned int *work_ctr;        /* [0] next tile, [1] stream CTAs done, [2] resolve CTAs done, [3] sticky overflow flag */
-    /* stream -> resolve hand-over: one region of the candidate list per stream CTA */
-    uint2 *cand;                   /* region r = cand[r * region_cap ...]: {position of 16/32 text bytes in the segment, hit mask} */
-    unsigned int region_cap;       /* entries per region */
-    unsigned int *region_count;    /* entries written per region (capped at region_cap) */
-    int n_regions;                 /* = grid of the stream kernel */
-    int static_tiles;              /* 1: tiles are assigned round-robin instead of claimed (bounds a CTA's share of the candidates) */
-    int last_segment;              /* the resolve launch of the last segment reports a sticky overflow in *count */
+    unsigned int *work_ctr;        /* [0] next tile, [1] CTAs done */
+    uint2 *cand;                   /* candidate entries, kWarpCand per consumer warp of every CTA: {position of a lane's bytes in the segment, hit mask} */
+    int step;                      /* bytes between the probes two adjacent mask bits stand for */
     int stride_shift;              /* log2(stride_bytes) when it is a power of two, else -1 */
     int letter_shift;              /* log2(L) */
 };
@@ -437,31 +436,110 @@ __device__ __forceinline__ uint32_t probe_pair(const ProbeCtx &c, const uint32_t
     return __brev(acc) >> (32 - kLaneBytes);
 }
 
+#ifdef ACB_EXP_L1ONLY
+/* timing experiment: the level-1 probe of a two-level design (one bit per pair, keyed by the three common bytes) */
+template <int N>
+__device__ __forceinline__ uint32_t probe_l1(const ProbeCtx &c, const uint32_t (&W)[N], uint32_t mulp) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int x = 0; x < kLaneBytes; x += 2) {
+        const uint32_t hc = window(W, x + 1) * mulp;
+        const uint32_t word = lds_bitmap((hc >> 18) * c.four + c.sbm);
+        const uint32_t t = __funnelshift_l(0u, word, hc >> 13);          /* word << (bit index): the tested bit lands in bit 31 */
+        asm("{ .reg .u32 t2; add.cc.u32 t2, %1, %1; addc.u32 %0, %0, %0; }" : "+r"(acc) : "r"(t));
+    }
+    return acc;
+}
+#endif
+
 /* shared-memory carve-up of the stream kernel (host and device agree through this one function) */
 struct StreamSmem {
-    uint32_t bitmap, stages, bars, tiles, ctl, total;
+    uint32_t bitmap, stages, stage_rec, stage_cnt, bars, tiles, total;
 };
 __host__ __device__ inline StreamSmem stream_smem(int log1) {
     StreamSmem s;
     uint32_t o = 0;
     s.bitmap = o;    o += 1u << (log1 - 3);                       o = (o + 127u) & ~127u;
     s.stages = o;    o += (uint32_t)kStages * kStageBytes;
+    s.stage_rec = o; o += (uint32_t)kConsumers * kStageCap * (uint32_t)sizeof(acb_match);
+    s.stage_cnt = o; o += (uint32_t)kConsumers * 4u;              o = (o + 15u) & ~15u;
     s.bars = o;      o += 2u * kStages * 8u;                      /* full[kStages], empty[kStages] */
     s.tiles = o;     o += (uint32_t)kStages * 4u;
-    s.ctl = o;       o += 16u;                                    /* [0] entries pushed into this CTA's candidate region */
     s.total = (o + 15u) & ~15u;
     return s;
 }
 
-/* acb_stream_kernel: the HBM stream.  Persistent, one CTA per SM, warp specialised:
+/* A consumer warp's collected candidates, entries [0, n) of `list`, through the anchor table.  Two entries per lane
+ * and turn, their loads issued together: the entries, then the text at their first hits, then the anchor slots the
+ * tags hash to -- three round trips per turn (kPer = 1: a second entry per lane makes ptxas spill inside the probe loop).
+ * Text and anchors come from L2: the bytes were streamed at most
+ * kPhaseFills tiles ago. */
+template <int NW>
+__device__ __forceinline__ void resolve_backlog(const ScanParams &p, uint8_t *smem_raw, unsigned int n) {
+    /* everything but n is rebuilt here rather than kept alive across the probe loop */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const StreamSmem lay = stream_smem(p.log1);
+    WarpStage ws;
+    ws.buf = reinterpret_cast<acb_match *>(smem_raw + lay.stage_rec) + warp * kStageCap;
+    ws.cnt = reinterpret_cast<int *>(smem_raw + lay.stage_cnt) + warp;
+    const uint2 *list = p.cand + ((size_t)blockIdx.x * kConsumers + warp) * kWarpCand;
+    uint32_t mul2[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) mul2[k] = p.mul2[k];
+    constexpr int kPer = 1;
+    __syncwarp();                                                        /* the entries were written by other lanes of this warp */
+    for (unsigned int i0 = 0; i0 < n; i0 += 32 * kPer) {
+        uint2 e[kPer];
+        bool got[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            const unsigned int i = i0 + 32u * j + lane;
+            got[j] = i < n;
+            e[j] = got[j] ? __ldcg(list + i) : make_uint2(0u, 0u);
+        }
+        long long q[kPer];
+        uint32_t tq[kPer][6], tag[kPer];
+        uint4 a0[kPer], a1[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) if (got[j]) {
+            q[j] = p.seg_begin + (long long)e[j].x + (long long)((uint32_t)(__ffs(e[j].y) - 1) * (uint32_t)p.step);
+            load_text(p, q[j], tq[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; j++) if (got[j]) {
+            tag[j] = tag_of<NW>(tq[j], q[j], mul2);
+            const uint32_t slot = tag[j] >> (32 - p.logA);
+            a0[j] = __ldg(p.anchors + 2 * (size_t)slot);
+            a1[j] = __ldg(p.anchors + 2 * (size_t)slot + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; j++) if (got[j]) resolve_chain(p, ws, q[j], tag[j], tq[j], a0[j], a1[j]);
+        /* further hits in the same bytes (rare on sparse-match text) */
+#pragma unroll
+        for (int j = 0; j < kPer; j++) if (got[j]) {
+            const long long q0 = p.seg_begin + (long long)e[j].x;
+            uint32_t m = e[j].y & (e[j].y - 1);
+            while (m) {
+                resolve_one<NW>(p, ws, q0 + (long long)((uint32_t)(__ffs(m) - 1) * (uint32_t)p.step), mul2);
+                m &= m - 1;
+            }
+        }
+        flush_stage(p, ws, lane);
+    }
+}
+
+/* acb_stream_kernel: persistent, one CTA per SM, warp specialised:
  *   producer  (1 warp)          claims tiles from a global counter and keeps the shared-memory ring full
  *                               (cp.async.bulk + mbarrier)
  *   consumers (kConsumers)      slice `warp` of every tile: the lane's bytes go to registers, the stage is released at
  *                               once, every probe position is tested against the gram bitmap in shared memory; a lane
- *                               whose bytes hold a survivor appends {position of its bytes, hit mask} to the CTA's own
- *                               region of the candidate list in global memory (a shared-memory cursor, no global atomic,
- *                               a plain store nobody waits for)
- * The warps that stream never wait for L2: everything that needs the anchor table is left to acb_resolve_kernel. */
+ *                               whose bytes hold a survivor appends {position of its bytes, hit mask} to the warp's own
+ *                               candidate list in global memory (the cursor is a register: no atomic, a plain store
+ *                               nobody waits for).  Every kPhaseFills slices the warp takes its list through the anchor
+ *                               table (resolve_backlog): the consumers of a CTA move in step, so they all do this at
+ *                               about the same fill while the producer refills the ring, and the text they compare with
+ *                               is still in L2.  A list has room for every lane of every slice of a phase: it cannot
+ *                               overflow. */
 template <int NW, int STRIDE, int MODE>
 __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -470,7 +548,6 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t bar_full = sbase + lay.bars, bar_empty = bar_full + 8u * kStages;
     volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem_raw + lay.tiles);
-    volatile unsigned int *s_ctl = reinterpret_cast<volatile unsigned int *>(smem_raw + lay.ctl);
 
     {   /* the bitmap -> shared memory with cp.async, so that all of a thread's 16-byte pieces are in flight at once */
         const int n16 = 1 << (p.log1 - 7);
@@ -478,7 +555,7 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         for (int i = tid; i < n16; i += kFThreads)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + lay.bitmap + 16u * i), "l"(src + i));
         asm volatile("cp.async.commit_group;");
-        if (tid < 4) s_ctl[tid] = 0u;
+        if (tid < kConsumers) reinterpret_cast<int *>(smem_raw + lay.stage_cnt)[tid] = 0;
         if (tid == 0) {
             for (int s = 0; s < kStages; s++) {
                 mbar_init(bar_full + 8u * s, 1);                 /* the producer's arrive(.expect_tx) */
@@ -500,7 +577,7 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         const long long exist = p.total - p.seg_begin;                   /* bytes that exist from seg onwards */
         unsigned int claim[kClaimDepth];
 #pragma unroll
-        for (int k = 0; k < kClaimDepth; k++) claim[k] = (lane == 0 && !p.static_tiles) ? atomicAdd(p.work_ctr, 1u) : 0u;
+        for (int k = 0; k < kClaimDepth; k++) claim[k] = (lane == 0) ? atomicAdd(p.work_ctr, 1u) : 0u;
         bool more = true;
         for (uint32_t base = 0; more; base += kClaimDepth) {
 #pragma unroll
@@ -508,9 +585,8 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
                 if (!more) break;
                 const uint32_t fill = base + k;
                 const uint32_t stage = fill % kStages;
-                /* static_tiles (the worst-case retry): tile f of CTA b is b + f * grid, so that a CTA's share is bounded */
-                const unsigned int tile = p.static_tiles ? blockIdx.x + fill * gridDim.x : __shfl_sync(kFull, claim[k], 0);
-                if (lane == 0 && !p.static_tiles && tile < p.n_tiles) claim[k] = atomicAdd(p.work_ctr, 1u);
+                const unsigned int tile = __shfl_sync(kFull, claim[k], 0);
+                if (lane == 0 && tile < p.n_tiles) claim[k] = atomicAdd(p.work_ctr, 1u);
                 if (fill >= (uint32_t)kStages) mbar_wait(bar_empty + 8u * stage, ((fill / kStages) - 1u) & 1u);
                 if (tile >= p.n_tiles) {                                 /* out of work: one sentinel fill ends every consumer */
                     if (lane == 0) { s_tile[stage] = kNoTile; mbar_arrive(bar_full + 8u * stage); }
@@ -546,7 +622,7 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
             unsigned int sink = 0;
 #pragma unroll
             for (int k = 0; k < kClaimDepth; k++) sink |= claim[k];
-            if (sink == 0x7fffffffu) s_ctl[3] = sink;
+            if (sink == 0x7fffffffu) s_tile[0] = sink;
         }
     } else {
         /* ---------------- consumer warps: slice `warp` of every fill */
@@ -563,150 +639,81 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         const uint32_t mulp = acb_pair_mul() + (uint32_t)(p.log1 >> 8);  /* registers, not immediates per use */
         const uint32_t ca = ACB_PAIR_CA + (uint32_t)(p.log1 >> 8), cb = ACB_PAIR_CB + (uint32_t)(p.log1 >> 8);
         const uint32_t slice_off = (uint32_t)warp * kSliceBytes;
-        uint2 *region = p.cand + (size_t)blockIdx.x * p.region_cap;
-
-        for (uint32_t fill = 0;; ++fill) {
-            const uint32_t stage = fill % kStages;
-            mbar_wait(bar_full + 8u * stage, (fill / kStages) & 1u);
-            const uint32_t tile = s_tile[stage];
-            if (tile == kNoTile) break;
-            const uint32_t tile_off = tile * (uint32_t)kTileBytes;       /* relative to the segment */
-            const uint32_t n_valid = (seg_len - tile_off < (uint32_t)kTileBytes) ? seg_len - tile_off : (uint32_t)kTileBytes;
-            const bool live = slice_off < n_valid;                       /* warp-uniform */
-            uint32_t W[kLaneWords + NW];
-            if (live) {
-                const uint32_t saddr = sbase + lay.stages + stage * (uint32_t)kStageBytes + slice_off + (uint32_t)lane * kLaneBytes;
+        uint2 *list = p.cand + ((size_t)blockIdx.x * kConsumers + warp) * kWarpCand;
+        uint32_t stage = 0, parity = 0;
+        bool more = true;
+        while (more) {
+            /* one phase: kPhaseFills slices of pure streaming (no call inside this loop), then the candidates they left */
+            unsigned int n_cand = 0;                                     /* warp-uniform */
+#pragma unroll 1
+            for (int s = 0; s < kPhaseFills; s++) {
+                mbar_wait(bar_full + 8u * stage, parity);
+                const uint32_t tile = s_tile[stage];
+                if (tile == kNoTile) { more = false; break; }
+                const uint32_t tile_off = tile * (uint32_t)kTileBytes;   /* relative to the segment */
+                const uint32_t n_valid = (seg_len - tile_off < (uint32_t)kTileBytes) ? seg_len - tile_off : (uint32_t)kTileBytes;
+                const bool live = slice_off < n_valid;                   /* warp-uniform */
+                uint32_t W[kLaneWords + NW];
+                if (live) {
+                    const uint32_t saddr = sbase + lay.stages + stage * (uint32_t)kStageBytes + slice_off + (uint32_t)lane * kLaneBytes;
 #pragma unroll
-                for (int i = 0; i < kLaneWords; i += 4) {
-                    const uint4 v = lds128(saddr + 4u * i);
-                    W[i] = v.x; W[i + 1] = v.y; W[i + 2] = v.z; W[i + 3] = v.w;
+                    for (int i = 0; i < kLaneWords; i += 4) {
+                        const uint4 v = lds128(saddr + 4u * i);
+                        W[i] = v.x; W[i + 1] = v.y; W[i + 2] = v.z; W[i + 3] = v.w;
+                    }
+                    /* look-ahead words: the next lane's first words; lane 31 reads past its slice (next slice / tile pad) */
+#pragma unroll
+                    for (int k = 0; k < NW; k++) W[kLaneWords + k] = __shfl_down_sync(kFull, W[k], 1);
+                    if (lane == 31) {
+#pragma unroll
+                        for (int k = 0; k < NW; k++) W[kLaneWords + k] = lds32(saddr + kLaneBytes + 4u * k);
+                    }
                 }
-                /* look-ahead words: the next lane's first words; lane 31 reads past its slice (next slice / tile pad) */
-#pragma unroll
-                for (int k = 0; k < NW; k++) W[kLaneWords + k] = __shfl_down_sync(kFull, W[k], 1);
-                if (lane == 31) {
-#pragma unroll
-                    for (int k = 0; k < NW; k++) W[kLaneWords + k] = lds32(saddr + kLaneBytes + 4u * k);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8u * stage);          /* the slice is in registers: the stage is free */
-            if (!live) continue;
-            uint32_t hits;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8u * stage);      /* the slice is in registers: the stage is free */
+                if (++stage == (uint32_t)kStages) { stage = 0; parity ^= 1u; }
+                if (!live) continue;
+                uint32_t hits;
 #ifdef ACB_EXP_NOPROBE
-            hits = (W[0] ^ W[3] ^ W[kLaneWords]) == 0x12345678u ? 1u : 0u;      /* timing experiment: the stream skeleton alone */
+                hits = (W[0] ^ W[3] ^ W[kLaneWords]) == 0x12345678u ? 1u : 0u;  /* timing experiment: the stream skeleton alone */
 #else
-            if constexpr (MODE == kModePair) hits = probe_pair(c, W, mulp, ca, cb);
-            else hits = probe_single<NW, STRIDE, MODE == kModeWide>(c, W, mul);
+#ifdef ACB_EXP_L1ONLY
+                if constexpr (MODE == kModePair) hits = probe_l1(c, W, mulp) == 0x12345u ? 1u : 0u;
+                else hits = 0;
+                if (ca == cb) hits = 1u;
+#else
+                if constexpr (MODE == kModePair) hits = probe_pair(c, W, mulp, ca, cb);
+                else hits = probe_single<NW, STRIDE, MODE == kModeWide>(c, W, mul);
 #endif
-            if (n_valid - slice_off < (uint32_t)kSliceBytes) {           /* last slice of the segment: probes that start past it */
-                const int v = (int)(n_valid - slice_off) - lane * kLaneBytes;
-                const int valid = (MODE == kModePair) ? v : (v + STRIDE - 1) / STRIDE;
-                hits = (valid <= 0) ? 0u : ((valid >= 32) ? hits : (hits & ((1u << valid) - 1u)));
-            }
+#endif
+                if (n_valid - slice_off < (uint32_t)kSliceBytes) {       /* last slice of the segment: probes that start past it */
+                    const int v = (int)(n_valid - slice_off) - lane * kLaneBytes;
+                    const int valid = (MODE == kModePair) ? v : (v + STRIDE - 1) / STRIDE;
+                    hits = (valid <= 0) ? 0u : ((valid >= 32) ? hits : (hits & ((1u << valid) - 1u)));
+                }
 #ifdef ACB_EXP_NOSURV
-            if (hits == 0x9e3779b9u) s_ctl[3] = 1u;                      /* timing experiment: probes only, survivors dropped */
-            hits = 0;
+                if (hits == 0x9e3779b9u) s_tile[0] = 1u;                 /* timing experiment: probes only, survivors dropped */
+                hits = 0;
 #endif
-            /* lanes with survivors: {where the lane's bytes are, which probes passed} -> this CTA's candidate region */
-            const unsigned any = __ballot_sync(kFull, hits != 0);
-            if (any) {
-                unsigned int idx = 0;
-                if (lane == 0) idx = atomicAdd(const_cast<unsigned int *>(s_ctl), (unsigned int)__popc(any));
-                idx = __shfl_sync(kFull, idx, 0) + __popc(any & lt_mask);
-                if (hits && idx < p.region_cap) region[idx] = make_uint2(tile_off + slice_off + (uint32_t)lane * kLaneBytes, hits);
+                /* lanes with survivors: {where the lane's bytes are, which probes passed} -> the warp's candidate list
+                   (room for every lane of every slice of the phase) */
+                const unsigned any = __ballot_sync(kFull, hits != 0);
+                if (hits) list[n_cand + __popc(any & lt_mask)] = make_uint2(tile_off + slice_off + (uint32_t)lane * kLaneBytes, hits);
+#ifndef ACB_EXP_NODRAIN
+                n_cand += __popc(any);
+#endif
             }
+            if (n_cand) resolve_backlog<NW>(p, smem_raw, n_cand);
         }
     }
-    /* hand the region over: its entry count (an overflow sets the sticky flag: the host repeats the scan with room for
-       every lane); the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
+    /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
     __syncthreads();
     if (tid == 0) {
-        const unsigned int n = s_ctl[0];
-        p.region_count[blockIdx.x] = n < p.region_cap ? n : p.region_cap;
-        if (n > p.region_cap) atomicOr(p.work_ctr + 3, 1u);
         __threadfence();
         unsigned int done = atomicAdd(p.work_ctr + 1, 1u);
         if (done == gridDim.x - 1) {
             p.work_ctr[0] = 0u;
             p.work_ctr[1] = 0u;
-            __threadfence();
-        }
-    }
-}
-
-/* acb_resolve_kernel: every hit of every candidate entry through the anchor table.  kResPerRegion CTAs share one
- * region; a thread takes one entry at a time: the text at the hit (L2 / HBM), hash2 of its gram, the anchor slot the
- * tag hashes to (L2), the compare.  Three dependent round trips per hit, hidden by occupancy (1536 threads per SM)
- * instead of by the streaming warps.  Match records are staged per warp and appended with one atomicAdd per flush. */
-template <int NW>
-__global__ void __launch_bounds__(kResThreads, 4) acb_resolve_kernel(const __grid_constant__ ScanParams p, int step) {
-    __shared__ acb_match s_stage[(kResThreads / 32) * kStageCap];
-    __shared__ int s_cnt[kResThreads / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < kResThreads / 32) s_cnt[tid] = 0;
-    __syncthreads();
-    WarpStage ws;
-    ws.buf = s_stage + warp * kStageCap;
-    ws.cnt = s_cnt + warp;
-    uint32_t mul2[NW];
-#pragma unroll
-    for (int k = 0; k < NW; k++) mul2[k] = p.mul2[k];
-    const int r = blockIdx.x / kResPerRegion, sub = blockIdx.x % kResPerRegion;
-    const unsigned int n = __ldcg(p.region_count + r);
-    const uint2 *region = p.cand + (size_t)r * p.region_cap;
-    /* Two entries per lane and turn, their loads issued together: the entries, then the text at their first hits, then
-       the anchor slots -- three round trips per turn instead of six.  The trip count is warp-uniform. */
-    constexpr int kPer = 2;
-    const unsigned int turn = kResPerRegion * kResThreads * kPer;
-    for (unsigned int i0 = (unsigned int)((sub * kResThreads + warp * 32) * kPer); i0 < n; i0 += turn) {
-        uint2 e[kPer];
-        bool got[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            const unsigned int i = i0 + 32u * j + lane;
-            got[j] = i < n;
-            e[j] = got[j] ? __ldcg(region + i) : make_uint2(0u, 0u);
-        }
-        long long q[kPer];
-        uint32_t tq[kPer][6], tag[kPer];
-        uint4 a0[kPer], a1[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) if (got[j]) {
-            q[j] = p.seg_begin + (long long)e[j].x + (long long)((uint32_t)(__ffs(e[j].y) - 1) * (uint32_t)step);
-            load_text(p, q[j], tq[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < kPer; j++) if (got[j]) {
-            tag[j] = tag_of<NW>(tq[j], q[j], mul2);
-            const uint32_t slot = tag[j] >> (32 - p.logA);
-            a0[j] = __ldg(p.anchors + 2 * (size_t)slot);
-            a1[j] = __ldg(p.anchors + 2 * (size_t)slot + 1);
-        }
-#pragma unroll
-        for (int j = 0; j < kPer; j++) if (got[j]) resolve_chain(p, ws, q[j], tag[j], tq[j], a0[j], a1[j]);
-        /* further hits in the same bytes (rare on sparse-match text) */
-#pragma unroll
-        for (int j = 0; j < kPer; j++) if (got[j]) {
-            const long long q0 = p.seg_begin + (long long)e[j].x;
-            uint32_t m = e[j].y & (e[j].y - 1);
-            while (m) {
-                resolve_one<NW>(p, ws, q0 + (long long)((uint32_t)(__ffs(m) - 1) * (uint32_t)step), mul2);
-                m &= m - 1;
-            }
-        }
-        __syncwarp();
-        if (*reinterpret_cast<volatile int *>(ws.cnt) >= kStageCap / 2) flush_stage(p, ws, lane);    /* warp-uniform */
-    }
-    flush_stage(p, ws, lane);
-    /* the last CTA of the last segment's launch turns a sticky overflow into *count = -1 and clears it */
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        unsigned int done = atomicAdd(p.work_ctr + 2, 1u);
-        if (done == gridDim.x - 1) {
-            p.work_ctr[2] = 0u;
-            if (p.last_segment && p.work_ctr[3]) { *p.count = ~0ULL; p.work_ctr[3] = 0u; }
             __threadfence();
         }
     }
@@ -837,10 +844,7 @@ struct acb_table {
     int32_t *d_goto = nullptr, *d_fail = nullptr, *d_keyof = nullptr, *d_outptr = nullptr, *d_outidx = nullptr, *d_keylen = nullptr;
     uint32_t *d_bm1 = nullptr, *d_anchors = nullptr;
     unsigned int *d_work = nullptr;
-    uint2 *d_cand = nullptr;                 /* candidate list (stream -> resolve), one region per stream CTA */
-    size_t cand_entries = 0;
-    unsigned int *d_region_count = nullptr;
-    bool cand_worst_case = false;
+    uint2 *d_cand = nullptr;                 /* candidate lists of the stream kernel's consumer warps (kWarpCand entries each) */
     long long dev_bytes = 0;
     std::vector<int32_t> key_len;            /* host copy, for sorting records */
     /* workspace of acb_scan_host */
@@ -880,7 +884,7 @@ extern "C" void acb_table_free(acb_table *tb) {
     cudaSetDevice(tb->device);
     cudaFree(tb->d_lfail); cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
     cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_anchors);
-    cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->d_region_count); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
+    cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
     if (tb->h_count) cudaFreeHost(tb->h_count);
     if (tb->h_out) cudaFreeHost(tb->h_out);
     if (tb->ev0) cudaEventDestroy(tb->ev0);
@@ -946,24 +950,11 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
 }
 
 extern "C" int64_t acb_table_device_bytes(const acb_table *tb) { return tb ? tb->dev_bytes : 0; }
-extern "C" int acb_table_reserve_candidates(acb_table *tb, int worst_case) {
-    if (!tb) return ACB_EINVAL;
-    tb->cand_worst_case = worst_case != 0;
-    return ACB_OK;
-}
 extern "C" int64_t acb_launch_count(void) { return g_launches.load(); }
 extern "C" int acb_set_kernel_timing(int enabled) { g_timing.store(enabled ? 1 : 0); return ACB_OK; }
 extern "C" float acb_last_kernel_ms(void) { return g_last_ms; }
 
 /* ------------------------------------------------------------- launching */
-
-template <int NW>
-static int launch_resolve(const ScanParams &p, int step, cudaStream_t s) {
-    acb_resolve_kernel<NW><<<p.n_regions * kResPerRegion, kResThreads, 0, s>>>(p, step);
-    CUDA_TRY(cudaGetLastError());
-    g_launches.fetch_add(1);
-    return ACB_OK;
-}
 
 template <int NW, int STRIDE, int MODE>
 static int launch_stream_m(const ScanParams &p, int grid, cudaStream_t s) {
@@ -977,7 +968,7 @@ static int launch_stream_m(const ScanParams &p, int grid, cudaStream_t s) {
     kern<<<grid, kFThreads, smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
-    return launch_resolve<NW>(p, MODE == kModePair ? 1 : STRIDE, s);
+    return ACB_OK;
 }
 
 /* the placement mode follows from the table's filter_flags */
@@ -1016,29 +1007,6 @@ static int launch_stream(const ScanParams &p, int flags, int stride, int grid, c
     }
     acb_set_error("unsupported gram length %d", p.gram);
     return ACB_EINVAL;
-}
-
-/* The candidate list of one segment launch: one region per stream CTA.  By default a region has room for a quarter
- * of the lanes an even share of the tiles holds (a lane = kLaneBytes of text = one possible entry); a scan that
- * overflows any region sets a sticky flag, reports *count = -1, and is repeated with static tile assignment and
- * room for every lane (acb_table_reserve_candidates; acb_scan_host does this by itself). */
-static int ensure_candidates(acb_table *tb, ScanParams &p, int grid) {
-    const size_t tile_lanes = kTileBytes / kLaneBytes;
-    const size_t share = ((size_t)p.n_tiles + grid - 1) / grid * tile_lanes;         /* lanes of an even share of the tiles */
-    const size_t cap = tb->cand_worst_case ? share : std::max<size_t>(4096, share / 4);
-    const size_t need = cap * (size_t)grid;
-    if (!tb->d_cand || tb->cand_entries < need) {
-        if (tb->d_cand) { cudaFree(tb->d_cand); tb->d_cand = nullptr; tb->cand_entries = 0; }
-        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_cand), need * sizeof(uint2)));
-        tb->cand_entries = need;
-    }
-    if (!tb->d_region_count) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_region_count), 1024 * sizeof(unsigned int)));
-    p.cand = tb->d_cand;
-    p.region_cap = (unsigned int)cap;
-    p.region_count = tb->d_region_count;
-    p.n_regions = grid;
-    p.static_tiles = tb->cand_worst_case ? 1 : 0;
-    return ACB_OK;
 }
 
 extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t total_bytes,
@@ -1083,15 +1051,18 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
         CUDA_TRY(cudaEventRecord(tb->ev0, s));
     }
     if (algo == ACB_ALGO_FILTER) {
+        if (!tb->d_cand) {                                  /* room for every lane of every slice of a phase: never overflows */
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_cand), (size_t)tb->sm_count * kConsumers * kWarpCand * sizeof(uint2)));
+            tb->dev_bytes += (long long)tb->sm_count * kConsumers * kWarpCand * (long long)sizeof(uint2);
+        }
+        p.cand = tb->d_cand;
+        p.step = (tb->filter_flags & ACB_FILTER_PAIR) ? 1 : tb->stride;
         for (long long seg = 0; seg < total_bytes; seg += kSegBytes) {
             p.seg_begin = seg;
             p.seg_end = std::min<long long>(seg + kSegBytes, total_bytes);
             p.n_tiles = (unsigned int)((p.seg_end - p.seg_begin + kTileBytes - 1) / kTileBytes);
             const int grid = (int)std::min<long long>(tb->sm_count, p.n_tiles);
-            int rc = ensure_candidates(tb, p, grid);
-            if (rc != ACB_OK) return rc;
-            p.last_segment = p.seg_end == total_bytes;
-            rc = launch_stream(p, tb->filter_flags, tb->stride, grid, s);
+            int rc = launch_stream(p, tb->filter_flags, tb->stride, grid, s);
             if (rc != ACB_OK) return rc;
         }
     } else if (algo == ACB_ALGO_DFA) {
@@ -1264,11 +1235,6 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
     CUDA_TRY(cudaStreamSynchronize(s));
     if (trace) t2 = now();
     unsigned long long n = *tb->h_count;
-    if (n == ~0ULL) {                                           /* a candidate region overflowed: redo with room for every lane */
-        if (tb->cand_worst_case) { acb_set_error("candidate list overflow even at worst-case capacity"); return ACB_ECUDA; }
-        tb->cand_worst_case = true;
-        return acb_scan_host(tb, hay, total_bytes, offsets, n_hay, stride_bytes, out, cap, n_found, algo, sort);
-    }
     *n_found = (int64_t)n;
     if (n > (unsigned long long)cap) {
         acb_set_error("match buffer too small: %llu matches, capacity %lld", n, (long long)cap);
