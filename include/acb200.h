@@ -119,8 +119,10 @@ typedef struct acb_flat_view {
     int32_t        stride;        /* s : probe every s-th byte position                       */
     int32_t        log2_bits1;    /* n: the gram bitmap has 2^n bits (shared memory on the device), 2^(n-5) words */
     int32_t        log2_anchor_slots; /* anchor table has 2^n slots of 8 uint32 (32 B)        */
+    int32_t        log2_bits3;    /* tag bitmap (global memory) has 2^k bits; 0 = not built    */
     const uint32_t *bitmap1;      /* a gram sets two bits of one word: single placement word = umulhi(hash1, 2^(n-5)),
                                      pair placement acb_pair_place (csrc/acb_hash.h)          */
+    const uint32_t *bitmap3;      /* 1<<(k-5) words: bit = (hash2|1) * 0x9E3779B1 >> (32-k); only for key sets the shared-memory filter cannot hold */
     const uint32_t *anchors;      /* slot: tag(hash2|1, 0=empty), key_id(-1=MULTI), j|len<<8|last<<16, 20 bytes */
     int32_t        filter_flags;  /* ACB_FILTER_* : how the bitmap places a gram (csrc/acb_hash.h) */
 } acb_flat_view;

@@ -28,8 +28,9 @@ class FlatView(ctypes.Structure):
         ("key_of", ctypes.POINTER(ctypes.c_int32)), ("out_ptr", ctypes.POINTER(ctypes.c_int32)),
         ("out_idx", ctypes.POINTER(ctypes.c_int32)), ("key_len", ctypes.POINTER(ctypes.c_int32)),
         ("gram_bytes", ctypes.c_int32), ("stride", ctypes.c_int32),
-        ("log2_bits1", ctypes.c_int32), ("log2_anchor_slots", ctypes.c_int32),
-        ("bitmap1", ctypes.POINTER(ctypes.c_uint32)), ("anchors", ctypes.POINTER(ctypes.c_uint32)),
+        ("log2_bits1", ctypes.c_int32), ("log2_anchor_slots", ctypes.c_int32), ("log2_bits3", ctypes.c_int32),
+        ("bitmap1", ctypes.POINTER(ctypes.c_uint32)), ("bitmap3", ctypes.POINTER(ctypes.c_uint32)),
+        ("anchors", ctypes.POINTER(ctypes.c_uint32)),
         ("filter_flags", ctypes.c_int32),
     ]
 

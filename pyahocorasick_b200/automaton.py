@@ -11,13 +11,27 @@ Reference semantics are cited as file:line relative to /root/reference.
 from __future__ import annotations
 
 import ctypes
+import functools
 import operator
 import pickle
+import threading
 from typing import Any, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import _native as N
+
+
+def _locked(method):
+    """Run a method under the Automaton's GPU lock.  The native calls release the GIL (ctypes.CDLL) and a scan works
+    in per-table scratch buffers, so two threads searching, or one searching while another changes the key set (which
+    frees the device table), must not interleave; the reference gets the same guarantee from holding the GIL for the
+    whole search (src/Automaton.c has no Py_BEGIN_ALLOW_THREADS)."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with self._gpu_lock:
+            return method(self, *args, **kwargs)
+    return wrapper
 
 # constants: src/Automaton.h:16-41, src/AutomatonItemsIter.h
 EMPTY, TRIE, AHOCORASICK = 0, 1, 2
@@ -128,6 +142,7 @@ class Automaton:
             store = args[0]
             self._check_store(store)
         self._lib = N.lib()
+        self._gpu_lock = threading.RLock()      # see _locked
         self._trie = None
         self._table = None
         self._narrow_trie = None
@@ -251,6 +266,7 @@ class Automaton:
     def __len__(self):
         return self._lib.acb_trie_count(self._trie)
 
+    @_locked
     def add_word(self, *args) -> bool:
         """src/Automaton.c:201-300."""
         if not args:
@@ -347,15 +363,18 @@ class Automaton:
         self._drop_table()
         return (value,)
 
+    @_locked
     def remove_word(self, key) -> bool:
         return self._remove(key) is not None
 
+    @_locked
     def pop(self, key):
         r = self._remove(key)
         if r is None:
             raise KeyError(key)
         return r[0]
 
+    @_locked
     def clear(self) -> None:
         N.check(self._lib.acb_trie_clear(self._trie))
         self._key_ids.clear()
@@ -468,6 +487,7 @@ class Automaton:
         serialize.save(self, *args)
 
     # ------------------------------------------------------------------ automaton
+    @_locked
     def make_automaton(self):
         """src/Automaton.c:560-649 -> None when built, False when there was nothing to do."""
         built = ctypes.c_int32(0)
@@ -478,6 +498,7 @@ class Automaton:
         self._drop_table()
         return None
 
+    @_locked
     def _drop_table(self):
         if self._table is not None:
             self._lib.acb_table_free(self._table)
@@ -493,6 +514,7 @@ class Automaton:
     def _uses_narrow(self) -> bool:
         return self._UNICODE and self._key_type == KEY_STRING
 
+    @_locked
     def _narrow_host(self):
         """host trie of the latin-1 automaton (built lazily), or None when no key is pure latin-1."""
         if self._narrow_empty:
@@ -520,6 +542,7 @@ class Automaton:
             self._narrow_trie = t
         return self._narrow_trie
 
+    @_locked
     def _ensure_narrow(self, device: Optional[int]):
         """(trie, table) of the latin-1 automaton, or None when no key is pure latin-1."""
         if self._narrow_host() is None:
@@ -536,6 +559,7 @@ class Automaton:
             self._narrow_device = device
         return self._narrow_trie, self._narrow_table
 
+    @_locked
     def _ensure_table(self, device: Optional[int] = None):
         if device is None:
             device = _default_device()
@@ -548,6 +572,7 @@ class Automaton:
         self._table_device = device
         return tb
 
+    @_locked
     def flat(self, narrow: bool = False) -> dict:
         """White-box view of the flattened automaton (numpy copies) -- used by tests and docs.
         narrow=True: the latin-1 automaton of a unicode-flavour Automaton (None if it has no latin-1 key)."""
@@ -572,11 +597,13 @@ class Automaton:
             fail=arr(fv.fail, S, np.int32), letter_fail=arr(fv.letter_fail, S, np.int32), key_of=arr(fv.key_of, S, np.int32), out_ptr=arr(fv.out_ptr, S + 1, np.int32),
             out_idx=arr(fv.out_idx, n_out, np.int32), key_len=arr(fv.key_len, fv.n_keys, np.int32),
             gram_bytes=fv.gram_bytes, stride=fv.stride, log2_bits1=fv.log2_bits1,
-            log2_anchor_slots=fv.log2_anchor_slots, filter_flags=fv.filter_flags,
+            log2_anchor_slots=fv.log2_anchor_slots, filter_flags=fv.filter_flags, log2_bits3=fv.log2_bits3,
+            bitmap3=arr(fv.bitmap3, (1 << (fv.log2_bits3 - 5)) if fv.log2_bits3 else 1, np.uint32),
             bitmap1=arr(fv.bitmap1, 1 << (fv.log2_bits1 - 5), np.uint32),
             anchors=arr(fv.anchors, 8 << fv.log2_anchor_slots, np.uint32).reshape(-1, 8))
 
     # ------------------------------------------------------------------ GPU scan plumbing
+    @_locked
     def _scan_flat(self, flat: np.ndarray, offsets: Optional[np.ndarray], n_hay: int, stride_bytes: int,
                    algo: str = "auto", sort: bool = True, device: Optional[int] = None, narrow: bool = False) -> np.ndarray:
         """flat uint8 buffer (+ int64 byte offsets or a fixed stride) -> sorted match records.
@@ -610,6 +637,7 @@ class Automaton:
                 raise N.NativeError("acb_take_records: no records to take")
             return np.asarray(_PinnedRecords(self._lib, ptr.value, n.value, room.value))
 
+    @_locked
     def _scan_device_tensor(self, t, algo: str, sort: bool) -> np.ndarray:
         """Batch already resident in HBM: a C-contiguous uint8 torch CUDA tensor [n, stride].  No host copy of
         the haystacks; the scan runs on torch's current stream, only the records come back."""
@@ -783,6 +811,16 @@ class Automaton:
         # the latin-1 automaton finds exactly the matches of a latin-1 haystack -- all of them.  iter_long's walk is
         # different: which match it keeps depends on the whole trie (a non-latin-1 key whose prefix is latin-1 adds
         # nodes the walk passes through, src/AutomatonSearchIterLong.c:118-126), so it always runs on the full one
+        if not self._UNICODE and self._key_type == KEY_STRING and isinstance(haystacks, (list, tuple)) and haystacks \
+                and all(type(h) is bytes for h in haystacks):
+            # the common drop-in input, a list of bytes objects: one join instead of an array per haystack
+            n = len(haystacks)
+            offs = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(np.fromiter(map(len, haystacks), dtype=np.int64, count=n), out=offs[1:])
+            flat = np.frombuffer(b"".join(haystacks), dtype=np.uint8)
+            if not flat.size:
+                return Matches(np.empty(0, dtype=N.MATCH_DTYPE), self._values)
+            return Matches(self._scan_flat(flat, offs, n, 0, algo=algo, sort=sort, device=device), self._values)
         get = self._letters if algo == "long" else self._hay_letters
         letters = [get(h, required=True) for h in haystacks]
         narrow = self._uses_narrow() and len(letters) > 0 and all(a.dtype == np.uint8 for a in letters)

@@ -59,20 +59,20 @@
 namespace {
 
 #ifndef ACB_CONSUMERS
-#define ACB_CONSUMERS 31
+#define ACB_CONSUMERS 24
 #endif
 #ifndef ACB_STAGES
-#define ACB_STAGES 5
+#define ACB_STAGES 3
 #endif
 #ifndef ACB_LANE_BYTES
-#define ACB_LANE_BYTES 16
+#define ACB_LANE_BYTES 32
 #endif
 #ifndef ACB_PHASE_FILLS
-#define ACB_PHASE_FILLS 32
+#define ACB_PHASE_FILLS 16
 #endif
 constexpr int kConsumers    = ACB_CONSUMERS;          /* consumer warps of the stream kernel           */
 constexpr int kFThreads     = (kConsumers + 1) * 32;  /* + the producer warp                           */
-constexpr int kLaneBytes    = ACB_LANE_BYTES;         /* text bytes per lane and iteration (16 or 32)  */
+constexpr int kLaneBytes    = ACB_LANE_BYTES;         /* text bytes per lane and iteration             */
 constexpr int kLaneWords    = kLaneBytes / 4;
 constexpr int kSliceBytes   = 32 * kLaneBytes;        /* one warp iteration                            */
 constexpr int kTileBytes    = kConsumers * kSliceBytes;
@@ -80,11 +80,10 @@ constexpr int kLook         = 16;                     /* bytes copied past a til
 constexpr int kStageBytes   = (kTileBytes + kLook + 127) / 128 * 128;   /* tile + look-ahead, stages stay 128 B aligned */
 constexpr int kStages       = ACB_STAGES;
 constexpr int kClaimDepth   = 8;                      /* tile claims in flight per producer            */
-constexpr int kPhaseFills   = ACB_PHASE_FILLS;        /* a consumer warp resolves its candidates every kPhaseFills slices,
-                                                         while their text is still in L2 (kPhaseFills tiles per SM)  */
-constexpr int kWarpCand     = kPhaseFills * 32;       /* candidate entries a warp can collect between two phases: every lane of every slice */
-constexpr int kStageCap     = 32;                     /* match records staged per consumer warp (smem) */
-static_assert(kFThreads <= 1024 && kTileBytes % 16 == 0 && (kPhaseFills & (kPhaseFills - 1)) == 0, "stream kernel shape");
+constexpr int kWarpCand     = kSliceBytes + 32;       /* candidate entries per consumer warp: a warp resolves them as soon as it
+                                                         has 32, and one slice adds at most kSliceBytes (one per byte) */
+constexpr int kStageCap     = 64;                     /* match records staged per consumer warp (smem) */
+static_assert(kFThreads <= 1024 && kTileBytes % 16 == 0 && kLaneBytes == 32 && kStageCap * 12 / 2 >= 8 * 32, "stream kernel shape");
 constexpr uint32_t kFull    = 0xffffffffu;
 constexpr uint32_t kNoTile  = 0xffffffffu;
 constexpr int32_t  kTermBit = 0x40000000;             /* goto entry flag: child ends a key             */
@@ -119,8 +118,9 @@ struct ScanParams {
     int32_t gram;
     int32_t max_key_bytes;
     const uint32_t *bm1;           /* gram bitmap, 2^(log1-5) words */
+    const uint32_t *bm3;           /* tag bitmap in global memory, 2^log3 bits; log3 == 0: not built */
     const uint4 *anchors;          /* 2 x uint4 per slot */
-    int32_t log1, logA;
+    int32_t log1, log3, logA;
     uint32_t mul1[ACB_MAX_WINDOWS];
     uint32_t mul2[ACB_MAX_WINDOWS];
     acb_match *out;
@@ -129,8 +129,7 @@ struct ScanParams {
     long long seg_begin, seg_end;  /* byte range of this launch */
     unsigned int n_tiles;          /* kTileBytes tiles in the segment */
     unsigned int *work_ctr;        /* [0] next tile, [1] CTAs done */
-    uint2 *cand;                   /* candidate entries, kWarpCand per consumer warp of every CTA: {position of a lane's bytes in the segment, hit mask} */
-    int step;                      /* bytes between the probes two adjacent mask bits stand for */
+    uint2 *cand;                   /* candidate entries, kWarpCand per consumer warp of every CTA: {position in the segment, anchor tag} */
     int stride_shift;              /* log2(stride_bytes) when it is a power of two, else -1 */
     int letter_shift;              /* log2(L) */
 };
@@ -302,16 +301,6 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-/* hash2 (the anchor tag) of the gram at byte position q, from the aligned words load_text(q) returned */
-template <int NW>
-__device__ __forceinline__ uint32_t tag_of(const uint32_t (&tq)[6], long long q, const uint32_t (&mul2)[NW]) {
-    const int sh = (int)(q & 3) * 8;
-    uint32_t tag = 0;
-#pragma unroll
-    for (int k = 0; k < NW; k++) tag += __funnelshift_r(tq[k], tq[k + 1], sh) * mul2[k];
-    return tag | 1u;
-}
-
 /* Follow the anchor chain of `tag` for the candidate at q, starting with the slot (e0, e1) already loaded.
  * Three ways out, in the order of their frequency on sparse-match text: an empty slot (the bitmap let a foreign
  * gram through); ONE entry that is the last of its tag, UNIQUE and anchored at its first byte (every such lane of
@@ -358,24 +347,14 @@ __device__ __forceinline__ void resolve_chain(const ScanParams &p, const WarpSta
     }
 }
 
-/* one candidate position, start to end (used for the second and later hits of a lane's 32 bytes) */
-template <int NW>
-__device__ __forceinline__ void resolve_one(const ScanParams &p, const WarpStage &ws, long long q, const uint32_t (&mul2)[NW]) {
-    uint32_t tq[6];
-    load_text(p, q, tq);
-    const uint32_t tag = tag_of<NW>(tq, q, mul2);
-    const uint32_t slot = tag >> (32 - p.logA);
-    const uint4 e0 = __ldg(p.anchors + 2 * (size_t)slot), e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
-    resolve_chain(p, ws, q, tag, tq, e0, e1);
-}
-
 /* what a consumer warp needs to probe a slice */
 struct ProbeCtx {
     uint32_t sbm;              /* shared-memory address of the bitmap */
+    uint32_t sbm2;             /* PAIR: shared-memory address of level 2 (the second half of the bits) */
     uint32_t n_words;          /* umulhi(h, n_words) = word index */
     uint32_t four;             /* == 4, opaque to the compiler so the address is one IMAD (FMA pipe, which has room) */
     uint32_t two;              /* == 2, same trick for the hit accumulator */
-    int sh_bit;                /* NARROW: h >> sh_bit supplies the first bit index (low 5 bits, wrap shift); PAIR: the word index */
+    int sh_bit;                /* NARROW: h >> sh_bit supplies the first bit index (low 5 bits, wrap shift); PAIR: hc >> sh_bit = level-1 bit index, hc >> (sh_bit + 5) = word index of both levels */
 };
 
 /* window t of the lane's text: the 4 bytes at byte offset t of W[] (little endian) */
@@ -421,40 +400,25 @@ __device__ __forceinline__ uint32_t dp4a_u32(uint32_t x, uint32_t c) {
     return d;
 }
 
+/* PAIR placement, level 1 (acb_hash.h): one bit per pair of positions, keyed by the three bytes the pair's two grams
+ * share.  Per pair: the window at x+1, one multiply, the word (one shared-memory load), a left shift that brings the
+ * tested bit to bit 31, and an add-with-carry pair that shifts it into the mask.  Bit j of the result = pair j. */
 template <int N>
-__device__ __forceinline__ uint32_t probe_pair(const ProbeCtx &c, const uint32_t (&W)[N], uint32_t mulp, uint32_t ca, uint32_t cb) {
-    uint32_t acc = 0;
-#pragma unroll
-    for (int x = 0; x < kLaneBytes; x += 2) {
-        const uint32_t w0 = window(W, x), w1 = window(W, x + 1);
-        const uint32_t word = lds_bitmap(((w1 * mulp) >> c.sh_bit) * c.four + c.sbm);     /* sh_bit = 32 - log2(words) */
-        const uint32_t r0 = __funnelshift_r(word, 0u, dp4a_u32(w0, ca)) & __funnelshift_r(word, 0u, dp4a_u32(w0, cb)) & 1u;
-        const uint32_t r1 = __funnelshift_r(word, 0u, dp4a_u32(w1, ca)) & __funnelshift_r(word, 0u, dp4a_u32(w1, cb)) & 1u;
-        acc = acc + acc + r0;                                     /* plain adds: they issue on either pipe */
-        acc = acc + acc + r1;
-    }
-    return __brev(acc) >> (32 - kLaneBytes);
-}
-
-#ifdef ACB_EXP_L1ONLY
-/* timing experiment: the level-1 probe of a two-level design (one bit per pair, keyed by the three common bytes) */
-template <int N>
-__device__ __forceinline__ uint32_t probe_l1(const ProbeCtx &c, const uint32_t (&W)[N], uint32_t mulp) {
+__device__ __forceinline__ uint32_t probe_pair_level1(const ProbeCtx &c, const uint32_t (&W)[N], uint32_t mulp) {
     uint32_t acc = 0;
 #pragma unroll
     for (int x = 0; x < kLaneBytes; x += 2) {
         const uint32_t hc = window(W, x + 1) * mulp;
-        const uint32_t word = lds_bitmap((hc >> 18) * c.four + c.sbm);
-        const uint32_t t = __funnelshift_l(0u, word, hc >> 13);          /* word << (bit index): the tested bit lands in bit 31 */
+        const uint32_t word = lds_bitmap((hc >> (c.sh_bit + 5)) * c.four + c.sbm);
+        const uint32_t t = __funnelshift_l(0u, word, hc >> c.sh_bit);    /* word << (index & 31): bit 31 - (index & 31) -> bit 31 */
         asm("{ .reg .u32 t2; add.cc.u32 t2, %1, %1; addc.u32 %0, %0, %0; }" : "+r"(acc) : "r"(t));
     }
-    return acc;
+    return __brev(acc) >> (32 - kLaneBytes / 2);
 }
-#endif
 
 /* shared-memory carve-up of the stream kernel (host and device agree through this one function) */
 struct StreamSmem {
-    uint32_t bitmap, stages, stage_rec, stage_cnt, bars, tiles, total;
+    uint32_t bitmap, stages, stage_rec, stage_cnt, bars, tiles, next, total;
 };
 __host__ __device__ inline StreamSmem stream_smem(int log1) {
     StreamSmem s;
@@ -465,16 +429,15 @@ __host__ __device__ inline StreamSmem stream_smem(int log1) {
     s.stage_cnt = o; o += (uint32_t)kConsumers * 4u;              o = (o + 15u) & ~15u;
     s.bars = o;      o += 2u * kStages * 8u;                      /* full[kStages], empty[kStages] */
     s.tiles = o;     o += (uint32_t)kStages * 4u;
+    s.next = o;      o += 4u;                                     /* next slice to hand out */
     s.total = (o + 15u) & ~15u;
     return s;
 }
 
-/* A consumer warp's collected candidates, entries [0, n) of `list`, through the anchor table.  Two entries per lane
- * and turn, their loads issued together: the entries, then the text at their first hits, then the anchor slots the
- * tags hash to -- three round trips per turn (kPer = 1: a second entry per lane makes ptxas spill inside the probe loop).
- * Text and anchors come from L2: the bytes were streamed at most
- * kPhaseFills tiles ago. */
-template <int NW>
+/* A consumer warp's collected candidates {position in the segment, tag}, entries [0, n) of its list, through the anchor
+ * table: one entry per lane and turn, the text at the position and the anchor slot its tag hashes to loaded together
+ * (one round trip; a second entry per lane makes ptxas spill inside the probe loop).  Text and anchors come from L2:
+ * the bytes were streamed at most kPhaseFills tiles ago.  Records are flushed when the staging area is a quarter full. */
 __device__ __forceinline__ void resolve_backlog(const ScanParams &p, uint8_t *smem_raw, unsigned int n) {
     /* everything but n is rebuilt here rather than kept alive across the probe loop */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -483,49 +446,22 @@ __device__ __forceinline__ void resolve_backlog(const ScanParams &p, uint8_t *sm
     ws.buf = reinterpret_cast<acb_match *>(smem_raw + lay.stage_rec) + warp * kStageCap;
     ws.cnt = reinterpret_cast<int *>(smem_raw + lay.stage_cnt) + warp;
     const uint2 *list = p.cand + ((size_t)blockIdx.x * kConsumers + warp) * kWarpCand;
-    uint32_t mul2[NW];
-#pragma unroll
-    for (int k = 0; k < NW; k++) mul2[k] = p.mul2[k];
-    constexpr int kPer = 1;
     __syncwarp();                                                        /* the entries were written by other lanes of this warp */
-    for (unsigned int i0 = 0; i0 < n; i0 += 32 * kPer) {
-        uint2 e[kPer];
-        bool got[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            const unsigned int i = i0 + 32u * j + lane;
-            got[j] = i < n;
-            e[j] = got[j] ? __ldcg(list + i) : make_uint2(0u, 0u);
+    for (unsigned int i0 = 0; i0 < n; i0 += 32) {
+        const unsigned int i = i0 + lane;
+        if (i < n) {
+            const uint2 e = __ldcg(list + i);
+            const long long q = p.seg_begin + (long long)e.x;
+            uint32_t tq[6];
+            load_text(p, q, tq);
+            const uint32_t slot = e.y >> (32 - p.logA);
+            const uint4 a0 = __ldg(p.anchors + 2 * (size_t)slot), a1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
+            resolve_chain(p, ws, q, e.y, tq, a0, a1);
         }
-        long long q[kPer];
-        uint32_t tq[kPer][6], tag[kPer];
-        uint4 a0[kPer], a1[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) if (got[j]) {
-            q[j] = p.seg_begin + (long long)e[j].x + (long long)((uint32_t)(__ffs(e[j].y) - 1) * (uint32_t)p.step);
-            load_text(p, q[j], tq[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < kPer; j++) if (got[j]) {
-            tag[j] = tag_of<NW>(tq[j], q[j], mul2);
-            const uint32_t slot = tag[j] >> (32 - p.logA);
-            a0[j] = __ldg(p.anchors + 2 * (size_t)slot);
-            a1[j] = __ldg(p.anchors + 2 * (size_t)slot + 1);
-        }
-#pragma unroll
-        for (int j = 0; j < kPer; j++) if (got[j]) resolve_chain(p, ws, q[j], tag[j], tq[j], a0[j], a1[j]);
-        /* further hits in the same bytes (rare on sparse-match text) */
-#pragma unroll
-        for (int j = 0; j < kPer; j++) if (got[j]) {
-            const long long q0 = p.seg_begin + (long long)e[j].x;
-            uint32_t m = e[j].y & (e[j].y - 1);
-            while (m) {
-                resolve_one<NW>(p, ws, q0 + (long long)((uint32_t)(__ffs(m) - 1) * (uint32_t)p.step), mul2);
-                m &= m - 1;
-            }
-        }
-        flush_stage(p, ws, lane);
+        __syncwarp();
+        if (*reinterpret_cast<volatile int *>(ws.cnt) >= kStageCap / 4) flush_stage(p, ws, lane);    /* warp-uniform */
     }
+    flush_stage(p, ws, lane);
 }
 
 /* acb_stream_kernel: persistent, one CTA per SM, warp specialised:
@@ -556,6 +492,7 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + lay.bitmap + 16u * i), "l"(src + i));
         asm volatile("cp.async.commit_group;");
         if (tid < kConsumers) reinterpret_cast<int *>(smem_raw + lay.stage_cnt)[tid] = 0;
+        if (tid == 0) *reinterpret_cast<unsigned int *>(smem_raw + lay.next) = 0u;
         if (tid == 0) {
             for (int s = 0; s < kStages; s++) {
                 mbar_init(bar_full + 8u * s, 1);                 /* the producer's arrive(.expect_tx) */
@@ -628,10 +565,11 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         /* ---------------- consumer warps: slice `warp` of every fill */
         ProbeCtx c;
         c.sbm = sbase + lay.bitmap;
+        c.sbm2 = c.sbm + (1u << (p.log1 - 4));                          /* PAIR: level 2 = the second half of the bits */
         c.n_words = 1u << (p.log1 - 5);
         c.four = 4u + (uint32_t)(p.log1 >> 8);                           /* always 4 */
         c.two = 2u + (uint32_t)(p.log1 >> 8);                            /* always 2 */
-        c.sh_bit = (MODE == kModePair) ? 37 - p.log1 : 32 - p.log1;     /* PAIR: hash >> sh_bit = word index */
+        c.sh_bit = (MODE == kModePair) ? 33 - p.log1 : 32 - p.log1;
         const uint32_t lt_mask = (1u << lane) - 1u;
         uint32_t mul[NW];
 #pragma unroll
@@ -640,71 +578,145 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         const uint32_t ca = ACB_PAIR_CA + (uint32_t)(p.log1 >> 8), cb = ACB_PAIR_CB + (uint32_t)(p.log1 >> 8);
         const uint32_t slice_off = (uint32_t)warp * kSliceBytes;
         uint2 *list = p.cand + ((size_t)blockIdx.x * kConsumers + warp) * kWarpCand;
-        uint32_t stage = 0, parity = 0;
-        bool more = true;
-        while (more) {
-            /* one phase: kPhaseFills slices of pure streaming (no call inside this loop), then the candidates they left */
-            unsigned int n_cand = 0;                                     /* warp-uniform */
-#pragma unroll 1
-            for (int s = 0; s < kPhaseFills; s++) {
-                mbar_wait(bar_full + 8u * stage, parity);
-                const uint32_t tile = s_tile[stage];
-                if (tile == kNoTile) { more = false; break; }
-                const uint32_t tile_off = tile * (uint32_t)kTileBytes;   /* relative to the segment */
-                const uint32_t n_valid = (seg_len - tile_off < (uint32_t)kTileBytes) ? seg_len - tile_off : (uint32_t)kTileBytes;
-                const bool live = slice_off < n_valid;                   /* warp-uniform */
+        uint32_t mul2[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) mul2[k] = p.mul2[k];
+        /* the match staging area is idle while the warp streams: it holds the slice's work items (lane << 5 | bit) */
+        volatile uint16_t *items = reinterpret_cast<volatile uint16_t *>(smem_raw + lay.stage_rec + (size_t)warp * kStageCap * sizeof(acb_match));
+        constexpr int kItemCap = kStageCap * (int)sizeof(acb_match) / 2;
+        constexpr int kPendBits = (MODE == kModePair) ? kLaneBytes / 2 : kLaneBytes / STRIDE;
+        unsigned int *s_next = reinterpret_cast<unsigned int *>(smem_raw + lay.next);
+        unsigned int n_cand = 0;                                         /* warp-uniform */
+
+        /* Slices are handed out dynamically: slice g is slice g % kConsumers of fill g / kConsumers.  A warp that is busy
+           resolving candidates simply takes fewer slices.  With exactly kConsumers warps, kConsumers slices per fill and
+           one slice held per warp, a waiter can never be a whole ring turn ahead of the barrier phase it waits for. */
+        for (;;) {
+            unsigned int g = 0;
+            if (lane == 0) g = atomicAdd(s_next, 1u);
+            g = __shfl_sync(kFull, g, 0);
+            const uint32_t fill = g / (uint32_t)kConsumers, slice_off = (g % (uint32_t)kConsumers) * (uint32_t)kSliceBytes;
+            const uint32_t stage = fill % (uint32_t)kStages;
+            mbar_wait(bar_full + 8u * stage, (fill / (uint32_t)kStages) & 1u);
+            const uint32_t tile = s_tile[stage];
+            if (tile == kNoTile) break;
+            const uint32_t tile_off = tile * (uint32_t)kTileBytes;       /* relative to the segment */
+            const uint32_t n_valid = (seg_len - tile_off < (uint32_t)kTileBytes) ? seg_len - tile_off : (uint32_t)kTileBytes;
+            if (slice_off < n_valid) {                                   /* warp-uniform */
+                const uint32_t slice_saddr = sbase + lay.stages + stage * (uint32_t)kStageBytes + slice_off;
+                const uint32_t saddr = slice_saddr + (uint32_t)lane * kLaneBytes;
                 uint32_t W[kLaneWords + NW];
-                if (live) {
-                    const uint32_t saddr = sbase + lay.stages + stage * (uint32_t)kStageBytes + slice_off + (uint32_t)lane * kLaneBytes;
 #pragma unroll
-                    for (int i = 0; i < kLaneWords; i += 4) {
-                        const uint4 v = lds128(saddr + 4u * i);
-                        W[i] = v.x; W[i + 1] = v.y; W[i + 2] = v.z; W[i + 3] = v.w;
-                    }
-                    /* look-ahead words: the next lane's first words; lane 31 reads past its slice (next slice / tile pad) */
-#pragma unroll
-                    for (int k = 0; k < NW; k++) W[kLaneWords + k] = __shfl_down_sync(kFull, W[k], 1);
-                    if (lane == 31) {
-#pragma unroll
-                        for (int k = 0; k < NW; k++) W[kLaneWords + k] = lds32(saddr + kLaneBytes + 4u * k);
-                    }
+                for (int i = 0; i < kLaneWords; i += 4) {
+                    const uint4 v = lds128(saddr + 4u * i);
+                    W[i] = v.x; W[i + 1] = v.y; W[i + 2] = v.z; W[i + 3] = v.w;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8u * stage);      /* the slice is in registers: the stage is free */
-                if (++stage == (uint32_t)kStages) { stage = 0; parity ^= 1u; }
-                if (!live) continue;
-                uint32_t hits;
+                /* look-ahead words: the next lane's first words; lane 31 reads past its slice (next slice / tile pad) */
+#pragma unroll
+                for (int k = 0; k < NW; k++) W[kLaneWords + k] = __shfl_down_sync(kFull, W[k], 1);
+                if (lane == 31) {
+#pragma unroll
+                    for (int k = 0; k < NW; k++) W[kLaneWords + k] = lds32(saddr + kLaneBytes + 4u * k);
+                }
+                /* pend: what has to be looked at more closely -- SINGLE: bit i = probe i passed the bitmap;
+                   PAIR: bit j = the pair of positions 2j, 2j+1 passed level 1 */
+                uint32_t pend;
 #ifdef ACB_EXP_NOPROBE
-                hits = (W[0] ^ W[3] ^ W[kLaneWords]) == 0x12345678u ? 1u : 0u;  /* timing experiment: the stream skeleton alone */
+                pend = (W[0] ^ W[3] ^ W[kLaneWords]) == 0x12345678u ? 1u : 0u;      /* timing experiment: the stream skeleton alone */
 #else
-#ifdef ACB_EXP_L1ONLY
-                if constexpr (MODE == kModePair) hits = probe_l1(c, W, mulp) == 0x12345u ? 1u : 0u;
-                else hits = 0;
-                if (ca == cb) hits = 1u;
-#else
-                if constexpr (MODE == kModePair) hits = probe_pair(c, W, mulp, ca, cb);
-                else hits = probe_single<NW, STRIDE, MODE == kModeWide>(c, W, mul);
-#endif
+                if constexpr (MODE == kModePair) pend = probe_pair_level1(c, W, mulp);
+                else pend = probe_single<NW, STRIDE, MODE == kModeWide>(c, W, mul);
 #endif
                 if (n_valid - slice_off < (uint32_t)kSliceBytes) {       /* last slice of the segment: probes that start past it */
                     const int v = (int)(n_valid - slice_off) - lane * kLaneBytes;
-                    const int valid = (MODE == kModePair) ? v : (v + STRIDE - 1) / STRIDE;
-                    hits = (valid <= 0) ? 0u : ((valid >= 32) ? hits : (hits & ((1u << valid) - 1u)));
+                    const int valid = (MODE == kModePair) ? (v + 1) / 2 : (v + STRIDE - 1) / STRIDE;
+                    pend = (valid <= 0) ? 0u : ((valid >= 32) ? pend : (pend & ((1u << valid) - 1u)));
                 }
 #ifdef ACB_EXP_NOSURV
-                if (hits == 0x9e3779b9u) s_tile[0] = 1u;                 /* timing experiment: probes only, survivors dropped */
-                hits = 0;
+                if (pend == 0x9e3779b9u) s_tile[0] = 1u;                 /* timing experiment: probes only, survivors dropped */
+                pend = 0;
 #endif
-                /* lanes with survivors: {where the lane's bytes are, which probes passed} -> the warp's candidate list
-                   (room for every lane of every slice of the phase) */
-                const unsigned any = __ballot_sync(kFull, hits != 0);
-                if (hits) list[n_cand + __popc(any & lt_mask)] = make_uint2(tile_off + slice_off + (uint32_t)lane * kLaneBytes, hits);
+                /* The pending bits of all lanes become work items, spread evenly over the warp (a lane's own bits would
+                   be worked off one per round: the busiest lane sets the pace); every item reads its text back from the
+                   stage, still ours.  A part = the bits whose items fit the staging area at once. */
+                if (__ballot_sync(kFull, pend != 0)) {
+                    const unsigned int total = __reduce_add_sync(kFull, (unsigned int)__popc(pend));
+                    const int nparts = (total > (unsigned int)kItemCap && kPendBits > 8) ? kPendBits / 8 : 1;
+                    for (int part = 0; part < nparts; part++) {
+                        uint32_t m = nparts > 1 ? ((pend >> (8 * part)) & 0xffu) : pend;
+                        const int cnt = __popc(m);
+                        int incl = cnt;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int v = __shfl_up_sync(kFull, incl, d);
+                            if (lane >= d) incl += v;
+                        }
+                        const int tot = __shfl_sync(kFull, incl, 31);
+                        int at = incl - cnt;
+                        while (m) {
+                            const int bit = __ffs(m) - 1;
+                            m &= m - 1;
+                            items[at++] = (uint16_t)((lane << 5) | (bit + (nparts > 1 ? 8 * part : 0)));
+                        }
+                        __syncwarp();
+                        for (int base = 0; base < tot; base += 32) {
+                            bool ok0 = false, ok1 = false;
+                            uint32_t pos0 = 0, tag0 = 0, tag1 = 0;
+                            if (base + lane < tot) {
+                                const uint32_t it = items[base + lane];
+                                const uint32_t t = (it >> 5) * (uint32_t)kLaneBytes + ((MODE == kModePair) ? 2u * (it & 31u) : (it & 31u) * (uint32_t)STRIDE);
+                                const uint32_t ga = slice_saddr + t, wa = ga & ~3u, sh = (ga & 3u) * 8u;
+                                pos0 = tile_off + slice_off + t;
+                                if constexpr (MODE == kModePair) {
+                                    const uint32_t lo = lds32(wa), hi = lds32(wa + 4u);
+                                    const uint32_t w0 = __funnelshift_r(lo, hi, sh), w1 = __funnelshift_r(lo, hi, sh + 8u);   /* t even: sh is 0 or 16 */
+                                    const uint32_t word = lds_bitmap((((w1 * mulp) >> (c.sh_bit + 5)) * c.four) + c.sbm2);
+                                    ok0 = (__funnelshift_r(word, 0u, dp4a_u32(w0, ca)) & __funnelshift_r(word, 0u, dp4a_u32(w0, cb)) & 1u) != 0u;
+                                    ok1 = (__funnelshift_r(word, 0u, dp4a_u32(w1, ca)) & __funnelshift_r(word, 0u, dp4a_u32(w1, cb)) & 1u) != 0u;
+                                    tag0 = (w0 * mul2[0]) | 1u;
+                                    tag1 = (w1 * mul2[0]) | 1u;
+                                } else {
+                                    uint32_t w0 = lds32(wa);
+#pragma unroll
+                                    for (int k = 0; k < NW; k++) {
+                                        const uint32_t w1 = lds32(wa + 4u * (k + 1));
+                                        tag0 += __funnelshift_r(w0, w1, sh) * mul2[k];
+                                        w0 = w1;
+                                    }
+                                    tag0 |= 1u;
+                                    ok0 = true;
+                                }
+                            }
+                            if (p.log3) {                                  /* large key sets: the tag bitmap in L2 first */
+                                const uint32_t i0 = (tag0 * ACB_TAGMAP_MIX) >> (32 - p.log3), i1 = (tag1 * ACB_TAGMAP_MIX) >> (32 - p.log3);
+                                if (ok0) ok0 = ((__ldg(p.bm3 + (i0 >> 5)) >> (i0 & 31u)) & 1u) != 0u;
+                                if (ok1) ok1 = ((__ldg(p.bm3 + (i1 >> 5)) >> (i1 & 31u)) & 1u) != 0u;
+                            }
 #ifndef ACB_EXP_NODRAIN
-                n_cand += __popc(any);
+                            /* append {position, hash2 of the gram = the anchor tag} to the warp's candidate list in global
+                               memory: the cursor is a register (no atomic), the store is one nobody waits for */
+                            const unsigned m0 = __ballot_sync(kFull, ok0);
+                            if (ok0) list[n_cand + __popc(m0 & lt_mask)] = make_uint2(pos0, tag0);
+                            n_cand += __popc(m0);
+                            if constexpr (MODE == kModePair) {
+                                const unsigned m1 = __ballot_sync(kFull, ok1);
+                                if (ok1) list[n_cand + __popc(m1 & lt_mask)] = make_uint2(pos0 + 1u, tag1);
+                                n_cand += __popc(m1);
+                            }
+#else
+                            if (ok0 && ok1 && tag0 == tag1 + pos0) s_tile[0] = 2u;      /* timing experiment: candidates dropped */
 #endif
+                        }
+                        __syncwarp();
+                    }
+                }
             }
-            if (n_cand) resolve_backlog<NW>(p, smem_raw, n_cand);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8u * stage);          /* this warp is done with the stage */
+            /* a full turn of candidates (one per lane): through the anchor table now, while the other warps stream on */
+            if (n_cand >= 32u) { resolve_backlog(p, smem_raw, n_cand); n_cand = 0; }
         }
+        if (n_cand) resolve_backlog(p, smem_raw, n_cand);
     }
     /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
     __syncthreads();
@@ -836,13 +848,13 @@ __global__ void __launch_bounds__(kDfaThreads) acb_long_kernel(const __grid_cons
 struct acb_table {
     int device = 0;
     int sm_count = 0;
-    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, logA = 10, filter_flags = 0;
+    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log3 = 0, logA = 10, filter_flags = 0;
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     uint8_t *d_cls = nullptr;
     int32_t *d_lfail = nullptr;
     int32_t *d_goto = nullptr, *d_fail = nullptr, *d_keyof = nullptr, *d_outptr = nullptr, *d_outidx = nullptr, *d_keylen = nullptr;
-    uint32_t *d_bm1 = nullptr, *d_anchors = nullptr;
+    uint32_t *d_bm1 = nullptr, *d_bm3 = nullptr, *d_anchors = nullptr;
     unsigned int *d_work = nullptr;
     uint2 *d_cand = nullptr;                 /* candidate lists of the stream kernel's consumer warps (kWarpCand entries each) */
     long long dev_bytes = 0;
@@ -883,7 +895,7 @@ extern "C" void acb_table_free(acb_table *tb) {
     if (!tb) return;
     cudaSetDevice(tb->device);
     cudaFree(tb->d_lfail); cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
-    cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_anchors);
+    cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_bm3); cudaFree(tb->d_anchors);
     cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
     if (tb->h_count) cudaFreeHost(tb->h_count);
     if (tb->h_out) cudaFreeHost(tb->h_out);
@@ -913,7 +925,7 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { acb_set_error("cudaGetDeviceProperties failed"); rc = ACB_ECUDA; break; }
         tb->sm_count = prop.multiProcessorCount;
         tb->S = f.n_states; tb->K = f.n_classes; tb->L = f.letter_bytes; tb->n_keys = f.n_keys;
-        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->logA = f.log2_anchor_slots; tb->filter_flags = f.filter_flags;
+        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log3 = f.log2_bits3; tb->logA = f.log2_anchor_slots; tb->filter_flags = f.filter_flags;
         tb->min_key_bytes = f.min_key_bytes; tb->max_key_bytes = f.max_key_bytes;
         acb_hash_multipliers(tb->gram, 1, tb->mul1);
         acb_hash_multipliers(tb->gram, 2, tb->mul2);
@@ -940,6 +952,7 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if ((rc = upload(&tb->d_outidx, f.out_idx, (size_t)f.out_ptr[f.n_states], tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_keylen, f.key_len, (size_t)f.n_keys, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_bm1, f.bitmap1, (size_t)1 << (f.log2_bits1 - 5), tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_bm3, f.bitmap3, f.log2_bits3 ? ((size_t)1 << (f.log2_bits3 - 5)) : 1, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_anchors, f.anchors, (size_t)8 << f.log2_anchor_slots, tb->dev_bytes))) break;
         unsigned int zero[4] = {0, 0, 0, 0};   /* work counters, re-armed by the kernels themselves */
         if ((rc = upload(&tb->d_work, zero, 4, tb->dev_bytes))) break;
@@ -1033,8 +1046,8 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     p.cls = tb->d_cls; p.gto = tb->d_goto; p.fail = tb->d_fail; p.letter_fail = tb->d_lfail; p.key_of = tb->d_keyof;
     p.out_ptr = tb->d_outptr; p.out_idx = tb->d_outidx; p.key_len = tb->d_keylen;
     p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.max_key_bytes = tb->max_key_bytes;
-    p.bm1 = tb->d_bm1; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
-    p.log1 = tb->log1; p.logA = tb->logA;
+    p.bm1 = tb->d_bm1; p.bm3 = tb->d_bm3; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
+    p.log1 = tb->log1; p.log3 = tb->log3; p.logA = tb->logA;
     memcpy(p.mul1, tb->mul1, sizeof(p.mul1));
     memcpy(p.mul2, tb->mul2, sizeof(p.mul2));
     p.out = d_out; p.cap = cap; p.count = reinterpret_cast<unsigned long long *>(d_count);
@@ -1056,7 +1069,6 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
             tb->dev_bytes += (long long)tb->sm_count * kConsumers * kWarpCand * (long long)sizeof(uint2);
         }
         p.cand = tb->d_cand;
-        p.step = (tb->filter_flags & ACB_FILTER_PAIR) ? 1 : tb->stride;
         for (long long seg = 0; seg < total_bytes; seg += kSegBytes) {
             p.seg_begin = seg;
             p.seg_end = std::min<long long>(seg + kSegBytes, total_bytes);

@@ -37,6 +37,7 @@
 #define ACB_S2_M1 0xD3A2646Du
 #define ACB_S2_M2 0xFD7046C5u
 #define ACB_S2_M3 0xB55A4F09u
+#define ACB_TAGMAP_MIX 0x9E3779B1u   /* tag bitmap (global memory): bit index = (tag * ACB_TAGMAP_MIX) >> (32 - log2_bits3) */
 
 /* fill mul[0..3] for a gram of g bytes; stage = 1 or 2 */
 ACB_HD void acb_hash_multipliers(int g, int stage, uint32_t mul[ACB_MAX_WINDOWS]) {
@@ -102,18 +103,22 @@ ACB_HD uint32_t acb_stage1_bit_a(uint64_t hw, int g, int log2_bits) {
 }
 ACB_HD uint32_t acb_stage1_bit_b(uint64_t hw) { return (uint32_t)hw & 31u; }
 
-/* ---- PAIR placement (gram 4, stride 1, 1-byte letters) --------------------------------------------------
- * Positions x (even) and x+1 share ONE bitmap word, selected by the three bytes their 4-byte grams have in
- * common, so the probe loop needs one shared-memory load per two positions.  With G the gram read as a
- * little-endian word:
- *      word   : top bits of ((common three bytes) * ACB_PAIR_M << 8) mod 2^32 -- a plain 32-bit multiply; the shifted
- *               multiplier drops the fourth byte of the register the kernel happens to have (the window at x+1)
- *      bits   : a = dp4a(G, ACB_PAIR_CA) & 31,  b = dp4a(G, ACB_PAIR_CB) & 31 -- byte-wise dot products with odd
- *               coefficients: their LOW five bits are already mixed over all four bytes, so they feed a wrap shift
- *               directly (no extraction), and IDP.4A issues at the rate of a 32-bit multiply (mul.hi / mul.wide, which
- *               the first version used for these bits, issue at half of it: measured, tools/ubench/pipes.cu)
- * Role 0 = G starts at the even position x (its bytes 1..3 are the common ones), role 1 = G starts at x+1 (bytes
- * 0..2).  Every key gram is entered under both roles (a key may start at an even or an odd position). */
+/* ---- PAIR placement (gram 4, stride 1, 1-byte letters): two levels, both keyed by the pair ------------------
+ * Positions x (even) and x+1 share the three bytes text[x+1 .. x+3].  Their hash
+ *      hc = (the three common bytes as a little-endian word) * (ACB_PAIR_M << 8)   (mod 2^32)
+ * (a plain 32-bit multiply of the window at x+1: the shifted multiplier drops that window's fourth byte) selects
+ *   level 1:  ONE BIT of a bitmap of 2^(n-1) bits  -- index hc >> (33-n): word index hc >> (38-n), bit 31 - (index & 31)
+ *             (the kernel shifts the word LEFT by the index, so the tested bit lands in bit 31 and is added into the
+ *             pass mask through the carry) -- "does any key gram have these three bytes where this pair has them?"
+ *   level 2:  ONE WORD of 2^(n-6) words, word index hc >> (38-n) as well, in which a gram G (little-endian word) of
+ *             either role sets two bits: a = dp4a(G, ACB_PAIR_CA) & 31, b = dp4a(G, ACB_PAIR_CB) & 31 (byte-wise dot
+ *             products with odd coefficients: their low five bits are already mixed over all four bytes, so they feed
+ *             a wrap shift directly, and IDP.4A issues at the rate of a 32-bit multiply -- mul.hi / mul.wide, which an
+ *             earlier version used here, issue at half of it: tools/ubench/pipes.cu).
+ * n = log2 of all the bits (2^n bits of shared memory: level 1 in the first half, level 2 in the second).  Only pairs
+ * that pass level 1 (a few per cent on random text) are looked at position by position.  Role 0 = G starts at the even
+ * position x (its bytes 1..3 are the common ones), role 1 = G starts at x+1 (bytes 0..2); every key gram is entered
+ * under both roles (a key may start at an even or an odd position). */
 #define ACB_PAIR_M  0x9E3779B1u
 #define ACB_PAIR_CA 0x1B0D0701u   /* bytes  1,  7, 13, 27 */
 #define ACB_PAIR_CB 0x1F091503u   /* bytes  3, 21,  9, 31 */
@@ -122,12 +127,16 @@ ACB_HD uint32_t acb_dp4a(uint32_t x, uint32_t c) {
     return (x & 0xffu) * (c & 0xffu) + ((x >> 8) & 0xffu) * ((c >> 8) & 0xffu) +
            ((x >> 16) & 0xffu) * ((c >> 16) & 0xffu) + (x >> 24) * (c >> 24);
 }
-/* role 0 / 1 placement of gram G: *word = index into 2^log2_words words, *bits = the two bits to set / test */
-ACB_HD void acb_pair_place(uint32_t G, int role, int log2_words, uint32_t *word, uint32_t *bits) {
+/* role 0 / 1 placement of gram G in a filter of 2^log2_bits bits: level 1 (*word1 |= *bit1) and level 2 (*word2 |= *bits2);
+ * word indices count 32-bit words from the start of the bitmap */
+ACB_HD void acb_pair_place(uint32_t G, int role, int log2_bits, uint32_t *word1, uint32_t *bit1, uint32_t *word2, uint32_t *bits2) {
     const uint32_t common = role ? G : (G >> 8);
-    const uint32_t lo = common * (ACB_PAIR_M << 8);
-    *word = lo >> (32 - log2_words);
-    *bits = (1u << (acb_dp4a(G, ACB_PAIR_CA) & 31u)) | (1u << (acb_dp4a(G, ACB_PAIR_CB) & 31u));
+    const uint32_t hc = common * (ACB_PAIR_M << 8);
+    const uint32_t idx = hc >> (33 - log2_bits);
+    *word1 = idx >> 5;
+    *bit1 = 1u << (31u - (idx & 31u));
+    *word2 = (1u << (log2_bits - 6)) + (hc >> (38 - log2_bits));
+    *bits2 = (1u << (acb_dp4a(G, ACB_PAIR_CA) & 31u)) | (1u << (acb_dp4a(G, ACB_PAIR_CB) & 31u));
 }
 
 #endif

@@ -104,8 +104,8 @@ struct Flat {
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint8_t byte_class[256];
     std::vector<int32_t> goto_cm, fail, letter_fail, key_of, out_ptr, out_idx, key_len;
-    int32_t gram = 0, stride = 0, log1 = 0, logA = 0, filter_flags = 0;
-    std::vector<uint32_t> bm1, anchors;
+    int32_t gram = 0, stride = 0, log1 = 0, log3 = 0, logA = 0, filter_flags = 0;
+    std::vector<uint32_t> bm1, bm3, anchors;
 };
 
 } // namespace
@@ -398,6 +398,7 @@ static void build_filter(acb_trie *t, Flat &f) {
     const double Kb = std::max(1, f.K - 1);
     FilterChoice best;
     int best_pair = 0;
+    double best_pass = 0;
     std::vector<Gram16> best_grams;
     std::vector<uint64_t> scratch;
     auto pass_rate = [](double lambda) {                 /* blocked Bloom, k = 2: P(both bits of a foreign gram are set) */
@@ -429,12 +430,17 @@ static void build_filter(acb_trie *t, Flat &f) {
             for (int pair = 0; pair <= 1; pair++) {
                 if (pair && !(L == 1 && s == 1 && g == 4)) continue;
                 if (forced_mode >= 0 && pair != forced_mode) continue;
-                const double pass1 = p_true + (1 - p_true) * pass_rate((pair ? 2.0 : 1.0) * E / words);
-                const double probe = pair ? 9.0 : std::max(17.0, 5.0 + 3.0 * nw);
+                /* pair: a foreign gram must find its level-1 bit set (fill of 2E entries in half the bits) and then both
+                   of its bits in a level-2 word that is known to hold at least the entry it collided with */
+                const double fill1 = std::min(1.0, 2.0 * E / (words * 16.0));
+                const double pass1 = pair ? p_true + (1 - p_true) * fill1 * std::min(1.0, 8.0 * pass_rate(1.0 + 4.0 * E / words))
+                                          : p_true + (1 - p_true) * pass_rate(E / words);
+                const double probe = pair ? 6.0 : std::max(17.0, 5.0 + 3.0 * nw);
                 const double cost = (probe + pass1 * 120.0 + p_true * (s / L) * 40.0) / s;
                 if (cost < best.cost) {
                     best.g = g; best.s = s; best.log1 = log1; best.cost = cost;
                     best_pair = pair;
+                    best_pass = pass1 - p_true;
                 }
             }
         }
@@ -448,7 +454,7 @@ static void build_filter(acb_trie *t, Flat &f) {
     /* The bitmap: 2^log1 bits of shared memory, 2^(log1-5) words.  A gram sets two bits of ONE word (a blocked
      * Bloom filter with k = 2: the probe costs one shared-memory load, and a random gram has to find BOTH bits set).
      *   single: word = umulhi(hash1, n_words), bits acb_stage1_bit_a AND acb_stage1_bit_b (acb_hash.h);
-     *   pair  : acb_pair_place, every gram once per role. */
+     *   pair  : two levels in the two halves of the bits, acb_pair_place, every gram once per role. */
     const uint32_t n_words = 1u << (best.log1 - 5);
     f.bm1.assign((size_t)n_words, 0);
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
@@ -460,9 +466,10 @@ static void build_filter(acb_trie *t, Flat &f) {
             const uint8_t *b = gr.data();
             const uint32_t G = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
             for (int role = 0; role < 2; role++) {
-                uint32_t word, bits;
-                acb_pair_place(G, role, best.log1 - 5, &word, &bits);
-                f.bm1[word] |= bits;
+                uint32_t word1, bit1, word2, bits2;
+                acb_pair_place(G, role, best.log1, &word1, &bit1, &word2, &bits2);
+                f.bm1[word1] |= bit1;
+                f.bm1[word2] |= bits2;
             }
         } else {
             const uint64_t hw = acb_hash_bytes_wide(gr.data(), g, mul1);
@@ -567,6 +574,18 @@ static void build_filter(acb_trie *t, Flat &f) {
         a = b;
     }
     pt.lap("filter: anchor entries");
+    /* The tag bitmap: a bitmap in global memory (L2-resident) over a re-mix of the anchor tag, 64 bits per distinct tag.
+     * Only built when the shared-memory filter lets more than one per cent of foreign grams through (large or very
+     * repetitive key sets): it keeps that flood away from the candidate lists and the anchor table at the price of one
+     * L2 access per survivor. */
+    f.log3 = 0;
+    f.bm3.assign(1, 0);
+    if (best_pass > 0.01 || getenv("ACB_FORCE_TAGMAP")) {
+        int log3 = std::min(30, std::max(16, ceil_log2_u64((uint64_t)entries.size() * 64 + 1)));
+        f.log3 = log3;
+        f.bm3.assign((size_t)1 << (log3 - 5), 0);
+        for (const Entry &e : entries) set_bit(f.bm3, (e.w[0] * ACB_TAGMAP_MIX) >> (32 - log3));
+    }
     int logA = std::max(10, ceil_log2_u64((uint64_t)entries.size() * 4 + 1));     /* load factor <= 1/4 */
     if (logA > 28) logA = 28;
     while (((size_t)1 << logA) < entries.size() + entries.size() / 4 + 1) logA++;
@@ -702,7 +721,7 @@ extern "C" int acb_trie_make_automaton(acb_trie *t, int32_t *built) {
         pt.lap("goto / fail / outputs");
         if (f.n_keys > 0) build_filter(t, f);
         else {                                               /* nothing can ever match */
-            f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.logA = 10;
+            f.gram = t->letter_bytes; f.stride = t->letter_bytes; f.log1 = 13; f.logA = 10; f.log3 = 0; f.bm3.assign(1, 0);
             f.filter_flags = acb_hash_is_wide(f.gram) ? ACB_FILTER_WIDE : 0;
             f.bm1.assign((size_t)1 << (13 - 5), 0);
             f.anchors.assign(((size_t)1 << 10) * 8, 0);
@@ -745,6 +764,8 @@ extern "C" int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out) {
     out->stride = f.stride;
     out->log2_bits1 = f.log1;
     out->log2_anchor_slots = f.logA;
+    out->log2_bits3 = f.log3;
+    out->bitmap3 = f.bm3.data();
     out->bitmap1 = f.bm1.data();
     out->anchors = f.anchors.data();
     out->filter_flags = f.filter_flags;

@@ -156,6 +156,34 @@ def make(name: str, scale: float = 1.0, planted: bool = True) -> Workload:
     raise ValueError(name)
 
 
+ROW_BLOCK = 65536
+
+
+def make_rows(name: str, lo: int, hi: int, planted: bool = True) -> Workload:
+    """Rows [lo, hi) of the SHARDED form of a fixed-stride workload (C2 / C5), for multi-GPU strong scaling.
+
+    The global batch is defined block by block -- ROW_BLOCK rows each, every block its own PCG64 stream seeded by
+    (seed, block index) -- so a rank builds only the blocks its shard touches, and all ranks agree on the global batch
+    whatever the world size is.  (The bytes differ from make(name): that one draws the whole batch from one stream.)
+    Keys are make(name)'s.  planted_hay is relative to `lo`."""
+    seed, alphabet, nk, klo, khi, stride = {"C2": (1001, ALNUM, 10_000, 4, 16, 256), "C5": (1005, ALNUM, 100_000, 4, 16, 256)}[name]
+    keys = draw_keys(np.random.Generator(np.random.PCG64(seed)), alphabet, nk, klo, khi)
+    parts, ph, pe, pk = [], [], [], []
+    for b in range(lo // ROW_BLOCK, (max(hi, lo + 1) - 1) // ROW_BLOCK + 1):
+        rng = np.random.Generator(np.random.PCG64([seed, b]))
+        hay = random_haystacks(rng, alphabet, ROW_BLOCK, stride)
+        pl = plant(rng, hay, keys, np.arange(ROW_BLOCK)) if planted else None
+        r0, r1 = max(lo, b * ROW_BLOCK) - b * ROW_BLOCK, min(hi, (b + 1) * ROW_BLOCK) - b * ROW_BLOCK
+        parts.append(hay[r0:r1])
+        if pl is not None:
+            keep = (pl[0] >= r0) & (pl[0] < r1)
+            ph.append(pl[0][keep] + b * ROW_BLOCK - lo); pe.append(pl[1][keep]); pk.append(pl[2][keep])
+    hay = np.ascontiguousarray(np.concatenate(parts, axis=0)) if parts else np.empty((0, stride), dtype=np.uint8)
+    if planted:
+        return Workload(name, keys, hay, np.concatenate(ph), np.concatenate(pe), np.concatenate(pk))
+    return Workload(name, keys, hay, None, None, None)
+
+
 def build_automaton(keys: List[bytes], module=None):
     """STORE_INTS automaton, value = insertion index."""
     if module is None:

@@ -111,11 +111,13 @@ def _dp4a(G, c):
     return sum(((G >> (8 * i)) & 0xFF) * c[i] for i in range(4))
 
 
-def pair_place(G, role, log2_words):
-    """acb_pair_place (csrc/acb_hash.h): word index and the two bits of gram G (little-endian u32) in one role"""
+def pair_place(G, role, log2_bits):
+    """acb_pair_place (csrc/acb_hash.h): (word1, bit1, word2, bits2) of gram G (little-endian u32) in one role"""
     common = G if role else (G >> 8)
-    lo = (common * ((PAIR_M << 8) & M32)) & M32
-    return lo >> (32 - log2_words), (1 << (_dp4a(G, PAIR_CA) & 31)) | (1 << (_dp4a(G, PAIR_CB) & 31))
+    hc = (common * ((PAIR_M << 8) & M32)) & M32
+    idx = hc >> (33 - log2_bits)
+    word2 = (1 << (log2_bits - 6)) + (hc >> (38 - log2_bits))
+    return idx >> 5, 1 << (31 - (idx & 31)), word2, (1 << (_dp4a(G, PAIR_CA) & 31)) | (1 << (_dp4a(G, PAIR_CB) & 31))
 
 
 def _u32_at(buf, q):
@@ -132,8 +134,8 @@ def _passes_bitmap(f, buf, q):
     if flags & FILTER_PAIR:
         assert g == 4 and f["stride"] == 1 and f["letter_bytes"] == 1
         role = q & 1                                   # x even: role 0 of pair (x, x+1); x odd: role 1 of (x-1, x)
-        word, bits = pair_place(_u32_at(buf, q), role, l1 - 5)
-        return (int(f["bitmap1"][word]) & bits) == bits
+        word1, bit1, word2, bits2 = pair_place(_u32_at(buf, q), role, l1)
+        return bool(int(f["bitmap1"][word1]) & bit1) and (int(f["bitmap1"][word2]) & bits2) == bits2
     mul1 = multipliers(g, 1)
     hw = hash_bytes_wide(buf, q, g, mul1)
     h1 = hw & M32
@@ -162,6 +164,9 @@ def emul_filter(f, buf, offsets=None, stride_bytes=0):
         if q + g > total:
             continue
         tag = hash_bytes(buf, q, g, mul2) | 1
+        l3 = f["log2_bits3"]
+        if l3 and not _bit(f["bitmap3"], ((tag * 0x9E3779B1) & M32) >> (32 - l3)):
+            continue
         slot = tag >> (32 - lA)
         bounds = None
         while True:

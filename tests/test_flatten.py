@@ -105,8 +105,10 @@ def test_filter_choice_for_baseline_configs():
     f = synth.build_automaton(w.keys).flat()
     assert (f["gram_bytes"], f["stride"], f["log2_bits1"]) == (4, 1, 20)
     assert f["filter_flags"] == emul.FILTER_PAIR          # 10 k grams of 4 bytes at stride 1: one word per two positions
-    fill = np.unpackbits(f["bitmap1"].view(np.uint8)).mean()
-    assert 0.03 < fill < 0.045              # two bits per gram and role (blocked Bloom, k = 2) in 2^20 bits
+    bits = np.unpackbits(f["bitmap1"].view(np.uint8))
+    half = bits.size // 2
+    assert 0.03 < bits[:half].mean() < 0.04     # level 1: one bit per gram and role in 2^19 bits
+    assert 0.06 < bits[half:].mean() < 0.08     # level 2: two bits per gram and role (blocked Bloom, k = 2) in 2^19 bits
     a = f["anchors"]
     used = a[a[:, 0] != 0]
     assert 9000 < len(used) <= 10000 and len(used) * 4 <= len(a)         # one anchor per distinct 4-byte prefix
@@ -152,3 +154,26 @@ def test_pickle_round_trip_keeps_keys_values_and_kind():
         T.add_word(conv("abc"))
         D = pickle.loads(pickle.dumps(T))
         assert D.kind == ac.TRIE and D.get(conv("abc")) == 3 and D.store == ac.STORE_LENGTH
+
+
+def test_tag_bitmap_is_built_for_dense_key_sets_and_never_loses_a_match(monkeypatch):
+    """key sets the shared-memory filter cannot hold (100k keys of C5; forced here for a small set too) get the tag
+    bitmap in global memory; the emulated filter path with it still equals the oracle"""
+    w5 = synth.make("C5", scale=0.1)
+    f5 = synth.build_automaton(w5.keys).flat()
+    assert f5["log2_bits3"] >= 16 and f5["bitmap3"].size == 1 << (f5["log2_bits3"] - 5)
+    monkeypatch.setenv("ACB_FORCE_TAGMAP", "1")
+    rng = np.random.Generator(np.random.PCG64(5))
+    keys = synth.draw_keys(rng, synth.ALNUM, 300, 3, 9)
+    A = synth.build_automaton(keys)
+    f = A.flat()
+    assert f["log2_bits3"] >= 16
+    hay = synth.random_haystacks(rng, synth.ALNUM, 40, 200)
+    synth.plant(rng, hay, keys, np.arange(40))
+    O = oracle.OracleAutomaton()
+    for i, k in enumerate(keys):
+        O.add_word(k, i)
+    O.make_automaton()
+    off = np.arange(41, dtype=np.int64) * 200
+    want = [tuple(r) for r in O.scan_batch_bytes(hay.reshape(-1), off).tolist()]
+    assert emul.emul_filter(f, hay.reshape(-1), None, 200) == want

@@ -57,3 +57,43 @@ def test_unicode_narrow_and_wide_paths_agree_with_oracle(monkeypatch):
     B.add_word("中文", 1)
     B.make_automaton()
     assert list(B.iter("latin only")) == [] and list(B.iter("x中文")) == [(2, 1)]
+
+
+def test_one_automaton_is_safe_to_share_between_threads(monkeypatch):
+    """the native calls drop the GIL, so searches and key-set changes on one Automaton are serialised by a
+    per-object lock (the reference holds the GIL for a whole search).  Hammer one automaton from several threads."""
+    import threading
+    import emul
+    import pyahocorasick_b200 as pkg
+    emul.install(monkeypatch)
+    A = pkg.flavour("bytes").Automaton()
+    for w in (b"he", b"her", b"hers", b"she"):
+        A.add_word(w, w)
+    A.make_automaton()
+    want = list(A.iter(b"_sherhershe_"))
+    errors = []
+
+    def search():
+        try:
+            for _ in range(30):
+                assert list(A.iter(b"_sherhershe_")) == want
+        except Exception as e:                                   # pragma: no cover
+            errors.append(e)
+
+    def churn():
+        try:
+            for i in range(30):
+                B = A                                            # same object: add and remove a key, rebuild
+                B.add_word(b"zz%d" % i, b"zz")
+                B.make_automaton()
+                B.remove_word(b"zz%d" % i)
+                B.make_automaton()
+        except Exception as e:                                   # pragma: no cover
+            errors.append(e)
+
+    ts = [threading.Thread(target=search) for _ in range(3)] + [threading.Thread(target=churn)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not [e for e in errors if not isinstance(e, (ValueError, AttributeError))], errors   # stale iterators may raise, nothing may crash

@@ -7,6 +7,6 @@ if grep -q "passed" gpurun_out/r2b_pytest.log && ! grep -q "failed" gpurun_out/r
 fi
 tools/gpu_variants.sh "$@" > gpurun_out/r2b_variants.log 2>&1
 if [ -n "$NCU" ]; then
-  timeout 600 ncu --set full --import-source on --clock-control none -k regex:acb_stream -s 3 -c 1 -f -o gpurun_out/r2b_stream python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2b_ncu.log 2>&1
+  timeout 600 ncu --set full --import-source on --clock-control none -k regex:acb_stream -s 3 -c 1 -f -o gpurun_out/r2b_stream python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-latency > gpurun_out/r2b_ncu.log 2>&1
 fi
 tail -6 gpurun_out/r2b_pytest.log; cat gpurun_out/r2b_variants.log

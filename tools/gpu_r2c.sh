@@ -6,7 +6,7 @@ i=0
 for spec in $NCU_SPECS; do   # name:ENV=..:variant
   name=$(echo $spec | cut -d: -f1); envs=$(echo $spec | cut -d: -f2); var=$(echo $spec | cut -d: -f3)
   lib=$PWD/pyahocorasick_b200/_native/libacb200${name:+_$name}.so
-  env $envs ACB_LIB=$lib timeout 600 ncu --set full --import-source on --clock-control none -k regex:acb_stream -s 3 -c 1 -f -o gpurun_out/r2c_$i python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --variant $var > gpurun_out/r2c_ncu_$i.log 2>&1
+  env $envs ACB_LIB=$lib timeout 600 ncu --set full --import-source on --clock-control none -k regex:acb_stream -s 3 -c 1 -f -o gpurun_out/r2c_$i python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-latency --variant $var > gpurun_out/r2c_ncu_$i.log 2>&1
   i=$((i+1))
 done
 cat gpurun_out/r2c_variants.log
