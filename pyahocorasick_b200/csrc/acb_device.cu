@@ -59,10 +59,10 @@
 namespace {
 
 #ifndef ACB_CONSUMERS
-#define ACB_CONSUMERS 24
+#define ACB_CONSUMERS 31
 #endif
 #ifndef ACB_STAGES
-#define ACB_STAGES 3
+#define ACB_STAGES 2
 #endif
 #ifndef ACB_LANE_BYTES
 #define ACB_LANE_BYTES 32
@@ -860,7 +860,9 @@ struct acb_table {
     long long dev_bytes = 0;
     std::vector<int32_t> key_len;            /* host copy, for sorting records */
     /* workspace of acb_scan_host */
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_copy = nullptr, s_sort = nullptr;      /* compute; H2D of the pipelined host scan; sort + D2H */
+    std::vector<cudaEvent_t> ev_h2d, ev_scan;                               /* per chunk of the pipelined host scan */
+    unsigned long long *h_counts = nullptr; size_t h_counts_cap = 0;        /* pinned: record count after every chunk */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint8_t *w_hay = nullptr; size_t w_hay_cap = 0;
     long long *w_off = nullptr; size_t w_off_cap = 0;
@@ -902,6 +904,11 @@ extern "C" void acb_table_free(acb_table *tb) {
     if (tb->ev0) cudaEventDestroy(tb->ev0);
     if (tb->ev1) cudaEventDestroy(tb->ev1);
     if (tb->stream) cudaStreamDestroy(tb->stream);
+    if (tb->s_copy) cudaStreamDestroy(tb->s_copy);
+    if (tb->s_sort) cudaStreamDestroy(tb->s_sort);
+    for (cudaEvent_t e : tb->ev_h2d) cudaEventDestroy(e);
+    for (cudaEvent_t e : tb->ev_scan) cudaEventDestroy(e);
+    if (tb->h_counts) cudaFreeHost(tb->h_counts);
     delete tb;
 }
 
@@ -1022,6 +1029,44 @@ static int launch_stream(const ScanParams &p, int flags, int stride, int grid, c
     return ACB_EINVAL;
 }
 
+/* the stream kernel over the start positions [begin, end) of the flat buffer (begin a multiple of 32), one launch per
+ * <= 2 GiB segment.  Text after `end` is read as far as a key can reach, never interpreted as a start position. */
+static int launch_filter_range(acb_table *tb, ScanParams &p, long long begin, long long end, cudaStream_t s) {
+    if (!tb->d_cand) {                                      /* room for every byte of a slice per consumer warp: never overflows */
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_cand), (size_t)tb->sm_count * kConsumers * kWarpCand * sizeof(uint2)));
+        tb->dev_bytes += (long long)tb->sm_count * kConsumers * kWarpCand * (long long)sizeof(uint2);
+    }
+    p.cand = tb->d_cand;
+    for (long long seg = begin; seg < end; seg += kSegBytes) {
+        p.seg_begin = seg;
+        p.seg_end = std::min<long long>(seg + kSegBytes, end);
+        p.n_tiles = (unsigned int)((p.seg_end - p.seg_begin + kTileBytes - 1) / kTileBytes);
+        const int grid = (int)std::min<long long>(tb->sm_count, p.n_tiles);
+        int rc = launch_stream(p, tb->filter_flags, tb->stride, grid, s);
+        if (rc != ACB_OK) return rc;
+    }
+    return ACB_OK;
+}
+
+static void fill_params(const acb_table *tb, ScanParams &p, const uint8_t *d_hay, int64_t total_bytes, const int64_t *d_offsets,
+                        int64_t n_hay, int64_t stride_bytes, acb_match *d_out, int64_t cap, int64_t *d_count) {
+    memset(&p, 0, sizeof(p));
+    p.hay = d_hay; p.total = total_bytes; p.offsets = reinterpret_cast<const long long *>(d_offsets);
+    p.n_hay = n_hay; p.stride_bytes = stride_bytes;
+    p.cls = tb->d_cls; p.gto = tb->d_goto; p.fail = tb->d_fail; p.letter_fail = tb->d_lfail; p.key_of = tb->d_keyof;
+    p.out_ptr = tb->d_outptr; p.out_idx = tb->d_outidx; p.key_len = tb->d_keylen;
+    p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.max_key_bytes = tb->max_key_bytes;
+    p.bm1 = tb->d_bm1; p.bm3 = tb->d_bm3; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
+    p.log1 = tb->log1; p.log3 = tb->log3; p.logA = tb->logA;
+    memcpy(p.mul1, tb->mul1, sizeof(p.mul1));
+    memcpy(p.mul2, tb->mul2, sizeof(p.mul2));
+    p.out = d_out; p.cap = cap; p.count = reinterpret_cast<unsigned long long *>(d_count);
+    p.work_ctr = tb->d_work;
+    p.stride_shift = -1;
+    if (!d_offsets) for (int b = 0; b < 62; b++) if ((1LL << b) == stride_bytes) p.stride_shift = b;
+    p.letter_shift = tb->L == 4 ? 2 : (tb->L == 2 ? 1 : 0);
+}
+
 extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t total_bytes,
                                const int64_t *d_offsets, int64_t n_hay, int64_t stride_bytes,
                                acb_match *d_out, int64_t cap, int64_t *d_count, void *stream, int algo) {
@@ -1040,21 +1085,7 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 
     ScanParams p;
-    memset(&p, 0, sizeof(p));
-    p.hay = d_hay; p.total = total_bytes; p.offsets = reinterpret_cast<const long long *>(d_offsets);
-    p.n_hay = n_hay; p.stride_bytes = stride_bytes;
-    p.cls = tb->d_cls; p.gto = tb->d_goto; p.fail = tb->d_fail; p.letter_fail = tb->d_lfail; p.key_of = tb->d_keyof;
-    p.out_ptr = tb->d_outptr; p.out_idx = tb->d_outidx; p.key_len = tb->d_keylen;
-    p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.max_key_bytes = tb->max_key_bytes;
-    p.bm1 = tb->d_bm1; p.bm3 = tb->d_bm3; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
-    p.log1 = tb->log1; p.log3 = tb->log3; p.logA = tb->logA;
-    memcpy(p.mul1, tb->mul1, sizeof(p.mul1));
-    memcpy(p.mul2, tb->mul2, sizeof(p.mul2));
-    p.out = d_out; p.cap = cap; p.count = reinterpret_cast<unsigned long long *>(d_count);
-    p.work_ctr = tb->d_work;
-    p.stride_shift = -1;
-    if (!d_offsets) for (int b = 0; b < 62; b++) if ((1LL << b) == stride_bytes) p.stride_shift = b;
-    p.letter_shift = tb->L == 4 ? 2 : (tb->L == 2 ? 1 : 0);
+    fill_params(tb, p, d_hay, total_bytes, d_offsets, n_hay, stride_bytes, d_out, cap, d_count);
 
     if (algo == ACB_ALGO_AUTO) algo = ACB_ALGO_FILTER;
     if (tb->n_keys == 0) return ACB_OK;                     /* empty key set: nothing can match */
@@ -1064,19 +1095,8 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
         CUDA_TRY(cudaEventRecord(tb->ev0, s));
     }
     if (algo == ACB_ALGO_FILTER) {
-        if (!tb->d_cand) {                                  /* room for every lane of every slice of a phase: never overflows */
-            CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_cand), (size_t)tb->sm_count * kConsumers * kWarpCand * sizeof(uint2)));
-            tb->dev_bytes += (long long)tb->sm_count * kConsumers * kWarpCand * (long long)sizeof(uint2);
-        }
-        p.cand = tb->d_cand;
-        for (long long seg = 0; seg < total_bytes; seg += kSegBytes) {
-            p.seg_begin = seg;
-            p.seg_end = std::min<long long>(seg + kSegBytes, total_bytes);
-            p.n_tiles = (unsigned int)((p.seg_end - p.seg_begin + kTileBytes - 1) / kTileBytes);
-            const int grid = (int)std::min<long long>(tb->sm_count, p.n_tiles);
-            int rc = launch_stream(p, tb->filter_flags, tb->stride, grid, s);
-            if (rc != ACB_OK) return rc;
-        }
+        int rc = launch_filter_range(tb, p, 0, total_bytes, s);
+        if (rc != ACB_OK) return rc;
     } else if (algo == ACB_ALGO_DFA) {
         long long spans = (total_bytes + kDfaSpan - 1) / kDfaSpan;
         long long grid = (spans + kDfaThreads - 1) / kDfaThreads;
@@ -1217,6 +1237,123 @@ static int ensure(T **buf, size_t *cap, size_t need) {
     return ACB_OK;
 }
 
+/* pinned staging for n records (from the pool some caller has given back, or new) */
+static int ensure_pinned_out(acb_table *tb, size_t n) {
+    if (tb->h_out_cap >= n && tb->h_out) return ACB_OK;
+    if (tb->h_out) { acb_release_records(tb->h_out, (int64_t)tb->h_out_cap); tb->h_out = nullptr; tb->h_out_cap = 0; }
+    size_t got = 0;
+    if (acb_match *p = pool_take(n, &got)) {
+        tb->h_out = p;
+        tb->h_out_cap = got;
+    } else {
+        size_t want = n + n / 4 + 1024;
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&tb->h_out), want * sizeof(acb_match)));
+        tb->h_out_cap = want;
+    }
+    return ACB_OK;
+}
+
+/* The host-buffer scan as a pipeline over 32 MiB chunks of the batch: chunk c is copied to the device on the copy
+ * stream while the stream kernel scans the start positions the copy of chunk c-1 completed, and its records are sorted
+ * and copied back (the other PCIe direction) while later chunks are still going up.  A start position belongs to the
+ * chunk in which a key of maximal length starting there ends, so a launch never needs bytes that are not on the device
+ * yet.  Chunks are in position order and each is sorted by itself; only the one haystack a chunk boundary cuts can have
+ * its records out of order across the cut, and those two adjacent runs are merged on the host at the end. */
+static int scan_host_pipelined(acb_table *tb, const uint8_t *hay, int64_t total, const int64_t *offsets, int64_t n_hay,
+                               int64_t stride_bytes, int64_t cap, int64_t *n_found, int sort) {
+    constexpr long long kChunk = 32LL << 20;
+    const int nch = (int)((total + kChunk - 1) / kChunk);
+    if (!tb->s_copy) CUDA_TRY(cudaStreamCreateWithFlags(&tb->s_copy, cudaStreamNonBlocking));
+    if (!tb->s_sort) CUDA_TRY(cudaStreamCreateWithFlags(&tb->s_sort, cudaStreamNonBlocking));
+    while ((int)tb->ev_h2d.size() < nch) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        tb->ev_h2d.push_back(a);
+        tb->ev_scan.push_back(b);
+    }
+    if (tb->h_counts_cap < (size_t)nch) {
+        if (tb->h_counts) cudaFreeHost(tb->h_counts);
+        tb->h_counts = nullptr;
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&tb->h_counts), (size_t)(nch + 16) * sizeof(unsigned long long)));
+        tb->h_counts_cap = (size_t)nch + 16;
+    }
+    int rc;
+    if ((rc = ensure_pinned_out(tb, (size_t)cap))) return rc;
+    const int64_t max_letters = (offsets ? total : stride_bytes) / tb->L;
+    if (sort) {                                                 /* scratch of the per-chunk sorts, once, before anything is in flight */
+        size_t temp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                        (const acb_match *)nullptr, (acb_match *)nullptr, (int)std::min<int64_t>(cap, 0x7fffffff), 0, 64, tb->s_sort);
+        const size_t need = (size_t)cap * (2 * sizeof(unsigned long long) + sizeof(acb_match)) + temp + 1024;
+        if (tb->sort_cap < need) {
+            if (tb->d_sort) { cudaFree(tb->d_sort); tb->d_sort = nullptr; tb->sort_cap = 0; }
+            CUDA_TRY(cudaMalloc(&tb->d_sort, need));
+            tb->sort_cap = need;
+        }
+    }
+    cudaStream_t sc = tb->stream, sh = tb->s_copy, ss = tb->s_sort;
+    const int64_t *d_off = nullptr;
+    if (offsets) {
+        CUDA_TRY(cudaMemcpyAsync(tb->w_off, offsets, (size_t)(n_hay + 1) * sizeof(long long), cudaMemcpyHostToDevice, sh));
+        d_off = reinterpret_cast<const int64_t *>(tb->w_off);
+    }
+    for (int c = 0; c < nch; c++) {
+        const long long b0 = (long long)c * kChunk, b1 = std::min<long long>(b0 + kChunk, total);
+        CUDA_TRY(cudaMemcpyAsync(tb->w_hay + b0, hay + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, sh));
+        CUDA_TRY(cudaEventRecord(tb->ev_h2d[c], sh));
+    }
+    CUDA_TRY(cudaMemsetAsync(tb->w_count, 0, sizeof(unsigned long long), sc));
+    ScanParams p;
+    fill_params(tb, p, tb->w_hay, total, d_off, n_hay, stride_bytes, tb->w_out, cap, reinterpret_cast<int64_t *>(tb->w_count));
+    const long long reach = ((long long)tb->max_key_bytes + 31) & ~31LL;      /* a start position this far before a cut waits for the next chunk */
+    auto cut = [&](int c) { return c <= 0 ? 0LL : (c >= nch ? (long long)total : std::max<long long>(0, (long long)c * kChunk - reach)); };
+    for (int c = 0; c < nch; c++) {
+        CUDA_TRY(cudaStreamWaitEvent(sc, tb->ev_h2d[c], 0));
+        if (cut(c + 1) > cut(c) && (rc = launch_filter_range(tb, p, cut(c), cut(c + 1), sc))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(tb->h_counts + c, tb->w_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sc));
+        CUDA_TRY(cudaEventRecord(tb->ev_scan[c], sc));
+    }
+    unsigned long long prev = 0;
+    for (int c = 0; c < nch; c++) {
+        CUDA_TRY(cudaEventSynchronize(tb->ev_scan[c]));
+        const unsigned long long cur = std::min<unsigned long long>(tb->h_counts[c], (unsigned long long)cap);
+        if (cur > prev) {
+            if (sort && (rc = acb_sort_matches_device(tb, tb->w_out + prev, (int64_t)(cur - prev), n_hay, max_letters, ss))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(tb->h_out + prev, tb->w_out + prev, (size_t)(cur - prev) * sizeof(acb_match), cudaMemcpyDeviceToHost, ss));
+        }
+        prev = cur;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ss));
+    const unsigned long long n = tb->h_counts[nch - 1];
+    *n_found = (int64_t)n;
+    if (n > (unsigned long long)cap) {
+        acb_set_error("match buffer too small: %llu matches, capacity %lld", n, (long long)cap);
+        return ACB_EOVERFLOW;
+    }
+    if (sort) {                                                 /* the haystack every cut goes through: merge its two runs */
+        const int32_t *kl = tb->key_len.data();
+        auto less = [kl](const acb_match &a, const acb_match &b) {
+            if (a.hay_id != b.hay_id) return a.hay_id < b.hay_id;
+            if (a.end_index != b.end_index) return a.end_index < b.end_index;
+            return kl[a.key_id] > kl[b.key_id];
+        };
+        for (int c = 0; c + 1 < nch; c++) {
+            const unsigned long long mid = tb->h_counts[c];
+            if (mid == 0 || mid >= n) continue;
+            const int32_t h = tb->h_out[mid - 1].hay_id;          /* the last haystack of chunk c; the cut lies in it or right after it */
+            if (tb->h_out[mid].hay_id != h) continue;
+            unsigned long long lo = mid, hi = mid;
+            while (lo > 0 && tb->h_out[lo - 1].hay_id == h) lo--;
+            const unsigned long long stop = std::min<unsigned long long>(n, tb->h_counts[c + 1]);   /* this cut's run ends with chunk c+1; a longer haystack meets the next cut */
+            while (hi < stop && tb->h_out[hi].hay_id == h) hi++;
+            std::inplace_merge(tb->h_out + lo, tb->h_out + mid, tb->h_out + hi, less);
+        }
+    }
+    tb->h_out_n = n;
+    return ACB_OK;
+}
+
 extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_bytes,
                              const int64_t *offsets, int64_t n_hay, int64_t stride_bytes,
                              acb_match *out, int64_t cap, int64_t *n_found, int algo, int sort) {
@@ -1233,6 +1370,17 @@ extern "C" int acb_scan_host(acb_table *tb, const uint8_t *hay, int64_t total_by
     if (offsets && (rc = ensure(&tb->w_off, &tb->w_off_cap, (size_t)n_hay + 1))) return rc;
     if ((rc = ensure(&tb->w_out, &tb->w_out_cap, (size_t)std::max<int64_t>(cap, 1)))) return rc;
     cudaStream_t s = tb->stream;
+    {   /* large batches on the fast path: copy, scan, sort and copy-back as a pipeline over chunks */
+        const int64_t max_letters = (offsets ? total_bytes : stride_bytes) / tb->L;
+        const int bits = bits_for((unsigned long long)std::max<int64_t>(n_hay - 1, 1)) + bits_for((unsigned long long)std::max<int64_t>(max_letters, 1)) +
+                         bits_for((unsigned long long)(tb->max_key_bytes / tb->L));
+        static const bool no_pipe = getenv("ACB_NO_PIPELINE") != nullptr;
+        if (!no_pipe && (algo == ACB_ALGO_AUTO || algo == ACB_ALGO_FILTER) && tb->n_keys > 0 && total_bytes >= (48LL << 20) && bits <= 64 && cap < 0x7fffffffLL) {
+            rc = scan_host_pipelined(tb, hay, total_bytes, offsets, n_hay, stride_bytes, cap, n_found, sort);
+            if (rc == ACB_OK && out && *n_found) memcpy(out, tb->h_out, (size_t)*n_found * sizeof(acb_match));
+            return rc;
+        }
+    }
     static const bool trace = getenv("ACB_TRACE") != nullptr;          /* phase timing to stderr (adds syncs) */
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = trace ? now() : 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;

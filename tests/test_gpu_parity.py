@@ -195,29 +195,76 @@ def _check_full(w, A, sample=20000):
     return len(got)
 
 
+def _check_reference_rows(w, A, rows):
+    """the compiled reference (oracle/_ref) over the listed haystacks: identical records in identical order"""
+    if not oracle.ref_available("bytes"):
+        pytest.skip("oracle/_ref did not travel")
+    ref = oracle.ref_module("bytes")
+    R = ref.Automaton(ref.STORE_INTS)
+    for i, k in enumerate(w.keys):
+        R.add_word(k, i)
+    R.make_automaton()
+    sub = np.ascontiguousarray(w.haystacks[rows])
+    want = [(h, e, v) for h in range(len(rows)) for e, v in R.iter(sub[h].tobytes())]
+    m = A.find_all_batch(sub)
+    assert list(zip(m.hay_id.tolist(), m.end_index.tolist(), m.values())) == want
+
+
 def test_full_size_c2_properties():
     w = synth.make("C2", scale=1.0)
     A = synth.build_automaton(w.keys)
     n = _check_full(w, A)
     assert n >= w.n_hay
+    _check_reference_rows(w, A, np.arange(0, w.n_hay, 10))           # every 10th haystack: 100 k, BASELINE.md section 2
 
 
-def test_c3_dna_properties():
-    w = synth.make("C3", scale=0.1)          # 1 M reads x 150 B, 100 k 20-mers
+def test_full_size_c3_dna_properties():
+    w = synth.make("C3", scale=1.0)          # BASELINE config 3 at its stated size: 10 M reads x 150 B, 100 k 20-mers
     A = synth.build_automaton(w.keys)
     _check_full(w, A)
+    _check_reference_rows(w, A, np.arange(0, w.n_hay, 100))          # 100 k reads through the reference
 
 
-def test_c4_long_haystacks_properties():
-    w = synth.make("C4", scale=0.25)         # 64 x 4 MiB, keys straddling every 16 KiB work unit
+def test_full_size_c4_long_haystacks_properties():
+    w = synth.make("C4", scale=1.0)          # BASELINE config 4 at its stated size: 64 x 16 MiB, a key across every 16 KiB
     A = synth.build_automaton(w.keys)
+    # more straddlers, one across every boundary the kernel or the host pipeline has: 512-byte slices of a tile, the
+    # tiles themselves, and the 32 MiB chunks of the pipelined host scan (minus the reach of the longest key)
+    flat = w.haystacks.reshape(-1)
+    rng = np.random.Generator(np.random.PCG64(44))
+    size = w.haystacks.shape[1]
+    extra_h, extra_e, extra_k = [], [], []
+    cuts = list(range(31 * 1024, flat.size, 31 * 1024 * 37)) + [c * (32 << 20) - d for c in range(1, flat.size >> 25) for d in (0, 32)]
+    for b in cuts:
+        if b <= 64 or b >= flat.size - 64 or b % size < 32 or b % size > size - 32:
+            continue
+        kid = int(rng.integers(0, len(w.keys)))
+        k = np.frombuffer(w.keys[kid], dtype=np.uint8)
+        st = b - int(rng.integers(1, len(k)))
+        flat[st:st + len(k)] = k
+        extra_h.append(st // size); extra_e.append(st % size + len(k) - 1); extra_k.append(kid)
+    klen = np.fromiter((len(k) for k in w.keys), dtype=np.int64, count=len(w.keys))
+    ph = np.concatenate([w.planted_hay, np.asarray(extra_h, dtype=np.int64)])
+    pe = np.concatenate([w.planted_end, np.asarray(extra_e, dtype=np.int64)])
+    pk = np.concatenate([w.planted_key, np.asarray(extra_k, dtype=np.int64)])
+    starts = ph * size + pe - klen[pk] + 1                              # keep only plants whose bytes survived the new ones
+    ok = np.ones(len(ph), dtype=bool)
+    for L in np.unique(klen[pk]).tolist():
+        sel = np.nonzero(klen[pk] == L)[0]
+        got = flat[starts[sel][:, None] + np.arange(L)[None, :]]
+        want = np.stack([np.frombuffer(w.keys[int(k)], dtype=np.uint8) for k in pk[sel]])
+        ok[sel] = (got == want).all(axis=1)
+    w.planted_hay, w.planted_end, w.planted_key = ph[ok], pe[ok], pk[ok]
+    assert len(extra_h) > 40
     _check_full(w, A)
+    _check_reference_rows(w, A, np.array([1]))                        # one whole 16 MiB haystack through the reference
 
 
 def test_c5_100k_keys_properties():
-    w = synth.make("C5", scale=0.125)        # 1 M x 256 B (one GPU's shard), 100 k keys
+    w = synth.make("C5", scale=0.125)        # 1 M x 256 B (one GPU's shard of BASELINE config 5), 100 k keys
     A = synth.build_automaton(w.keys)
     _check_full(w, A)
+    _check_reference_rows(w, A, np.arange(0, w.n_hay, 10))
 
 
 def test_dense_matches_grow_the_buffers():
