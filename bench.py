@@ -218,6 +218,20 @@ def run_reference_arm(args):
     step_rows = rows_all.shape[0]
     kind = "reference" if oracle.ref_available("bytes") else "port"
     min_s = 0.25
+    # one thread alone, before the pool exists: what a core can do when nothing else runs
+    alone = None
+    if kind == "reference":
+        R1 = _ref_build(w.keys)
+        hs1 = [r.tobytes() for r in rows_all[:4096]]
+        t0 = time.perf_counter()
+        done = 0
+        while time.perf_counter() - t0 < 1.0:
+            for h in hs1:
+                for _ in R1.iter(h):
+                    pass
+            done += 1
+        alone = done * sum(len(h) for h in hs1) / (time.perf_counter() - t0)
+        del R1, hs1
     rates, matches, single = [], 0, None
     t_region = time.perf_counter()
     if kind == "reference" and cores > 1:
@@ -249,7 +263,9 @@ def run_reference_arm(args):
         "best_step_gbs": float(np.max(rates)) / 1e9, "worst_step_gbs": float(np.min(rates)) / 1e9, "timed_region_s": t_region,
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": used, "kind": kind,
                          "sample": f"{step_rows} x {rows_all.shape[1]} B, one process per core looping Automaton.iter(), sum of the workers' rates",
-                         "single_thread_gbs": (single / 1e9) if single else None},
+                         "best_worker_under_load_gbs": (single / 1e9) if single else None,
+                         "single_thread_alone_gbs": (alone / 1e9) if alone else None,
+                         "effective_cores": (val * 1e9 / alone) if alone else None},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -357,6 +373,30 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # strong scaling: the same global batch on ONE GPU (rank 0, untimed extra, the other ranks wait), so that the line
+    # carries its own single-GPU reference point for this configuration (the N=1 bench line is C2, a different workload)
+    single = None
+    if strong:
+        if rank == 0:
+            wf = synth.make_rows(cfg, 0, n_global, planted=(args.variant == "planted"))
+            d_full = torch.from_numpy(wf.haystacks).cuda()
+            nf, tot_f = wf.haystacks.shape[0], int(wf.haystacks.size)
+            capf = max(4 * nf, 1 << 20)
+            d_out_f = torch.empty((capf, 3), dtype=torch.int32, device="cuda")
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(3 + 5):
+                if i == 3:
+                    e0.record()
+                d_cnt.zero_()
+                N.check(L.acb_scan_device(tb, d_full.data_ptr(), tot_f, None, nf, stride, d_out_f.data_ptr(), capf, d_cnt.data_ptr(), stream, algo))
+            e1.record()
+            torch.cuda.synchronize()
+            single = {"gbs": tot_f / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e9, "ms_per_step": e0.elapsed_time(e1) / 5,
+                      "matches": int(d_cnt.item()), "what": "the whole global batch on one GPU (rank 0, before the timed region)"}
+            del d_full, d_out_f, wf
+            torch.cuda.empty_cache()
+        barrier()
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -503,7 +543,9 @@ def main():
                        "algo": args.algo,
                        "parallelism": (f"one batch sharded x{world} (strong scaling)" if strong else f"one batch per rank x{world} (weak scaling)") + ", NCCL all-gather of match counts on a side stream" if world > 1 else "single GPU"},
             "matches_per_s": total_matches / (ms_step * 1e-3), "matches_per_step": total_matches,
-            "results_verified": {"per_rank_planted_lower_bound": True, "gathered_counts_consistent": world > 1},
+            "results_verified": {"per_rank_planted_lower_bound": True, "gathered_counts_consistent": world > 1,
+                                 "sum_equals_single_gpu_count": (single["matches"] == total_matches) if single else None},
+            "strong_scaling": ({"single_gpu": single, "efficiency_vs_single_gpu": value / (world * single["gbs"])} if single else None),
             "parity_checked": parity_checked, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "latency": latency,
             "gpu_launches": int(launches), "clocks": clk,
         }

@@ -74,3 +74,18 @@ def test_shard_bounds_cover_everything():
             b = [shard_bounds(n, w, r) for r in range(w)]
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_strong_scaling_shards_tile_the_global_batch():
+    """bench.py --gpus N (strong scaling): every rank builds only its rows of the one global batch; the shards of any
+    world size concatenate to the same batch, plants included"""
+    from pyahocorasick_b200 import distributed as D
+    from pyahocorasick_b200 import synth
+    n = 70_000 * 2
+    full = synth.make_rows("C2", 0, n)
+    for world in (2, 3):
+        parts = [synth.make_rows("C2", *D.shard_bounds(n, world, r)) for r in range(world)]
+        assert np.array_equal(np.concatenate([p.haystacks for p in parts]), full.haystacks)
+        lo = [D.shard_bounds(n, world, r)[0] for r in range(world)]
+        assert np.array_equal(np.concatenate([p.planted_hay + lo[r] for r, p in enumerate(parts)]), full.planted_hay)
+        assert sum(len(p.planted_hay) for p in parts) == n
