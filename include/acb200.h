@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ACB_ABI_VERSION 3
+#define ACB_ABI_VERSION 4
 
 enum {
     ACB_OK        =  0,
@@ -132,6 +132,19 @@ typedef struct acb_flat_view {
 #define ACB_FILTER_PAIR 2   /* pair placement (gram 4, stride 1, 1-byte letters): two adjacent positions share one word   */
 
 int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out);
+
+/* ---- the flat-table cache (last clause) ---------------------------------------
+ * A loaded or unpickled automaton of kind AHOCORASICK is searchable at once in the reference, whose files carry the
+ * failure links (src/custompickle/load/module_automaton_load.c:85-93, src/Automaton.c:139-145).  Here the links are a
+ * function of the key set, so what is cached is everything make_automaton derives from it: acb_trie_flat_save writes
+ * the flattened tables (goto / fail / outputs / filter / anchors) with a content hash of the key set as
+ * make_automaton numbers it; acb_trie_flat_load installs them on a trie that holds the same keys (kind TRIE) and turns
+ * it into an automaton without the BFS, the flatten and the filter construction.  ACB_EINVAL when the blob does not
+ * belong to this key set or library version: call acb_trie_make_automaton then.
+ * acb_trie_flat_save: call with out == NULL first, *need is always set. */
+uint64_t acb_trie_content_hash(const acb_trie *t);
+int acb_trie_flat_save(const acb_trie *t, uint8_t *out, int64_t cap, int64_t *need);
+int acb_trie_flat_load(acb_trie *t, const uint8_t *buf, int64_t len);
 
 /* ---- the reference's on-disk node records -------------------------------
  * Both of the reference's serialisations write one record per trie node, in pre-order (`trie_traverse`,

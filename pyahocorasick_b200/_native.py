@@ -10,7 +10,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ACB_LIB") or os.path.join(_PKG, "_native", "libacb200.so")   # ACB_LIB: experimental builds
 
-ABI_VERSION = 3            # ACB_ABI_VERSION of include/acb200.h this binding was written against
+ABI_VERSION = 4            # ACB_ABI_VERSION of include/acb200.h this binding was written against
 ACB_OK, ACB_ENOMEM, ACB_EINVAL, ACB_ESTATE, ACB_ECUDA, ACB_EOVERFLOW, ACB_ERANGE = 0, -1, -2, -3, -4, -5, -6
 ALGO_AUTO, ALGO_FILTER, ALGO_DFA, ALGO_LONG = 0, 1, 2, 3
 ALGOS = {"auto": ALGO_AUTO, "filter": ALGO_FILTER, "dfa": ALGO_DFA, "long": ALGO_LONG}
@@ -69,6 +69,9 @@ def lib() -> ctypes.CDLL:
         "acb_trie_nodes": (i64, [vp]),
         "acb_trie_links": (i64, [vp]),
         "acb_trie_host_bytes": (i64, [vp]),
+        "acb_trie_content_hash": (ctypes.c_uint64, [vp]),
+        "acb_trie_flat_save": (ctypes.c_int, [vp, vp, i64, ctypes.POINTER(i64)]),
+        "acb_trie_flat_load": (ctypes.c_int, [vp, vp, i64]),
         "acb_trie_flat_view": (ctypes.c_int, [vp, ctypes.POINTER(FlatView)]),
         "acb_trie_export_nodes": (ctypes.c_int, [vp, ctypes.c_int, vp, i64, vp, i64, pi64, pi64, vp, vp, i64]),
         "acb_trie_import_nodes": (ctypes.c_int, [vp, vp, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, i64, pi64, pi64,
@@ -105,6 +108,7 @@ EXPORTED_SYMBOLS = [
     "acb_trie_new", "acb_trie_free", "acb_trie_clear", "acb_trie_add_word", "acb_trie_remove_word",
     "acb_trie_find", "acb_trie_longest_prefix", "acb_trie_make_automaton", "acb_trie_kind",
     "acb_trie_count", "acb_trie_longest_word", "acb_trie_nodes", "acb_trie_links", "acb_trie_host_bytes", "acb_trie_flat_view",
+    "acb_trie_content_hash", "acb_trie_flat_save", "acb_trie_flat_load",
     "acb_trie_export_nodes", "acb_trie_import_nodes", "acb_node_records_span",
     "acb_device_count", "acb_table_upload", "acb_table_free", "acb_table_device_bytes",
     "acb_scan_device", "acb_scan_host", "acb_copy_records", "acb_take_records", "acb_release_records", "acb_sort_matches_device", "acb_launch_count", "acb_set_kernel_timing",

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import functools
+import os
 import operator
 import pickle
 import threading
@@ -497,6 +498,43 @@ class Automaton:
         self._version += 1                                 # :640
         self._drop_table()
         return None
+
+    @_locked
+    def _make_automaton_cached(self, cache_path: Optional[str] = None):
+        """make_automaton() for an automaton that comes out of a file or a pickle: the reference's
+        files carry the failure links, so a loaded automaton is searchable at once; here everything make_automaton
+        derives from the key set (goto / fail / outputs / gram filter / anchors) is cached in a file keyed by a content
+        hash of the key set -- `cache_path` (load() passes `<file>.acb200`), else `$ACB200_CACHE_DIR/<hash>.acb200`
+        when that variable names a directory.  A hit installs the tables without BFS, flatten or filter construction;
+        a miss builds them and writes the cache (best effort: an unwritable place is not an error)."""
+        if self.kind != TRIE:
+            return self.make_automaton()
+        if cache_path is None:
+            d = os.environ.get("ACB200_CACHE_DIR")
+            if d and os.path.isdir(d):
+                cache_path = os.path.join(d, "%016x.acb200" % int(self._lib.acb_trie_content_hash(self._trie)))
+        if cache_path is not None and os.path.exists(cache_path):
+            try:
+                blob = np.fromfile(cache_path, dtype=np.uint8)
+                if self._lib.acb_trie_flat_load(self._trie, N.ptr(blob), int(blob.size)) == N.ACB_OK:
+                    self._version += 1
+                    self._drop_table()
+                    return None
+            except OSError:
+                pass
+        r = self.make_automaton()
+        if cache_path is not None and self.kind == AHOCORASICK:
+            try:
+                need = ctypes.c_int64(0)
+                N.check(self._lib.acb_trie_flat_save(self._trie, None, 0, ctypes.byref(need)))
+                blob = np.empty(need.value, dtype=np.uint8)
+                N.check(self._lib.acb_trie_flat_save(self._trie, N.ptr(blob), need.value, ctypes.byref(need)))
+                tmp = cache_path + ".tmp%d" % os.getpid()
+                blob.tofile(tmp)
+                os.replace(tmp, cache_path)
+            except (OSError, N.NativeError):
+                pass
+        return r
 
     @_locked
     def _drop_table(self):

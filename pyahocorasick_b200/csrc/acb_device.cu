@@ -841,6 +841,13 @@ __global__ void __launch_bounds__(kDfaThreads) acb_long_kernel(const __grid_cons
     }
 }
 
+__global__ void acb_flag_goto_kernel(int32_t *gto, const int32_t *key_of, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int32_t v = gto[i];
+        if (v >= 0 && key_of[v] >= 0) gto[i] = v | kTermBit;
+    }
+}
+
 } // namespace
 
 /* ------------------------------------------------------------- the table */
@@ -936,25 +943,24 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         tb->min_key_bytes = f.min_key_bytes; tb->max_key_bytes = f.max_key_bytes;
         acb_hash_multipliers(tb->gram, 1, tb->mul1);
         acb_hash_multipliers(tb->gram, 2, tb->mul2);
-        /* goto entries get a flag bit when the child ends a key, saving a key_of lookup per step */
-        std::vector<int32_t> flagged;
         try {
             tb->key_len.assign(f.key_len, f.key_len + f.n_keys);
-            flagged.resize((size_t)f.n_classes * f.n_states);
         } catch (const std::exception &) {                   /* nothing may cross the C ABI */
             acb_set_error("out of host memory while staging the tables");
             rc = ACB_ENOMEM;
             break;
         }
-        for (size_t i = 0; i < flagged.size(); i++) {
-            int32_t v = f.goto_cm[i];
-            flagged[i] = (v >= 0 && f.key_of[v] >= 0) ? (v | kTermBit) : v;
-        }
         if ((rc = upload(&tb->d_cls, f.byte_class, 256, tb->dev_bytes))) break;
-        if ((rc = upload(&tb->d_goto, flagged.data(), flagged.size(), tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_goto, f.goto_cm, (size_t)f.n_classes * f.n_states, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_fail, f.fail, (size_t)f.n_states, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_lfail, f.letter_fail, (size_t)f.n_states, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_keyof, f.key_of, (size_t)f.n_states, tb->dev_bytes))) break;
+        {   /* goto entries get a flag bit when the child ends a key, saving a key_of lookup per step: set on the device,
+               in place (no second host copy of a table that can be gigabytes) */
+            const size_t n = (size_t)f.n_classes * f.n_states;
+            acb_flag_goto_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 1u << 20), 256>>>(tb->d_goto, tb->d_keyof, n);
+            if (cudaDeviceSynchronize() != cudaSuccess) { acb_set_error("flagging the goto table failed: %s", cudaGetErrorString(cudaGetLastError())); rc = ACB_ECUDA; break; }
+        }
         if ((rc = upload(&tb->d_outptr, f.out_ptr, (size_t)f.n_states + 1, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_outidx, f.out_idx, (size_t)f.out_ptr[f.n_states], tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_keylen, f.key_len, (size_t)f.n_keys, tb->dev_bytes))) break;

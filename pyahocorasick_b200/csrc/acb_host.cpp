@@ -772,6 +772,136 @@ extern "C" int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out) {
     return ACB_OK;
 }
 
+/* ------------------------------------------------ the flat-table cache (include/acb200.h) */
+namespace {
+
+constexpr char kFlatMagic[8] = {'A', 'C', 'B', 'F', 'L', 'A', 'T', '2'};
+
+/* FNV-1a over the live trie in the order make_automaton numbers it (BFS, children in insertion order): parent's BFS id,
+ * edge byte, key id of every node.  Two tries with the same hash flatten to the same tables. */
+static uint64_t content_hash(const acb_trie *t) {
+    uint64_t h = 1469598103934665603ULL;
+    auto mix = [&h](uint64_t v) { for (int i = 0; i < 8; i++) { h ^= (v >> (8 * i)) & 0xff; h *= 1099511628211ULL; } };
+    mix((uint64_t)t->letter_bytes);
+    if (t->nodes.empty() || t->live_nodes <= 0) return h;
+    std::vector<int32_t> order;
+    order.reserve((size_t)t->live_nodes);
+    order.push_back(0);
+    std::vector<int32_t> parent_new;
+    parent_new.reserve((size_t)t->live_nodes);
+    parent_new.push_back(-1);
+    for (size_t i = 0; i < order.size(); i++) {
+        const Node &nd = t->nodes[order[i]];
+        mix(((uint64_t)(uint32_t)parent_new[i] << 32) | ((uint64_t)nd.byte << 24) | (uint64_t)((uint32_t)nd.key_id & 0xffffffu));
+        mix((uint64_t)(uint32_t)nd.key_id);
+        for (int32_t c = nd.first_child; c >= 0; c = t->nodes[c].next_sibling)
+            if (t->nodes[c].live_below > 0) { order.push_back(c); parent_new.push_back((int32_t)i); }
+    }
+    return h;
+}
+
+template <typename T>
+static void put_vec(std::vector<uint8_t> &out, const std::vector<T> &v) {
+    const uint64_t n = v.size();
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(&n);
+    out.insert(out.end(), p, p + 8);
+    const uint8_t *d = reinterpret_cast<const uint8_t *>(v.data());
+    out.insert(out.end(), d, d + n * sizeof(T));
+    while (out.size() % 8) out.push_back(0);
+}
+
+template <typename T>
+static bool get_vec(const uint8_t *buf, int64_t len, int64_t &pos, std::vector<T> &v, uint64_t max_items) {
+    if (pos + 8 > len) return false;
+    uint64_t n;
+    memcpy(&n, buf + pos, 8);
+    pos += 8;
+    if (n > max_items || (int64_t)(n * sizeof(T)) > len - pos) return false;
+    v.resize((size_t)n);
+    if (n) memcpy(v.data(), buf + pos, (size_t)n * sizeof(T));
+    pos += (int64_t)(n * sizeof(T));
+    pos = (pos + 7) & ~(int64_t)7;
+    return pos <= len + 7;
+}
+
+struct FlatHeader {
+    char magic[8];
+    uint64_t hash;
+    int32_t abi, letter_bytes, S, K, n_keys, min_key_bytes, max_key_bytes, gram, stride, log1, log3, logA, filter_flags, pad;
+    uint8_t byte_class[256];
+};
+
+} // namespace
+
+extern "C" uint64_t acb_trie_content_hash(const acb_trie *t) {
+    if (!t) return 0;
+    try { return content_hash(t); } catch (const std::exception &) { return 0; }
+}
+
+extern "C" int acb_trie_flat_save(const acb_trie *t, uint8_t *out, int64_t cap, int64_t *need) {
+    if (!t || !need) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    if (t->kind != ACB_AHOCORASICK || !t->flat.valid) { acb_set_error("not an Aho-Corasick automaton yet"); return ACB_ESTATE; }
+    try {
+        const Flat &f = t->flat;
+        std::vector<uint8_t> b;
+        FlatHeader h;
+        memset(&h, 0, sizeof(h));
+        memcpy(h.magic, kFlatMagic, 8);
+        h.hash = content_hash(t);
+        h.abi = ACB_ABI_VERSION; h.letter_bytes = t->letter_bytes; h.S = f.S; h.K = f.K; h.n_keys = f.n_keys;
+        h.min_key_bytes = f.min_key_bytes; h.max_key_bytes = f.max_key_bytes; h.gram = f.gram; h.stride = f.stride;
+        h.log1 = f.log1; h.log3 = f.log3; h.logA = f.logA; h.filter_flags = f.filter_flags;
+        memcpy(h.byte_class, f.byte_class, 256);
+        b.insert(b.end(), reinterpret_cast<uint8_t *>(&h), reinterpret_cast<uint8_t *>(&h) + sizeof(h));
+        put_vec(b, f.goto_cm); put_vec(b, f.fail); put_vec(b, f.letter_fail); put_vec(b, f.key_of); put_vec(b, f.out_ptr);
+        put_vec(b, f.out_idx); put_vec(b, f.key_len); put_vec(b, f.bm1); put_vec(b, f.bm3); put_vec(b, f.anchors);
+        *need = (int64_t)b.size();
+        if (out && cap >= (int64_t)b.size()) memcpy(out, b.data(), b.size());
+        return ACB_OK;
+    } catch (const std::exception &) {
+        acb_set_error("out of memory while serialising the flat tables");
+        return ACB_ENOMEM;
+    }
+}
+
+extern "C" int acb_trie_flat_load(acb_trie *t, const uint8_t *buf, int64_t len) {
+    if (!t || !buf || len < (int64_t)sizeof(FlatHeader)) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    if (t->kind != ACB_TRIE) { acb_set_error("flat tables can only be installed on a trie that has keys and is not built"); return ACB_ESTATE; }
+    try {
+        FlatHeader h;
+        memcpy(&h, buf, sizeof(h));
+        if (memcmp(h.magic, kFlatMagic, 8) != 0 || h.abi != ACB_ABI_VERSION || h.letter_bytes != t->letter_bytes ||
+            (int64_t)h.S != t->live_nodes || h.hash != content_hash(t)) {
+            acb_set_error("flat-table cache does not belong to this key set (or to this library version)");
+            return ACB_EINVAL;
+        }
+        Flat f;
+        f.S = h.S; f.K = h.K; f.n_keys = h.n_keys; f.min_key_bytes = h.min_key_bytes; f.max_key_bytes = h.max_key_bytes;
+        f.gram = h.gram; f.stride = h.stride; f.log1 = h.log1; f.log3 = h.log3; f.logA = h.logA; f.filter_flags = h.filter_flags;
+        memcpy(f.byte_class, h.byte_class, 256);
+        int64_t pos = (int64_t)sizeof(FlatHeader);
+        const uint64_t big = (uint64_t)1 << 34;
+        bool ok = get_vec(buf, len, pos, f.goto_cm, big) && get_vec(buf, len, pos, f.fail, big) && get_vec(buf, len, pos, f.letter_fail, big) &&
+                  get_vec(buf, len, pos, f.key_of, big) && get_vec(buf, len, pos, f.out_ptr, big) && get_vec(buf, len, pos, f.out_idx, big) &&
+                  get_vec(buf, len, pos, f.key_len, big) && get_vec(buf, len, pos, f.bm1, big) && get_vec(buf, len, pos, f.bm3, big) &&
+                  get_vec(buf, len, pos, f.anchors, big);
+        ok = ok && f.S > 0 && f.K > 0 && f.K <= 256 && f.goto_cm.size() == (size_t)f.K * f.S && f.fail.size() == (size_t)f.S &&
+             f.letter_fail.size() == (size_t)f.S && f.key_of.size() == (size_t)f.S && f.out_ptr.size() == (size_t)f.S + 1 &&
+             f.key_len.size() == (size_t)f.n_keys && f.log1 >= 13 && f.log1 <= 20 && f.bm1.size() == ((size_t)1 << (f.log1 - 5)) &&
+             f.bm3.size() == (f.log3 ? ((size_t)1 << (f.log3 - 5)) : (size_t)1) && f.logA >= 10 && f.logA <= 28 &&
+             f.anchors.size() == ((size_t)8 << f.logA) && !f.out_ptr.empty() && f.out_idx.size() == (size_t)f.out_ptr.back();
+        if (!ok) { acb_set_error("flat-table cache is truncated or inconsistent"); return ACB_EINVAL; }
+        f.valid = true;
+        t->flat = std::move(f);
+        t->kind = ACB_AHOCORASICK;
+        return ACB_OK;
+    } catch (const std::exception &) {
+        t->flat = Flat();
+        acb_set_error("out of memory while restoring the flat tables");
+        return ACB_ENOMEM;
+    }
+}
+
 /* ------------------------------------------------ the reference's node records (include/acb200.h) */
 namespace {
 

@@ -24,7 +24,7 @@ import numpy as np
 from . import _native as N
 
 EMPTY, TRIE, AHOCORASICK = 0, 1, 2
-STORE_LENGTH, STORE_INTS, STORE_ANY = 10, 20, 30
+STORE_INTS, STORE_LENGTH, STORE_ANY = 10, 20, 30
 KEY_STRING, KEY_SEQUENCE = 100, 200
 
 MAGICK = b"pyahocorasick002"                     # src/custompickle/custompickle.c:5-8
@@ -127,9 +127,9 @@ def _int_values(vals: np.ndarray) -> list:
     return vals.astype(np.int32).tolist()        # int64 -> int32 keeps the low 32 bits, sign included
 
 
-def _finish(A, kind: int, count: int, longest: int):
+def _finish(A, kind: int, count: int, longest: int, cache_path=None):
     if kind == AHOCORASICK:
-        A.make_automaton()
+        A._make_automaton_cached(cache_path)         # the flat-table cache: a second load of the same keys skips the build
     # counters as written in the file; they equal what entering the keys produced unless the writer had
     # removed words (longest_word never shrinks, src/Automaton.c:285-286)
     A._version = 0
@@ -250,5 +250,5 @@ def load(cls, *args):
         A._values = [deserializer(data[base + o:base + o + s]) for o, s in zip(offs, sizes)]
     else:
         A._values = _int_values(vals)
-    _finish(A, kind, count, longest)
+    _finish(A, kind, count, longest, cache_path=path + ".acb200")
     return A

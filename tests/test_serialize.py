@@ -235,3 +235,88 @@ def test_argument_rules_and_malformed_input(tmp_path):
         mod.Automaton([bytes(loop)], *args[1:])
     with pytest.raises(IndexError):
         mod.Automaton(args[0], *args[1:6], [])                     # values list too short
+
+
+# ------------------------------------------------------------------ the flat-table cache (last clause)
+def _flat_equal(a, b):
+    return all(np.array_equal(a[k], b[k]) if isinstance(a[k], np.ndarray) else a[k] == b[k] for k in a)
+
+
+def test_flat_table_cache_round_trip_and_rejections(tmp_path, monkeypatch):
+    """a second load of the same file installs the cached tables instead of rebuilding them; a cache that belongs to
+    another key set, another library version or is damaged is refused and the automaton is built the long way"""
+    import ctypes
+    from pyahocorasick_b200 import _native as N
+    from pyahocorasick_b200 import synth
+    mod = pkg.flavour("bytes")
+    keys = synth.draw_keys(np.random.Generator(np.random.PCG64(9)), synth.ALNUM, 3000, 4, 12)
+    A = mod.Automaton(mod.STORE_INTS)
+    for i, k in enumerate(keys):
+        A.add_word(k, i)
+    A.make_automaton()
+    path = str(tmp_path / "a.save")
+    A.save(path)
+    assert not os.path.exists(path + ".acb200")
+    B = mod.load(path, pickle.loads)                                  # miss: builds, writes the cache
+    assert os.path.exists(path + ".acb200")
+    calls = []
+    real = mod.Automaton.make_automaton
+    monkeypatch.setattr(mod.Automaton, "make_automaton", lambda self: (calls.append(1), real(self))[1])
+    C = mod.load(path, pickle.loads)                                  # hit: make_automaton is never called
+    assert calls == [] and C.kind == pkg.AHOCORASICK
+    assert _flat_equal(B.flat(), C.flat()) and sorted(C.items()) == sorted(B.items())
+    # the same cache offered to a different key set: refused by the content hash, built the long way
+    D = mod.Automaton(mod.STORE_INTS)
+    for i, k in enumerate(keys[:-1]):
+        D.add_word(k, i)
+    D._make_automaton_cached(path + ".acb200")
+    assert calls == [1] and D.kind == pkg.AHOCORASICK
+    # damaged cache files: truncated, flipped magic -> rebuilt (and the cache rewritten)
+    blob = open(path + ".acb200", "rb").read()
+    for bad in (blob[:len(blob) // 2], b"X" + blob[1:], blob[:600]):
+        open(path + ".acb200", "wb").write(bad)
+        calls.clear()
+        E = mod.load(path, pickle.loads)
+        assert calls == [1] and _flat_equal(E.flat(), B.flat())
+    # the C entry points by themselves
+    L = N.lib()
+    need = ctypes.c_int64(0)
+    T = mod.Automaton(mod.STORE_INTS)
+    T.add_word(b"abc", 0)
+    assert L.acb_trie_flat_save(T._trie, None, 0, ctypes.byref(need)) == N.ACB_ESTATE     # not built yet
+    assert L.acb_trie_content_hash(T._trie) != L.acb_trie_content_hash(B._trie)
+
+
+def test_unpickling_uses_the_cache_directory(tmp_path, monkeypatch):
+    mod = pkg.flavour("unicode")
+    A = mod.Automaton()
+    for w in GOLD["words"]:
+        A.add_word(w, w.upper())
+    A.make_automaton()
+    blob = pickle.dumps(A)
+    monkeypatch.setenv("ACB200_CACHE_DIR", str(tmp_path))
+    B = pickle.loads(blob)
+    assert len(list(tmp_path.glob("*.acb200"))) == 1
+    calls = []
+    real = mod.Automaton.make_automaton
+    monkeypatch.setattr(mod.Automaton, "make_automaton", lambda self: (calls.append(1), real(self))[1])
+    C = pickle.loads(blob)
+    assert calls == [] and C.kind == pkg.AHOCORASICK and _flat_equal(B.flat(), C.flat())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(len(GOLD["scenarios"])))
+def test_loaded_automata_search_on_the_gpu(idx, tmp_path):
+    """every automaton the reference serialised, read back (twice: the second load comes from the flat-table cache)
+    and searched on the real kernels"""
+    sc = GOLD["scenarios"][idx]
+    if not sc["built"]:
+        pytest.skip("not an automaton")
+    mod = pkg.flavour(sc["flavour"])
+    p = tmp_path / "ref.save"
+    p.write_bytes(base64.b64decode(sc["save_file"]))
+    hay = _conv(sc["flavour"], GOLD["hay"])
+    for _ in range(2):
+        B = mod.load(str(p), pickle.loads)
+        assert [[e, json.dumps(v)] for e, v in B.iter(hay)] == sc["iter"]
+    assert os.path.exists(str(p) + ".acb200")
