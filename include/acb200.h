@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ACB_ABI_VERSION 4
+#define ACB_ABI_VERSION 5
 
 enum {
     ACB_OK        =  0,
@@ -120,16 +120,18 @@ typedef struct acb_flat_view {
     int32_t        log2_bits1;    /* n: the gram bitmap has 2^n bits (shared memory on the device), 2^(n-5) words */
     int32_t        log2_anchor_slots; /* anchor table has 2^n slots of 8 uint32 (32 B)        */
     int32_t        log2_bits3;    /* tag bitmap (global memory) has 2^k bits; 0 = not built    */
-    const uint32_t *bitmap1;      /* a gram sets two bits of one word: single placement word = umulhi(hash1, 2^(n-5)),
-                                     pair placement acb_pair_place (csrc/acb_hash.h)          */
+    const uint32_t *bitmap1;      /* single placement: a gram sets two bits of one word, word = umulhi(hash1, 2^(n-5));
+                                     pair placement: acb_pair_place / acb_pair_place2 (csrc/acb_hash.h), 2^(n-5) + 2^(k-5) words */
     const uint32_t *bitmap3;      /* 1<<(k-5) words: bit = (hash2|1) * 0x9E3779B1 >> (32-k); only for key sets the shared-memory filter cannot hold */
     const uint32_t *anchors;      /* slot: tag(hash2|1, 0=empty), key_id(-1=MULTI), j|len<<8|last<<16, 20 bytes */
     int32_t        filter_flags;  /* ACB_FILTER_* : how the bitmap places a gram (csrc/acb_hash.h) */
+    int32_t        log2_bits2;    /* PAIR placement: level 2 (2^k bits, keyed by the anchor tag) follows level 1 in bitmap1; else 0 */
 } acb_flat_view;
 
 /* filter_flags */
 #define ACB_FILTER_WIDE 1   /* single placement, g % 4 == 0: the first bit comes from the high half of the 64-bit hash sum */
-#define ACB_FILTER_PAIR 2   /* pair placement (gram 4, stride 1, 1-byte letters): two adjacent positions share one word   */
+#define ACB_FILTER_PAIR 2   /* pair placement (gram 4, stride 1, 1-byte letters): two adjacent positions share one word,
+                               one bit per (role, remaining byte); level 2 keyed by the anchor tag behind it                */
 
 int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out);
 

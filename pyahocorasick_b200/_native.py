@@ -10,7 +10,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ACB_LIB") or os.path.join(_PKG, "_native", "libacb200.so")   # ACB_LIB: experimental builds
 
-ABI_VERSION = 4            # ACB_ABI_VERSION of include/acb200.h this binding was written against
+ABI_VERSION = 5            # ACB_ABI_VERSION of include/acb200.h this binding was written against
 ACB_OK, ACB_ENOMEM, ACB_EINVAL, ACB_ESTATE, ACB_ECUDA, ACB_EOVERFLOW, ACB_ERANGE = 0, -1, -2, -3, -4, -5, -6
 ALGO_AUTO, ALGO_FILTER, ALGO_DFA, ALGO_LONG = 0, 1, 2, 3
 ALGOS = {"auto": ALGO_AUTO, "filter": ALGO_FILTER, "dfa": ALGO_DFA, "long": ALGO_LONG}
@@ -31,7 +31,7 @@ class FlatView(ctypes.Structure):
         ("log2_bits1", ctypes.c_int32), ("log2_anchor_slots", ctypes.c_int32), ("log2_bits3", ctypes.c_int32),
         ("bitmap1", ctypes.POINTER(ctypes.c_uint32)), ("bitmap3", ctypes.POINTER(ctypes.c_uint32)),
         ("anchors", ctypes.POINTER(ctypes.c_uint32)),
-        ("filter_flags", ctypes.c_int32),
+        ("filter_flags", ctypes.c_int32), ("log2_bits2", ctypes.c_int32),
     ]
 
 

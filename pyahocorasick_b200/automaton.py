@@ -637,7 +637,8 @@ class Automaton:
             gram_bytes=fv.gram_bytes, stride=fv.stride, log2_bits1=fv.log2_bits1,
             log2_anchor_slots=fv.log2_anchor_slots, filter_flags=fv.filter_flags, log2_bits3=fv.log2_bits3,
             bitmap3=arr(fv.bitmap3, (1 << (fv.log2_bits3 - 5)) if fv.log2_bits3 else 1, np.uint32),
-            bitmap1=arr(fv.bitmap1, 1 << (fv.log2_bits1 - 5), np.uint32),
+            log2_bits2=fv.log2_bits2,
+            bitmap1=arr(fv.bitmap1, (1 << (fv.log2_bits1 - 5)) + ((1 << (fv.log2_bits2 - 5)) if fv.log2_bits2 else 0), np.uint32),
             anchors=arr(fv.anchors, 8 << fv.log2_anchor_slots, np.uint32).reshape(-1, 8))
 
     # ------------------------------------------------------------------ GPU scan plumbing

@@ -62,7 +62,7 @@ namespace {
 #define ACB_CONSUMERS 31
 #endif
 #ifndef ACB_STAGES
-#define ACB_STAGES 2
+#define ACB_STAGES 3
 #endif
 #ifndef ACB_LANE_BYTES
 #define ACB_LANE_BYTES 32
@@ -75,7 +75,13 @@ constexpr int kFThreads     = (kConsumers + 1) * 32;  /* + the producer warp    
 constexpr int kLaneBytes    = ACB_LANE_BYTES;         /* text bytes per lane and iteration             */
 constexpr int kLaneWords    = kLaneBytes / 4;
 constexpr int kSliceBytes   = 32 * kLaneBytes;        /* one warp iteration                            */
-constexpr int kTileBytes    = kConsumers * kSliceBytes;
+#ifndef ACB_TILE_SLICES
+#define ACB_TILE_SLICES 20
+#endif
+constexpr int kTileSlices   = ACB_TILE_SLICES;        /* slices per tile (= arrivals on a stage's empty barrier).  Slices are handed out in order,
+                                                         one per warp at a time, so the fills in use span at most kConsumers / kTileSlices + 2
+                                                         consecutive ones: less than 2 * kStages, and no barrier phase can alias */
+constexpr int kTileBytes    = kTileSlices * kSliceBytes;
 constexpr int kLook         = 16;                     /* bytes copied past a tile (gram look-ahead)    */
 constexpr int kStageBytes   = (kTileBytes + kLook + 127) / 128 * 128;   /* tile + look-ahead, stages stay 128 B aligned */
 constexpr int kStages       = ACB_STAGES;
@@ -83,6 +89,7 @@ constexpr int kClaimDepth   = 8;                      /* tile claims in flight p
 constexpr int kWarpCand     = kSliceBytes + 32;       /* candidate entries per consumer warp: a warp resolves them as soon as it
                                                          has 32, and one slice adds at most kSliceBytes (one per byte) */
 constexpr int kStageCap     = 64;                     /* match records staged per consumer warp (smem) */
+static_assert((kConsumers + kTileSlices - 1) / kTileSlices + 2 < 2 * ACB_STAGES, "ring too shallow for the slice hand-out");
 static_assert(kFThreads <= 1024 && kTileBytes % 16 == 0 && kLaneBytes == 32 && kStageCap * 12 / 2 >= 8 * 32, "stream kernel shape");
 constexpr uint32_t kFull    = 0xffffffffu;
 constexpr uint32_t kNoTile  = 0xffffffffu;
@@ -93,7 +100,7 @@ constexpr long long kSegBytes = 1LL << 31;            /* candidates are uint32 o
 constexpr int kDfaSpan      = 64;                     /* bytes per lane in the DFA kernel              */
 constexpr int kDfaThreads   = 256;
 
-enum { kModeNarrow = 0, kModeWide = 1, kModePair = 2 };   /* how a gram is placed in the bitmap (acb_hash.h) */
+enum { kModeNarrow = 0, kModeWide = 1 };                  /* how a SINGLE gram is placed in the bitmap (acb_hash.h); PAIR has its own kernel */
 
 std::atomic<long long> g_launches{0};
 thread_local float g_last_ms = 0.f;
@@ -121,6 +128,7 @@ struct ScanParams {
     const uint32_t *bm3;           /* tag bitmap in global memory, 2^log3 bits; log3 == 0: not built */
     const uint4 *anchors;          /* 2 x uint4 per slot */
     int32_t log1, log3, logA;
+    int32_t log2b;                 /* PAIR: level 2 (behind level 1 in bm1) has 2^log2b bits */
     uint32_t mul1[ACB_MAX_WINDOWS];
     uint32_t mul2[ACB_MAX_WINDOWS];
     acb_match *out;
@@ -262,6 +270,19 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ uint2 lds64(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("{ .reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h; }" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t saddr, uint32_t v) {
+    asm volatile("{ .reg .u16 h; cvt.u16.u32 h, %1; st.shared.u16 [%0], h; }" :: "r"(saddr), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
@@ -350,11 +371,10 @@ __device__ __forceinline__ void resolve_chain(const ScanParams &p, const WarpSta
 /* what a consumer warp needs to probe a slice */
 struct ProbeCtx {
     uint32_t sbm;              /* shared-memory address of the bitmap */
-    uint32_t sbm2;             /* PAIR: shared-memory address of level 2 (the second half of the bits) */
     uint32_t n_words;          /* umulhi(h, n_words) = word index */
     uint32_t four;             /* == 4, opaque to the compiler so the address is one IMAD (FMA pipe, which has room) */
     uint32_t two;              /* == 2, same trick for the hit accumulator */
-    int sh_bit;                /* NARROW: h >> sh_bit supplies the first bit index (low 5 bits, wrap shift); PAIR: hc >> sh_bit = level-1 bit index, hc >> (sh_bit + 5) = word index of both levels */
+    int sh_bit;                /* NARROW: h >> sh_bit supplies the first bit index (low 5 bits, wrap shift); */
 };
 
 /* window t of the lane's text: the 4 bytes at byte offset t of W[] (little endian) */
@@ -390,30 +410,6 @@ __device__ __forceinline__ uint32_t probe_single(const ProbeCtx &c, const uint32
         acc = acc * c.two + both;
     }
     return __brev(acc) >> (32 - kProbes);
-}
-
-/* PAIR placement (acb_hash.h): positions x (even) and x+1 test two bits each in ONE word selected by the three
- * bytes their grams share -- one shared-memory load per two positions.  Bit y of the result = position y. */
-__device__ __forceinline__ uint32_t dp4a_u32(uint32_t x, uint32_t c) {
-    uint32_t d;
-    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(c), "r"(0u));
-    return d;
-}
-
-/* PAIR placement, level 1 (acb_hash.h): one bit per pair of positions, keyed by the three bytes the pair's two grams
- * share.  Per pair: the window at x+1, one multiply, the word (one shared-memory load), a left shift that brings the
- * tested bit to bit 31, and an add-with-carry pair that shifts it into the mask.  Bit j of the result = pair j. */
-template <int N>
-__device__ __forceinline__ uint32_t probe_pair_level1(const ProbeCtx &c, const uint32_t (&W)[N], uint32_t mulp) {
-    uint32_t acc = 0;
-#pragma unroll
-    for (int x = 0; x < kLaneBytes; x += 2) {
-        const uint32_t hc = window(W, x + 1) * mulp;
-        const uint32_t word = lds_bitmap((hc >> (c.sh_bit + 5)) * c.four + c.sbm);
-        const uint32_t t = __funnelshift_l(0u, word, hc >> c.sh_bit);    /* word << (index & 31): bit 31 - (index & 31) -> bit 31 */
-        asm("{ .reg .u32 t2; add.cc.u32 t2, %1, %1; addc.u32 %0, %0, %0; }" : "+r"(acc) : "r"(t));
-    }
-    return __brev(acc) >> (32 - kLaneBytes / 2);
 }
 
 /* shared-memory carve-up of the stream kernel (host and device agree through this one function) */
@@ -464,6 +460,75 @@ __device__ __forceinline__ void resolve_backlog(const ScanParams &p, uint8_t *sm
     flush_stage(p, ws, lane);
 }
 
+/* The producer warp of a streaming kernel: claims tiles from the global counter and keeps the shared-memory ring full
+ * (cp.async.bulk + mbarrier); `stages` = offset of the ring in the CTA's shared memory. */
+__device__ __forceinline__ void stream_producer(const ScanParams &p, uint8_t *smem_raw, uint32_t sbase, uint32_t stages,
+                                                uint32_t bar_full, uint32_t bar_empty, volatile uint32_t *s_tile, int lane) {
+    struct { uint32_t stages; } lay = {stages};
+        /* ---------------- producer warp.  Tiles come from one global counter.  A claim is a ~1 us round trip to L2, so
+       kClaimDepth of them are kept in flight: claim[k] serves fills k, k + kClaimDepth, ... and is re-issued as soon
+       as it has been read (one register per slot, so that reading a slot never waits for a younger atomic). */
+    const uint8_t *seg = p.hay + p.seg_begin;
+    const long long exist = p.total - p.seg_begin;                   /* bytes that exist from seg onwards */
+    unsigned int claim[kClaimDepth];
+#pragma unroll
+    for (int k = 0; k < kClaimDepth; k++) claim[k] = (lane == 0) ? atomicAdd(p.work_ctr, 1u) : 0u;
+    bool more = true;
+    for (uint32_t base = 0; more; base += kClaimDepth) {
+#pragma unroll
+        for (int k = 0; k < kClaimDepth; k++) {
+            if (!more) break;
+            const uint32_t fill = base + k;
+            const uint32_t stage = fill % kStages;
+            const unsigned int tile = __shfl_sync(kFull, claim[k], 0);
+            if (lane == 0 && tile < p.n_tiles) claim[k] = atomicAdd(p.work_ctr, 1u);
+            if (fill >= (uint32_t)kStages) mbar_wait(bar_empty + 8u * stage, ((fill / kStages) - 1u) & 1u);
+            if (tile >= p.n_tiles) {
+                /* out of work: sentinel fills end the consumers -- a consumer leaves at the first sentinel slice it is
+                   handed, so as many fills as it takes to hand every warp one (they are never released: <= kStages) */
+                constexpr uint32_t kSentinels = (kConsumers + kTileSlices - 1) / kTileSlices;
+                static_assert(kSentinels <= (uint32_t)kStages, "sentinel fills must not wrap the ring");
+                for (uint32_t k2 = 0; k2 < kSentinels; k2++) {
+                    const uint32_t f2 = fill + k2, st2 = f2 % kStages;
+                    if (k2 > 0 && f2 >= (uint32_t)kStages) mbar_wait(bar_empty + 8u * st2, ((f2 / kStages) - 1u) & 1u);
+                    if (lane == 0) { s_tile[st2] = kNoTile; mbar_arrive(bar_full + 8u * st2); }
+                }
+                more = false;
+                break;
+            }
+            const long long off = (long long)tile * kTileBytes;
+            const long long avail = exist - off;                     /* > 0 */
+            const uint32_t want = kTileBytes + kLook;
+            const uint32_t bulk = avail >= (long long)want ? want : (uint32_t)(avail & ~15LL);
+            uint8_t *dst = smem_raw + lay.stages + (size_t)stage * kStageBytes;
+            if (avail < (long long)want) {
+                /* last tile of the buffer: the bytes past the last whole 16 are copied by hand, and the rest of the
+                   slice they end in (plus look-ahead) is zero filled so that no lane reads stale shared memory */
+                const uint32_t a = (uint32_t)avail;
+                uint32_t zend = ((a + (uint32_t)kSliceBytes - 1u) & ~((uint32_t)kSliceBytes - 1u)) + kLook;
+                if (zend > want) zend = want;
+                for (uint32_t i = bulk + lane; i < zend; i += 32) dst[i] = i < a ? seg[off + i] : (uint8_t)0;
+                __syncwarp();
+            }
+            if (lane == 0) {
+                s_tile[stage] = tile;
+                if (bulk) {
+                    mbar_arrive_expect_tx(bar_full + 8u * stage, bulk);
+                    bulk_load(sbase + lay.stages + stage * (uint32_t)kStageBytes, seg + off, bulk, bar_full + 8u * stage);
+                } else {
+                    mbar_arrive(bar_full + 8u * stage);
+                }
+            }
+        }
+    }
+    {   /* every claim still in flight must have landed before this CTA reports itself done (the last CTA re-arms the counter) */
+        unsigned int sink = 0;
+#pragma unroll
+        for (int k = 0; k < kClaimDepth; k++) sink |= claim[k];
+        if (sink == 0x7fffffffu) s_tile[0] = sink;
+    }
+}
+
 /* acb_stream_kernel: persistent, one CTA per SM, warp specialised:
  *   producer  (1 warp)          claims tiles from a global counter and keeps the shared-memory ring full
  *                               (cp.async.bulk + mbarrier)
@@ -496,7 +561,7 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         if (tid == 0) {
             for (int s = 0; s < kStages; s++) {
                 mbar_init(bar_full + 8u * s, 1);                 /* the producer's arrive(.expect_tx) */
-                mbar_init(bar_empty + 8u * s, kConsumers);       /* one arrive per consumer warp */
+                mbar_init(bar_empty + 8u * s, kTileSlices);      /* one arrive per slice */
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -507,75 +572,19 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
     const uint32_t seg_len = (uint32_t)(p.seg_end - p.seg_begin);        /* <= 2^31 */
 
     if (warp == kConsumers) {
-        /* ---------------- producer warp.  Tiles come from one global counter.  A claim is a ~1 us round trip to L2, so
-           kClaimDepth of them are kept in flight: claim[k] serves fills k, k + kClaimDepth, ... and is re-issued as soon
-           as it has been read (one register per slot, so that reading a slot never waits for a younger atomic). */
-        const uint8_t *seg = p.hay + p.seg_begin;
-        const long long exist = p.total - p.seg_begin;                   /* bytes that exist from seg onwards */
-        unsigned int claim[kClaimDepth];
-#pragma unroll
-        for (int k = 0; k < kClaimDepth; k++) claim[k] = (lane == 0) ? atomicAdd(p.work_ctr, 1u) : 0u;
-        bool more = true;
-        for (uint32_t base = 0; more; base += kClaimDepth) {
-#pragma unroll
-            for (int k = 0; k < kClaimDepth; k++) {
-                if (!more) break;
-                const uint32_t fill = base + k;
-                const uint32_t stage = fill % kStages;
-                const unsigned int tile = __shfl_sync(kFull, claim[k], 0);
-                if (lane == 0 && tile < p.n_tiles) claim[k] = atomicAdd(p.work_ctr, 1u);
-                if (fill >= (uint32_t)kStages) mbar_wait(bar_empty + 8u * stage, ((fill / kStages) - 1u) & 1u);
-                if (tile >= p.n_tiles) {                                 /* out of work: one sentinel fill ends every consumer */
-                    if (lane == 0) { s_tile[stage] = kNoTile; mbar_arrive(bar_full + 8u * stage); }
-                    more = false;
-                    break;
-                }
-                const long long off = (long long)tile * kTileBytes;
-                const long long avail = exist - off;                     /* > 0 */
-                const uint32_t want = kTileBytes + kLook;
-                const uint32_t bulk = avail >= (long long)want ? want : (uint32_t)(avail & ~15LL);
-                uint8_t *dst = smem_raw + lay.stages + (size_t)stage * kStageBytes;
-                if (avail < (long long)want) {
-                    /* last tile of the buffer: the bytes past the last whole 16 are copied by hand, and the rest of the
-                       slice they end in (plus look-ahead) is zero filled so that no lane reads stale shared memory */
-                    const uint32_t a = (uint32_t)avail;
-                    uint32_t zend = ((a + (uint32_t)kSliceBytes - 1u) & ~((uint32_t)kSliceBytes - 1u)) + kLook;
-                    if (zend > want) zend = want;
-                    for (uint32_t i = bulk + lane; i < zend; i += 32) dst[i] = i < a ? seg[off + i] : (uint8_t)0;
-                    __syncwarp();
-                }
-                if (lane == 0) {
-                    s_tile[stage] = tile;
-                    if (bulk) {
-                        mbar_arrive_expect_tx(bar_full + 8u * stage, bulk);
-                        bulk_load(sbase + lay.stages + stage * (uint32_t)kStageBytes, seg + off, bulk, bar_full + 8u * stage);
-                    } else {
-                        mbar_arrive(bar_full + 8u * stage);
-                    }
-                }
-            }
-        }
-        {   /* every claim still in flight must have landed before this CTA reports itself done (the last CTA re-arms the counter) */
-            unsigned int sink = 0;
-#pragma unroll
-            for (int k = 0; k < kClaimDepth; k++) sink |= claim[k];
-            if (sink == 0x7fffffffu) s_tile[0] = sink;
-        }
+        stream_producer(p, smem_raw, sbase, lay.stages, bar_full, bar_empty, s_tile, lane);
     } else {
         /* ---------------- consumer warps: slice `warp` of every fill */
         ProbeCtx c;
         c.sbm = sbase + lay.bitmap;
-        c.sbm2 = c.sbm + (1u << (p.log1 - 4));                          /* PAIR: level 2 = the second half of the bits */
         c.n_words = 1u << (p.log1 - 5);
         c.four = 4u + (uint32_t)(p.log1 >> 8);                           /* always 4 */
         c.two = 2u + (uint32_t)(p.log1 >> 8);                            /* always 2 */
-        c.sh_bit = (MODE == kModePair) ? 33 - p.log1 : 32 - p.log1;
+        c.sh_bit = 32 - p.log1;
         const uint32_t lt_mask = (1u << lane) - 1u;
         uint32_t mul[NW];
 #pragma unroll
         for (int k = 0; k < NW; k++) mul[k] = p.mul1[k];
-        const uint32_t mulp = acb_pair_mul() + (uint32_t)(p.log1 >> 8);  /* registers, not immediates per use */
-        const uint32_t ca = ACB_PAIR_CA + (uint32_t)(p.log1 >> 8), cb = ACB_PAIR_CB + (uint32_t)(p.log1 >> 8);
         const uint32_t slice_off = (uint32_t)warp * kSliceBytes;
         uint2 *list = p.cand + ((size_t)blockIdx.x * kConsumers + warp) * kWarpCand;
         uint32_t mul2[NW];
@@ -584,7 +593,7 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         /* the match staging area is idle while the warp streams: it holds the slice's work items (lane << 5 | bit) */
         volatile uint16_t *items = reinterpret_cast<volatile uint16_t *>(smem_raw + lay.stage_rec + (size_t)warp * kStageCap * sizeof(acb_match));
         constexpr int kItemCap = kStageCap * (int)sizeof(acb_match) / 2;
-        constexpr int kPendBits = (MODE == kModePair) ? kLaneBytes / 2 : kLaneBytes / STRIDE;
+        constexpr int kPendBits = kLaneBytes / STRIDE;
         unsigned int *s_next = reinterpret_cast<unsigned int *>(smem_raw + lay.next);
         unsigned int n_cand = 0;                                         /* warp-uniform */
 
@@ -595,7 +604,7 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
             unsigned int g = 0;
             if (lane == 0) g = atomicAdd(s_next, 1u);
             g = __shfl_sync(kFull, g, 0);
-            const uint32_t fill = g / (uint32_t)kConsumers, slice_off = (g % (uint32_t)kConsumers) * (uint32_t)kSliceBytes;
+            const uint32_t fill = g / (uint32_t)kTileSlices, slice_off = (g % (uint32_t)kTileSlices) * (uint32_t)kSliceBytes;
             const uint32_t stage = fill % (uint32_t)kStages;
             mbar_wait(bar_full + 8u * stage, (fill / (uint32_t)kStages) & 1u);
             const uint32_t tile = s_tile[stage];
@@ -624,12 +633,11 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
 #ifdef ACB_EXP_NOPROBE
                 pend = (W[0] ^ W[3] ^ W[kLaneWords]) == 0x12345678u ? 1u : 0u;      /* timing experiment: the stream skeleton alone */
 #else
-                if constexpr (MODE == kModePair) pend = probe_pair_level1(c, W, mulp);
-                else pend = probe_single<NW, STRIDE, MODE == kModeWide>(c, W, mul);
+                pend = probe_single<NW, STRIDE, MODE == kModeWide>(c, W, mul);
 #endif
                 if (n_valid - slice_off < (uint32_t)kSliceBytes) {       /* last slice of the segment: probes that start past it */
                     const int v = (int)(n_valid - slice_off) - lane * kLaneBytes;
-                    const int valid = (MODE == kModePair) ? (v + 1) / 2 : (v + STRIDE - 1) / STRIDE;
+                    const int valid = (v + STRIDE - 1) / STRIDE;
                     pend = (valid <= 0) ? 0u : ((valid >= 32) ? pend : (pend & ((1u << valid) - 1u)));
                 }
 #ifdef ACB_EXP_NOSURV
@@ -660,22 +668,14 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
                         }
                         __syncwarp();
                         for (int base = 0; base < tot; base += 32) {
-                            bool ok0 = false, ok1 = false;
-                            uint32_t pos0 = 0, tag0 = 0, tag1 = 0;
+                            bool ok0 = false;
+                            uint32_t pos0 = 0, tag0 = 0;
                             if (base + lane < tot) {
                                 const uint32_t it = items[base + lane];
-                                const uint32_t t = (it >> 5) * (uint32_t)kLaneBytes + ((MODE == kModePair) ? 2u * (it & 31u) : (it & 31u) * (uint32_t)STRIDE);
+                                const uint32_t t = (it >> 5) * (uint32_t)kLaneBytes + (it & 31u) * (uint32_t)STRIDE;
                                 const uint32_t ga = slice_saddr + t, wa = ga & ~3u, sh = (ga & 3u) * 8u;
                                 pos0 = tile_off + slice_off + t;
-                                if constexpr (MODE == kModePair) {
-                                    const uint32_t lo = lds32(wa), hi = lds32(wa + 4u);
-                                    const uint32_t w0 = __funnelshift_r(lo, hi, sh), w1 = __funnelshift_r(lo, hi, sh + 8u);   /* t even: sh is 0 or 16 */
-                                    const uint32_t word = lds_bitmap((((w1 * mulp) >> (c.sh_bit + 5)) * c.four) + c.sbm2);
-                                    ok0 = (__funnelshift_r(word, 0u, dp4a_u32(w0, ca)) & __funnelshift_r(word, 0u, dp4a_u32(w0, cb)) & 1u) != 0u;
-                                    ok1 = (__funnelshift_r(word, 0u, dp4a_u32(w1, ca)) & __funnelshift_r(word, 0u, dp4a_u32(w1, cb)) & 1u) != 0u;
-                                    tag0 = (w0 * mul2[0]) | 1u;
-                                    tag1 = (w1 * mul2[0]) | 1u;
-                                } else {
+                                {
                                     uint32_t w0 = lds32(wa);
 #pragma unroll
                                     for (int k = 0; k < NW; k++) {
@@ -688,9 +688,8 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
                                 }
                             }
                             if (p.log3) {                                  /* large key sets: the tag bitmap in L2 first */
-                                const uint32_t i0 = (tag0 * ACB_TAGMAP_MIX) >> (32 - p.log3), i1 = (tag1 * ACB_TAGMAP_MIX) >> (32 - p.log3);
+                                const uint32_t i0 = (tag0 * ACB_TAGMAP_MIX) >> (32 - p.log3);
                                 if (ok0) ok0 = ((__ldg(p.bm3 + (i0 >> 5)) >> (i0 & 31u)) & 1u) != 0u;
-                                if (ok1) ok1 = ((__ldg(p.bm3 + (i1 >> 5)) >> (i1 & 31u)) & 1u) != 0u;
                             }
 #ifndef ACB_EXP_NODRAIN
                             /* append {position, hash2 of the gram = the anchor tag} to the warp's candidate list in global
@@ -698,13 +697,8 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
                             const unsigned m0 = __ballot_sync(kFull, ok0);
                             if (ok0) list[n_cand + __popc(m0 & lt_mask)] = make_uint2(pos0, tag0);
                             n_cand += __popc(m0);
-                            if constexpr (MODE == kModePair) {
-                                const unsigned m1 = __ballot_sync(kFull, ok1);
-                                if (ok1) list[n_cand + __popc(m1 & lt_mask)] = make_uint2(pos0 + 1u, tag1);
-                                n_cand += __popc(m1);
-                            }
 #else
-                            if (ok0 && ok1 && tag0 == tag1 + pos0) s_tile[0] = 2u;      /* timing experiment: candidates dropped */
+                            if (ok0 && tag0 == pos0) s_tile[0] = 2u;      /* timing experiment: candidates dropped */
 #endif
                         }
                         __syncwarp();
@@ -717,6 +711,360 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
             if (n_cand >= 32u) { resolve_backlog(p, smem_raw, n_cand); n_cand = 0; }
         }
         if (n_cand) resolve_backlog(p, smem_raw, n_cand);
+    }
+    /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        unsigned int done = atomicAdd(p.work_ctr + 1, 1u);
+        if (done == gridDim.x - 1) {
+            p.work_ctr[0] = 0u;
+            p.work_ctr[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+/* ------------------------------------------------------------ the pair kernel
+ * acb_pair_kernel: the stream kernel of the PAIR placement (gram 4, stride 1, 1-byte letters; acb_hash.h).  Same ring,
+ * same producer, same dynamic slices; what differs is everything a consumer warp does with its slice:
+ *   level 1   one shared-memory word per PAIR of positions, selected by the three bytes the pair's grams share; the
+ *             word holds one bit per (role, remaining byte), so the loop leaves a per-POSITION pass mask -- 9.5
+ *             instructions per pair, 2 % of the positions pass on random text against 10 k keys.  A lane owns two runs
+ *             of 16 bytes (16 * lane and 512 + 16 * lane of the slice): both 16-byte loads of a warp are conflict free;
+ *   items     while the stage is held: the pending positions of all lanes are pushed into a list in shared memory
+ *             (ballot rounds) and worked off 32 at a time -- the gram read back from the stage, the anchor tag
+ *             (hash 2), level 2 (shared memory, two bits keyed by the tag); survivors ({position, tag}) go to the
+ *             warp's candidate ring in SHARED memory (no global list, no round trip).  A round never takes more items
+ *             than the ring has room for, so the stage is not held across an anchor look-up unless one slice alone
+ *             overflows the ring;
+ *   resolve   after the release, as soon as the ring holds 32 entries -- one per lane: the text at the position and
+ *             the anchor slot of the tag are loaded together (L2), UNIQUE keys are compared in registers, the hits of
+ *             the warp take ONE atomicAdd on the record counter and are stored straight to the record buffer (no
+ *             staging copy); MULTI anchors (keys sharing their first four bytes) take the general path with one
+ *             atomic per record. */
+constexpr int kPairRing = 64;                                /* candidate ring entries per consumer warp */
+constexpr int kPairItems = 64;                               /* item list entries (uint16) per consumer warp */
+
+struct PairSmem {
+    uint32_t bitmap, bitmap2, stages, ring, items, bars, tiles, next, total;
+};
+__host__ __device__ inline PairSmem pair_smem(int log1, int log2b) {
+    PairSmem s;
+    uint32_t o = 0;
+    s.bitmap = o;    o += 1u << (log1 - 3);                       /* >= 1 KiB: level 2 follows without a gap, as in bm1 */
+    s.bitmap2 = o;   o += 1u << (log2b - 3);                      o = (o + 127u) & ~127u;
+    s.stages = o;    o += (uint32_t)kStages * kStageBytes;
+    s.ring = o;      o += (uint32_t)kConsumers * kPairRing * 8u;
+    s.items = o;     o += (uint32_t)kConsumers * kPairItems * 2u;
+    s.bars = o;      o += 2u * kStages * 8u;
+    s.tiles = o;     o += (uint32_t)kStages * 4u;
+    s.next = o;      o += 4u;
+    s.total = (o + 15u) & ~15u;
+    return s;
+}
+
+__device__ __forceinline__ void emit_direct(const ScanParams &p, int32_t h, int32_t e, int32_t k) {
+    const unsigned long long g = atomicAdd(p.count, 1ULL);
+    if (g < (unsigned long long)p.cap) { acb_match m; m.hay_id = h; m.end_index = e; m.key_id = k; p.out[g] = m; }
+}
+
+/* the general way through the anchor table from `slot` on (resolve_chain's loop), records emitted one by one */
+__device__ __noinline__ void pair_resolve_general(const ScanParams &p, long long q, uint32_t tag, uint32_t slot, uint4 e0, uint4 e1) {
+    const uint32_t amask = (1u << p.logA) - 1u;
+    long long h = -1, hs = 0, he = 0;
+    for (;;) {
+        if (e0.x == 0u) break;
+        if (e0.x == tag) {
+            const uint32_t kw[5] = {e0.w, e1.x, e1.y, e1.z, e1.w};
+            const int j = (int)(e0.z & 0xffu), len = (int)((e0.z >> 8) & 0xffu);
+            const int32_t kid = (int32_t)e0.y;
+            if (h < 0) find_haystack(p, q, h, hs, he);
+            const long long start = q - j;
+            if (start >= hs && start + len <= he) {
+                uint32_t ts[6];
+                load_text(p, start, ts);
+                if (text_equals(ts, start, len, kw)) {
+                    if (kid >= 0) {
+                        emit_direct(p, (int32_t)h, (int32_t)(((start + len - hs) >> p.letter_shift) - 1), kid);
+                    } else {                                           /* MULTI: exact gram, then the trie from the root */
+                        int32_t st = 0;
+                        for (long long i = start; i < he; ++i) {
+                            const int c = __ldg(p.cls + p.hay[i]);
+                            const int32_t nx = __ldg(p.gto + (long long)c * p.S + st);
+                            if (nx < 0) break;
+                            st = nx & kIdMask;
+                            if (nx & kTermBit) emit_direct(p, (int32_t)h, (int32_t)((i - hs + 1) / p.L - 1), __ldg(p.key_of + st));
+                        }
+                    }
+                }
+            }
+            if (e0.z & 0x10000u) break;
+        }
+        slot = (slot + 1) & amask;
+        e0 = __ldg(p.anchors + 2 * (size_t)slot);
+        e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
+    }
+}
+
+/* one turn of a warp's candidates (ring entries head .. head + n - 1, n <= 32, one per lane) through the anchor table.
+ * Not inlined: the streaming loop keeps its registers and its schedule, and this runs once per five slices or so. */
+__device__ __noinline__ void pair_resolve(const ScanParams &p, uint32_t sring, unsigned int head, unsigned int n) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    bool hit = false;
+    int32_t rh = 0, re = 0, rk = 0;
+    if ((unsigned)lane < n) {
+        const uint32_t amask = (1u << p.logA) - 1u;
+        const uint2 e = lds64(sring + (((head + (unsigned)lane) & (kPairRing - 1u)) << 3));
+        const long long q = p.seg_begin + (long long)e.x;
+        uint32_t tq[6];
+        load_text(p, q, tq);
+        uint32_t slot = e.y >> (32 - p.logA);
+        uint4 e0 = __ldg(p.anchors + 2 * (size_t)slot), e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
+        while (e0.x != 0u && e0.x != e.y) {                      /* a foreign tag in the way: linear probing */
+            slot = (slot + 1) & amask;
+            e0 = __ldg(p.anchors + 2 * (size_t)slot);
+            e1 = __ldg(p.anchors + 2 * (size_t)slot + 1);
+        }
+        if (e0.x != 0u) {
+            if ((int32_t)e0.y >= 0 && (e0.z & 0x100ffu) == 0x10000u) {   /* the tag's ONE entry: UNIQUE, anchored at its first byte */
+                const uint32_t kw[5] = {e0.w, e1.x, e1.y, e1.z, e1.w};
+                const int len = (int)((e0.z >> 8) & 0xffu);
+                long long h, hs, he;
+                find_haystack(p, q, h, hs, he);
+                hit = q + len <= he && text_equals(tq, q, len, kw);
+                rh = (int32_t)h;
+                re = (int32_t)(((q + len - hs) >> p.letter_shift) - 1);
+                rk = (int32_t)e0.y;
+            } else {
+                pair_resolve_general(p, q, e.y, slot, e0, e1);
+            }
+        }
+    }
+    /* the hits of the warp: ONE atomicAdd on the record counter, records stored straight to the record buffer */
+    const unsigned mh = __ballot_sync(kFull, hit);
+    if (mh) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.count, (unsigned long long)__popc(mh));
+        base = __shfl_sync(kFull, base, 0) + (unsigned long long)__popc(mh & lt_mask);
+        if (hit && base < (unsigned long long)p.cap) { acb_match m; m.hay_id = rh; m.end_index = re; m.key_id = rk; p.out[base] = m; }
+    }
+}
+
+/* level 1 of one 16-byte run (words R[0..3], look-ahead word R[4]): the pass bits of its 16 positions are shifted
+ * into acc, first position first (acb_hash.h, PAIR placement).  Per pair: the window at x+1, ONE 64-bit multiply (low
+ * half -> word index, high half -> role 1's bit), the word, and per role a left shift that brings the tested bit to
+ * bit 31 plus a one-bit funnel shift that moves it into the mask. */
+__device__ __forceinline__ uint32_t probe_pair_run(uint32_t acc, uint32_t sbm, uint32_t n_words, uint32_t four, const uint32_t (&R)[5], uint32_t mulp) {
+#pragma unroll
+    for (int x = 0; x < 16; x += 2) {
+#ifdef ACB_EXP_L1_NOWIDE
+        const uint32_t hc = window(R, x + 1) * mulp, hb = hc >> 7;
+#else
+        const unsigned long long pr = mul_wide(window(R, x + 1), mulp);
+        const uint32_t hc = (uint32_t)pr, hb = (uint32_t)(pr >> 32);
+#endif
+#ifdef ACB_EXP_L1_SHIFTIDX
+        const uint32_t waddr = (hc >> 17) * four + sbm;
+#else
+        const uint32_t waddr = __umulhi(hc, n_words) * four + sbm;
+#endif
+#ifdef ACB_EXP_L1_NOLDS
+        const uint32_t word = waddr;
+#else
+        const uint32_t word = lds_bitmap(waddr);
+#endif
+        const uint32_t ta = __funnelshift_l(0u, word, window(R, x));      /* word << (text[x] & 31): role 0's bit -> bit 31 */
+        acc = __funnelshift_l(ta, acc, 1);                                /* acc << 1 | bit 31 of ta */
+#ifndef ACB_EXP_L1_ONEROLE
+        const uint32_t tb = __funnelshift_l(0u, word, hb);                /* role 1's */
+        acc = __funnelshift_l(tb, acc, 1);
+#endif
+    }
+    return acc;
+}
+
+template <int L2B>
+__global__ void __launch_bounds__(kFThreads, 1) acb_pair_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const PairSmem lay = pair_smem(p.log1, p.log2b);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bar_full = sbase + lay.bars, bar_empty = bar_full + 8u * kStages;
+    volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem_raw + lay.tiles);
+
+    {   /* both levels of the bitmap -> shared memory with cp.async */
+        const int n16 = (1 << (p.log1 - 7)) + (1 << (p.log2b - 7));
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.bm1);
+        for (int i = tid; i < n16; i += kFThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + lay.bitmap + 16u * i), "l"(src + i));
+        asm volatile("cp.async.commit_group;");
+        if (tid == 0) {
+            *reinterpret_cast<unsigned int *>(smem_raw + lay.next) = 0u;
+            for (int s = 0; s < kStages; s++) {
+                mbar_init(bar_full + 8u * s, 1);
+                mbar_init(bar_empty + 8u * s, kTileSlices);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t seg_len = (uint32_t)(p.seg_end - p.seg_begin);        /* <= 2^31 */
+
+    if (warp == kConsumers) {
+        stream_producer(p, smem_raw, sbase, lay.stages, bar_full, bar_empty, s_tile, lane);
+    } else {
+        const uint32_t sbm = sbase + lay.bitmap, sbm2 = sbase + lay.bitmap2;
+        const uint32_t n_words = 1u << (p.log1 - 5);                     /* umulhi(hc, n_words) = hc >> (37 - log1) on the FMA pipe */
+        const int l2b = L2B ? L2B : p.log2b;                             /* L2B != 0: compile-time shifts */
+        const int shy_w = 37 - l2b, shy_a = 32 - l2b, shy_b = 27 - l2b;
+        const uint32_t four = 4u + (uint32_t)(p.log1 >> 8);              /* always 4, opaque: the address is one IMAD */
+        const uint32_t mulp = acb_pair_mul() + (uint32_t)(p.log1 >> 8);
+        const uint32_t mul2 = p.mul2[0];
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        const uint32_t sring = sbase + lay.ring + (uint32_t)warp * (kPairRing * 8u);
+        const uint32_t sitems = sbase + lay.items + (uint32_t)warp * (kPairItems * 2u);
+        const uint32_t snext = sbase + lay.next;
+        const uint32_t lane5 = (uint32_t)lane << 5;
+        unsigned int n_cand = 0, head = 0;                               /* warp-uniform: entries [head, head + n_cand) of the ring */
+#ifdef ACB_STATIC_SLICES
+        unsigned int g_static = (unsigned)warp;
+#endif
+
+        for (;;) {
+#ifdef ACB_STATIC_SLICES
+            const unsigned int g = g_static;                             /* experiment: slice g goes to warp g % kConsumers, no hand-out */
+            g_static += (unsigned)kConsumers;
+#else
+            unsigned int g = 0;
+            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(g) : "r"(snext) : "memory");
+            g = __shfl_sync(kFull, g, 0);
+#endif
+            const uint32_t fill = g / (uint32_t)kTileSlices, slice_off = (g % (uint32_t)kTileSlices) * (uint32_t)kSliceBytes;
+            const uint32_t stage = fill % (uint32_t)kStages;
+            mbar_wait(bar_full + 8u * stage, (fill / (uint32_t)kStages) & 1u);
+            const uint32_t tile = s_tile[stage];
+            if (tile == kNoTile) break;
+            const uint32_t tile_off = tile * (uint32_t)kTileBytes;       /* relative to the segment */
+            const uint32_t n_valid = (seg_len - tile_off < (uint32_t)kTileBytes) ? seg_len - tile_off : (uint32_t)kTileBytes;
+            const uint32_t slice_saddr = sbase + lay.stages + stage * (uint32_t)kStageBytes + slice_off;
+            const uint32_t pos_base = tile_off + slice_off;
+            uint32_t pend = 0;       /* bit y < 16: position 16 * lane + y of the slice passed level 1; y >= 16: position 512 + 16 * lane + y - 16 */
+            if (slice_off < n_valid) {                                   /* warp-uniform */
+                const uint32_t saddr = slice_saddr + (uint32_t)lane * 16u;
+                uint32_t R0[5], R1[5];
+                {
+                    const uint4 v = lds128(saddr), u = lds128(saddr + 512u);
+                    R0[0] = v.x; R0[1] = v.y; R0[2] = v.z; R0[3] = v.w;
+                    R1[0] = u.x; R1[1] = u.y; R1[2] = u.z; R1[3] = u.w;
+                }
+                /* look-ahead words: the next lane's first word of the same run; lane 31's are lane 0's first word of the
+                   second run and the first word after the slice (next slice / tile pad) */
+                R0[4] = __shfl_down_sync(kFull, R0[0], 1);
+                R1[4] = __shfl_down_sync(kFull, R1[0], 1);
+                const uint32_t r1_first = __shfl_sync(kFull, R1[0], 0);
+                if (lane == 31) { R0[4] = r1_first; R1[4] = lds32(slice_saddr + (uint32_t)kSliceBytes); }
+#ifdef ACB_EXP_NOPROBE
+                pend = (R0[0] ^ R0[3] ^ R0[4] ^ R1[1] ^ R1[4]) == 0x12345678u ? 1u : 0u;
+#else
+                pend = probe_pair_run(0u, sbm, n_words, four, R0, mulp);
+                pend = probe_pair_run(pend, sbm, n_words, four, R1, mulp);
+                pend = __brev(pend);
+#endif
+                if (n_valid - slice_off < (uint32_t)kSliceBytes) {       /* last slice of the segment: positions past its end */
+                    const int v0 = (int)(n_valid - slice_off) - lane * 16, v1 = v0 - 512;
+                    const uint32_t m0 = v0 <= 0 ? 0u : (v0 >= 16 ? 0xffffu : ((1u << v0) - 1u));
+                    const uint32_t m1 = v1 <= 0 ? 0u : (v1 >= 16 ? 0xffffu : ((1u << v1) - 1u));
+                    pend &= m0 | (m1 << 16);
+                }
+#ifdef ACB_EXP_NOSURV
+                if (pend == 0x9e3779b9u) s_tile[0] = 1u;
+                pend = 0;
+#endif
+            }
+            /* items: the pending positions of all lanes go to the list -- an exclusive scan of the lanes' counts places
+               them (dense text, more than the list holds: ballot rounds, one position per lane and round, a pass at a
+               time) -- and are worked off 32 at a time */
+            unsigned int tot = __reduce_add_sync(kFull, (unsigned)__popc(pend));
+            while (tot) {
+                unsigned int n_items;
+                if (tot <= (unsigned)kPairItems) {
+                    const unsigned int cnt = (unsigned)__popc(pend);
+                    unsigned int incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned int v = __shfl_up_sync(kFull, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    uint32_t at = sitems + 2u * (incl - cnt);
+                    while (pend) {
+                        const uint32_t z = (uint32_t)__clz((int)pend);
+                        pend ^= 0x80000000u >> z;
+                        sts16(at, lane5 | (z ^ 31u));                     /* lane << 5 | bit */
+                        at += 2u;
+                    }
+                    n_items = tot;
+                    tot = 0;
+                } else {
+                    n_items = 0;
+                    do {
+                        const unsigned int mp = __ballot_sync(kFull, pend != 0u);
+                        if (pend) {
+                            const uint32_t z = (uint32_t)__clz((int)pend);
+                            pend ^= 0x80000000u >> z;
+                            sts16(sitems + 2u * (n_items + (unsigned)__popc(mp & lt_mask)), lane5 | (z ^ 31u));
+                        }
+                        n_items += (unsigned)__popc(mp);
+                    } while (n_items <= (unsigned)(kPairItems - 32));
+                    tot -= n_items;
+                }
+                __syncwarp();
+                for (unsigned int base = 0; base < n_items;) {
+                    if (n_cand == (unsigned)kPairRing) { pair_resolve(p, sring, head, 32u); head += 32u; n_cand -= 32u; continue; }   /* one slice alone filled the ring */
+                    unsigned int take = n_items - base;
+                    if (take > 32u) take = 32u;
+                    if (take > (unsigned)kPairRing - n_cand) take = (unsigned)kPairRing - n_cand;
+                    bool ok = false;
+                    uint32_t pos = 0, tag = 0;
+                    if ((unsigned)lane < take) {
+                        const uint32_t it = lds16(sitems + 2u * (base + (unsigned)lane));
+                        const uint32_t y = it & 31u;
+                        const uint32_t t = ((it >> 1) & 0x1f0u) + ((y & 16u) * 31u + y);       /* 16 * lane + y, second run: + 496 */
+                        const uint32_t ga = slice_saddr + t, wa = ga & ~3u;
+                        const uint32_t lo = lds32(wa), hi = lds32(wa + 4u);
+                        const uint32_t w = __funnelshift_r(lo, hi, ga << 3);                    /* wrap shift: (ga & 3) * 8 */
+                        tag = (w * mul2) | 1u;
+                        const uint32_t word = lds_bitmap((tag >> shy_w) * four + sbm2);
+                        ok = (__funnelshift_r(word, 0u, tag >> shy_a) & __funnelshift_r(word, 0u, tag >> shy_b) & 1u) != 0u;
+                        pos = pos_base + t;
+                    }
+                    if (p.log3) {                                        /* very large key sets: the tag bitmap in L2 as well */
+                        const uint32_t i0 = (tag * ACB_TAGMAP_MIX) >> (32 - p.log3);
+                        if (ok) ok = ((__ldg(p.bm3 + (i0 >> 5)) >> (i0 & 31u)) & 1u) != 0u;
+                    }
+#ifdef ACB_EXP_NODRAIN
+                    if (ok && tag == pos) s_tile[0] = 2u;
+#else
+                    const unsigned mk = __ballot_sync(kFull, ok);
+                    if (ok) {
+                        const uint32_t at = sring + (((head + n_cand + (unsigned)__popc(mk & lt_mask)) & (kPairRing - 1u)) << 3);
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(at), "r"(pos), "r"(tag) : "memory");
+                    }
+                    n_cand += (unsigned)__popc(mk);
+#endif
+                    base += take;
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8u * stage);          /* this warp is done with the stage */
+            /* a full turn of candidates (one per lane): through the anchor table now, while the other warps stream on */
+            while (n_cand >= 32u) { pair_resolve(p, sring, head, 32u); head += 32u; n_cand -= 32u; }
+        }
+        if (n_cand) { __syncwarp(); pair_resolve(p, sring, head, n_cand); }
     }
     /* the last CTA to leave re-arms the work counter, so a launch needs no memset before it */
     __syncthreads();
@@ -855,7 +1203,7 @@ __global__ void acb_flag_goto_kernel(int32_t *gto, const int32_t *key_of, size_t
 struct acb_table {
     int device = 0;
     int sm_count = 0;
-    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log3 = 0, logA = 10, filter_flags = 0;
+    int32_t S = 0, K = 0, L = 1, n_keys = 0, gram = 1, stride = 1, log1 = 13, log3 = 0, logA = 10, filter_flags = 0, log2b = 0;
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     uint8_t *d_cls = nullptr;
@@ -939,7 +1287,7 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { acb_set_error("cudaGetDeviceProperties failed"); rc = ACB_ECUDA; break; }
         tb->sm_count = prop.multiProcessorCount;
         tb->S = f.n_states; tb->K = f.n_classes; tb->L = f.letter_bytes; tb->n_keys = f.n_keys;
-        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log3 = f.log2_bits3; tb->logA = f.log2_anchor_slots; tb->filter_flags = f.filter_flags;
+        tb->gram = f.gram_bytes; tb->stride = f.stride; tb->log1 = f.log2_bits1; tb->log3 = f.log2_bits3; tb->logA = f.log2_anchor_slots; tb->filter_flags = f.filter_flags; tb->log2b = f.log2_bits2;
         tb->min_key_bytes = f.min_key_bytes; tb->max_key_bytes = f.max_key_bytes;
         acb_hash_multipliers(tb->gram, 1, tb->mul1);
         acb_hash_multipliers(tb->gram, 2, tb->mul2);
@@ -964,7 +1312,7 @@ extern "C" int acb_table_upload(const acb_trie *t, int device, acb_table **out) 
         if ((rc = upload(&tb->d_outptr, f.out_ptr, (size_t)f.n_states + 1, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_outidx, f.out_idx, (size_t)f.out_ptr[f.n_states], tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_keylen, f.key_len, (size_t)f.n_keys, tb->dev_bytes))) break;
-        if ((rc = upload(&tb->d_bm1, f.bitmap1, (size_t)1 << (f.log2_bits1 - 5), tb->dev_bytes))) break;
+        if ((rc = upload(&tb->d_bm1, f.bitmap1, ((size_t)1 << (f.log2_bits1 - 5)) + (f.log2_bits2 ? (size_t)1 << (f.log2_bits2 - 5) : 0), tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_bm3, f.bitmap3, f.log2_bits3 ? ((size_t)1 << (f.log2_bits3 - 5)) : 1, tb->dev_bytes))) break;
         if ((rc = upload(&tb->d_anchors, f.anchors, (size_t)8 << f.log2_anchor_slots, tb->dev_bytes))) break;
         unsigned int zero[4] = {0, 0, 0, 0};   /* work counters, re-armed by the kernels themselves */
@@ -997,12 +1345,27 @@ static int launch_stream_m(const ScanParams &p, int grid, cudaStream_t s) {
     return ACB_OK;
 }
 
+static int launch_pair(const ScanParams &p, int grid, cudaStream_t s) {
+    const size_t smem = pair_smem(p.log1, p.log2b).total;
+    static std::atomic<size_t> opted{0};
+    if (opted.load(std::memory_order_relaxed) < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(acb_pair_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(acb_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opted.store(smem, std::memory_order_relaxed);
+    }
+    if (p.log2b == 17) acb_pair_kernel<17><<<grid, kFThreads, smem, s>>>(p);      /* the 2^20-bit level 1 of 10 k keys and more */
+    else acb_pair_kernel<0><<<grid, kFThreads, smem, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return ACB_OK;
+}
+
 /* the placement mode follows from the table's filter_flags */
 template <int NW, int STRIDE>
 static int launch_stream_t(const ScanParams &p, int flags, int grid, cudaStream_t s) {
     if (flags & ACB_FILTER_PAIR) {
-        if (NW != 1 || STRIDE != 1 || p.gram != 4 || p.L != 1) { acb_set_error("PAIR filter needs gram 4, stride 1, 1-byte letters"); return ACB_EINVAL; }
-        return launch_stream_m<1, 1, kModePair>(p, grid, s);
+        if (NW != 1 || STRIDE != 1 || p.gram != 4 || p.L != 1 || p.log2b < 13 || p.log2b > 19) { acb_set_error("PAIR filter needs gram 4, stride 1, 1-byte letters and a level 2"); return ACB_EINVAL; }
+        return launch_pair(p, grid, s);
     }
     if (flags & ACB_FILTER_WIDE) {
         if (p.gram != 4 * NW) { acb_set_error("WIDE filter with gram %d", p.gram); return ACB_EINVAL; }
@@ -1038,7 +1401,7 @@ static int launch_stream(const ScanParams &p, int flags, int stride, int grid, c
 /* the stream kernel over the start positions [begin, end) of the flat buffer (begin a multiple of 32), one launch per
  * <= 2 GiB segment.  Text after `end` is read as far as a key can reach, never interpreted as a start position. */
 static int launch_filter_range(acb_table *tb, ScanParams &p, long long begin, long long end, cudaStream_t s) {
-    if (!tb->d_cand) {                                      /* room for every byte of a slice per consumer warp: never overflows */
+    if (!(tb->filter_flags & ACB_FILTER_PAIR) && !tb->d_cand) {    /* room for every byte of a slice per consumer warp: never overflows */
         CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_cand), (size_t)tb->sm_count * kConsumers * kWarpCand * sizeof(uint2)));
         tb->dev_bytes += (long long)tb->sm_count * kConsumers * kWarpCand * (long long)sizeof(uint2);
     }
@@ -1063,7 +1426,7 @@ static void fill_params(const acb_table *tb, ScanParams &p, const uint8_t *d_hay
     p.out_ptr = tb->d_outptr; p.out_idx = tb->d_outidx; p.key_len = tb->d_keylen;
     p.S = tb->S; p.L = tb->L; p.gram = tb->gram; p.max_key_bytes = tb->max_key_bytes;
     p.bm1 = tb->d_bm1; p.bm3 = tb->d_bm3; p.anchors = reinterpret_cast<const uint4 *>(tb->d_anchors);
-    p.log1 = tb->log1; p.log3 = tb->log3; p.logA = tb->logA;
+    p.log1 = tb->log1; p.log3 = tb->log3; p.logA = tb->logA; p.log2b = tb->log2b;
     memcpy(p.mul1, tb->mul1, sizeof(p.mul1));
     memcpy(p.mul2, tb->mul2, sizeof(p.mul2));
     p.out = d_out; p.cap = cap; p.count = reinterpret_cast<unsigned long long *>(d_count);

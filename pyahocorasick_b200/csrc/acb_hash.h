@@ -103,40 +103,37 @@ ACB_HD uint32_t acb_stage1_bit_a(uint64_t hw, int g, int log2_bits) {
 }
 ACB_HD uint32_t acb_stage1_bit_b(uint64_t hw) { return (uint32_t)hw & 31u; }
 
-/* ---- PAIR placement (gram 4, stride 1, 1-byte letters): two levels, both keyed by the pair ------------------
- * Positions x (even) and x+1 share the three bytes text[x+1 .. x+3].  Their hash
- *      hc = (the three common bytes as a little-endian word) * (ACB_PAIR_M << 8)   (mod 2^32)
- * (a plain 32-bit multiply of the window at x+1: the shifted multiplier drops that window's fourth byte) selects
- *   level 1:  ONE BIT of a bitmap of 2^(n-1) bits  -- index hc >> (33-n): word index hc >> (38-n), bit 31 - (index & 31)
- *             (the kernel shifts the word LEFT by the index, so the tested bit lands in bit 31 and is added into the
- *             pass mask through the carry) -- "does any key gram have these three bytes where this pair has them?"
- *   level 2:  ONE WORD of 2^(n-6) words, word index hc >> (38-n) as well, in which a gram G (little-endian word) of
- *             either role sets two bits: a = dp4a(G, ACB_PAIR_CA) & 31, b = dp4a(G, ACB_PAIR_CB) & 31 (byte-wise dot
- *             products with odd coefficients: their low five bits are already mixed over all four bytes, so they feed
- *             a wrap shift directly, and IDP.4A issues at the rate of a 32-bit multiply -- mul.hi / mul.wide, which an
- *             earlier version used here, issue at half of it: tools/ubench/pipes.cu).
- * n = log2 of all the bits (2^n bits of shared memory: level 1 in the first half, level 2 in the second).  Only pairs
- * that pass level 1 (a few per cent on random text) are looked at position by position.  Role 0 = G starts at the even
- * position x (its bytes 1..3 are the common ones), role 1 = G starts at x+1 (bytes 0..2); every key gram is entered
- * under both roles (a key may start at an even or an odd position). */
+/* ---- PAIR placement (gram 4, stride 1, 1-byte letters) -----------------------------------------------------
+ * Positions x (even) and x+1 share the three bytes text[x+1 .. x+3].  ONE 64-bit product of the window at x+1,
+ *      pr = (uint64) window(x+1) * (ACB_PAIR_M << 8),     hc = low half (the shifted multiplier drops the window's
+ *      fourth byte: hc depends on the three common bytes only),     hb = high half (all four bytes),
+ * selects
+ *   level 1:  ONE WORD of 2^(n-5) words, index hc >> (37-n), one shared-memory load per TWO positions, in which
+ *             role 0 (the gram G starts at the even position x; its bytes 1..3 are the common ones) owns bit
+ *             31 - (G & 31) -- the low five bits of the gram's first byte, the one byte hc does not see -- and
+ *             role 1 (G starts at x+1, G IS the window; bytes 0..2 common) owns bit 31 - (hb & 31).  The kernel
+ *             shifts the word LEFT by the raw byte / by hb (wrap shifts use the low five bits), so the tested bit
+ *             lands in bit 31 and is added into a per-POSITION pass mask through the carry.  Every key gram is
+ *             entered under both roles (a key may start at an even or an odd position).
+ *   level 2:  a second bitmap of 2^k bits right behind level 1 (shared memory as well), a blocked Bloom filter with
+ *             two bits per gram keyed by the anchor tag (hash 2 of the gram, role-independent): word
+ *             tag >> (37-k), bits (tag >> (32-k)) & 31 and (tag >> (27-k)) & 31.  Only positions that pass level 1
+ *             (about 2 % on random text against 10 k keys) compute their tag at all. */
 #define ACB_PAIR_M  0x9E3779B1u
-#define ACB_PAIR_CA 0x1B0D0701u   /* bytes  1,  7, 13, 27 */
-#define ACB_PAIR_CB 0x1F091503u   /* bytes  3, 21,  9, 31 */
 ACB_HD uint32_t acb_pair_mul(void) { return ACB_PAIR_M << 8; }
-ACB_HD uint32_t acb_dp4a(uint32_t x, uint32_t c) {
-    return (x & 0xffu) * (c & 0xffu) + ((x >> 8) & 0xffu) * ((c >> 8) & 0xffu) +
-           ((x >> 16) & 0xffu) * ((c >> 16) & 0xffu) + (x >> 24) * (c >> 24);
-}
-/* role 0 / 1 placement of gram G in a filter of 2^log2_bits bits: level 1 (*word1 |= *bit1) and level 2 (*word2 |= *bits2);
- * word indices count 32-bit words from the start of the bitmap */
-ACB_HD void acb_pair_place(uint32_t G, int role, int log2_bits, uint32_t *word1, uint32_t *bit1, uint32_t *word2, uint32_t *bits2) {
+/* level-1 placement of gram G (little-endian word) in one role: *word (index from the start of the bitmap) |= *bit */
+ACB_HD void acb_pair_place(uint32_t G, int role, int log2_bits, uint32_t *word, uint32_t *bit) {
     const uint32_t common = role ? G : (G >> 8);
-    const uint32_t hc = common * (ACB_PAIR_M << 8);
-    const uint32_t idx = hc >> (33 - log2_bits);
-    *word1 = idx >> 5;
-    *bit1 = 1u << (31u - (idx & 31u));
-    *word2 = (1u << (log2_bits - 6)) + (hc >> (38 - log2_bits));
-    *bits2 = (1u << (acb_dp4a(G, ACB_PAIR_CA) & 31u)) | (1u << (acb_dp4a(G, ACB_PAIR_CB) & 31u));
+    const uint64_t pr = (uint64_t)common * (uint64_t)(ACB_PAIR_M << 8);
+    const uint32_t hc = (uint32_t)pr;
+    const uint32_t amount = role ? (uint32_t)(((uint64_t)G * (uint64_t)(ACB_PAIR_M << 8)) >> 32) : G;
+    *word = hc >> (37 - log2_bits);
+    *bit = 1u << (31u - (amount & 31u));
+}
+/* level-2 placement of the anchor tag: *word counts from the start of level 2 */
+ACB_HD void acb_pair_place2(uint32_t tag, int log2_bits2, uint32_t *word, uint32_t *bits) {
+    *word = tag >> (37 - log2_bits2);
+    *bits = (1u << ((tag >> (32 - log2_bits2)) & 31u)) | (1u << ((tag >> (27 - log2_bits2)) & 31u));
 }
 
 #endif

@@ -104,7 +104,7 @@ struct Flat {
     int32_t min_key_bytes = 0, max_key_bytes = 0;
     uint8_t byte_class[256];
     std::vector<int32_t> goto_cm, fail, letter_fail, key_of, out_ptr, out_idx, key_len;
-    int32_t gram = 0, stride = 0, log1 = 0, log3 = 0, logA = 0, filter_flags = 0;
+    int32_t gram = 0, stride = 0, log1 = 0, log3 = 0, logA = 0, filter_flags = 0, log2b = 0;
     std::vector<uint32_t> bm1, bm3, anchors;
 };
 
@@ -430,12 +430,15 @@ static void build_filter(acb_trie *t, Flat &f) {
             for (int pair = 0; pair <= 1; pair++) {
                 if (pair && !(L == 1 && s == 1 && g == 4)) continue;
                 if (forced_mode >= 0 && pair != forced_mode) continue;
-                /* pair: a foreign gram must find its level-1 bit set (fill of 2E entries in half the bits) and then both
-                   of its bits in a level-2 word that is known to hold at least the entry it collided with */
-                const double fill1 = std::min(1.0, 2.0 * E / (words * 16.0));
-                const double pass1 = pair ? p_true + (1 - p_true) * fill1 * std::min(1.0, 8.0 * pass_rate(1.0 + 4.0 * E / words))
+                /* pair: a foreign position must find its role's bit set in level 1 (2E entries in 2^log1 bits, a little
+                   more for the unevenly used five low bits of a text byte) -- it then costs an item round -- and both of
+                   its tag's bits in level 2 (blocked Bloom, k = 2, 2E bits in 2^log2b) to reach the anchor table */
+                const int log2b = log1 >= 20 ? 17 : std::min(19, std::max(13, log1));
+                const double pass_l1 = std::min(1.0, 1.3 * 2.0 * E / (words * 32.0));
+                const double fill2 = std::min(1.0, 2.0 * E / std::pow(2.0, log2b));
+                const double pass1 = pair ? p_true + (1 - p_true) * pass_l1 * fill2 * fill2
                                           : p_true + (1 - p_true) * pass_rate(E / words);
-                const double probe = pair ? 6.0 : std::max(17.0, 5.0 + 3.0 * nw);
+                const double probe = pair ? 6.0 + 40.0 * pass_l1 : std::max(17.0, 5.0 + 3.0 * nw);
                 const double cost = (probe + pass1 * 120.0 + p_true * (s / L) * 40.0) / s;
                 if (cost < best.cost) {
                     best.g = g; best.s = s; best.log1 = log1; best.cost = cost;
@@ -456,7 +459,10 @@ static void build_filter(acb_trie *t, Flat &f) {
      *   single: word = umulhi(hash1, n_words), bits acb_stage1_bit_a AND acb_stage1_bit_b (acb_hash.h);
      *   pair  : two levels in the two halves of the bits, acb_pair_place, every gram once per role. */
     const uint32_t n_words = 1u << (best.log1 - 5);
-    f.bm1.assign((size_t)n_words, 0);
+    /* pair placement: level 2 follows level 1.  Together with the ring and the candidate rings of the pair kernel a
+       2^20-bit level 1 leaves 16 KiB of shared memory; a smaller level 1 leaves room for 2^19 bits */
+    f.log2b = best_pair ? (best.log1 >= 20 ? 17 : std::min(19, std::max(13, best.log1))) : 0;       /* the cost model's */
+    f.bm1.assign((size_t)n_words + (f.log2b ? (size_t)1 << (f.log2b - 5) : 0), 0);
     uint32_t mul1[ACB_MAX_WINDOWS], mul2[ACB_MAX_WINDOWS];
     acb_hash_multipliers(g, 1, mul1);
     acb_hash_multipliers(g, 2, mul2);
@@ -466,11 +472,13 @@ static void build_filter(acb_trie *t, Flat &f) {
             const uint8_t *b = gr.data();
             const uint32_t G = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
             for (int role = 0; role < 2; role++) {
-                uint32_t word1, bit1, word2, bits2;
-                acb_pair_place(G, role, best.log1, &word1, &bit1, &word2, &bits2);
+                uint32_t word1, bit1;
+                acb_pair_place(G, role, best.log1, &word1, &bit1);
                 f.bm1[word1] |= bit1;
-                f.bm1[word2] |= bits2;
             }
+            uint32_t word2, bits2;
+            acb_pair_place2(acb_hash_bytes(b, g, mul2) | 1u, f.log2b, &word2, &bits2);
+            f.bm1[(size_t)n_words + word2] |= bits2;
         } else {
             const uint64_t hw = acb_hash_bytes_wide(gr.data(), g, mul1);
             const uint32_t h1 = (uint32_t)hw;
@@ -769,6 +777,7 @@ extern "C" int acb_trie_flat_view(const acb_trie *t, acb_flat_view *out) {
     out->bitmap1 = f.bm1.data();
     out->anchors = f.anchors.data();
     out->filter_flags = f.filter_flags;
+    out->log2_bits2 = f.log2b;
     return ACB_OK;
 }
 
@@ -827,7 +836,7 @@ static bool get_vec(const uint8_t *buf, int64_t len, int64_t &pos, std::vector<T
 struct FlatHeader {
     char magic[8];
     uint64_t hash;
-    int32_t abi, letter_bytes, S, K, n_keys, min_key_bytes, max_key_bytes, gram, stride, log1, log3, logA, filter_flags, pad;
+    int32_t abi, letter_bytes, S, K, n_keys, min_key_bytes, max_key_bytes, gram, stride, log1, log3, logA, filter_flags, log2b;
     uint8_t byte_class[256];
 };
 
@@ -850,7 +859,7 @@ extern "C" int acb_trie_flat_save(const acb_trie *t, uint8_t *out, int64_t cap, 
         h.hash = content_hash(t);
         h.abi = ACB_ABI_VERSION; h.letter_bytes = t->letter_bytes; h.S = f.S; h.K = f.K; h.n_keys = f.n_keys;
         h.min_key_bytes = f.min_key_bytes; h.max_key_bytes = f.max_key_bytes; h.gram = f.gram; h.stride = f.stride;
-        h.log1 = f.log1; h.log3 = f.log3; h.logA = f.logA; h.filter_flags = f.filter_flags;
+        h.log1 = f.log1; h.log3 = f.log3; h.logA = f.logA; h.filter_flags = f.filter_flags; h.log2b = f.log2b;
         memcpy(h.byte_class, f.byte_class, 256);
         b.insert(b.end(), reinterpret_cast<uint8_t *>(&h), reinterpret_cast<uint8_t *>(&h) + sizeof(h));
         put_vec(b, f.goto_cm); put_vec(b, f.fail); put_vec(b, f.letter_fail); put_vec(b, f.key_of); put_vec(b, f.out_ptr);
@@ -877,7 +886,7 @@ extern "C" int acb_trie_flat_load(acb_trie *t, const uint8_t *buf, int64_t len) 
         }
         Flat f;
         f.S = h.S; f.K = h.K; f.n_keys = h.n_keys; f.min_key_bytes = h.min_key_bytes; f.max_key_bytes = h.max_key_bytes;
-        f.gram = h.gram; f.stride = h.stride; f.log1 = h.log1; f.log3 = h.log3; f.logA = h.logA; f.filter_flags = h.filter_flags;
+        f.gram = h.gram; f.stride = h.stride; f.log1 = h.log1; f.log3 = h.log3; f.logA = h.logA; f.filter_flags = h.filter_flags; f.log2b = h.log2b;
         memcpy(f.byte_class, h.byte_class, 256);
         int64_t pos = (int64_t)sizeof(FlatHeader);
         const uint64_t big = (uint64_t)1 << 34;
@@ -887,7 +896,8 @@ extern "C" int acb_trie_flat_load(acb_trie *t, const uint8_t *buf, int64_t len) 
                   get_vec(buf, len, pos, f.anchors, big);
         ok = ok && f.S > 0 && f.K > 0 && f.K <= 256 && f.goto_cm.size() == (size_t)f.K * f.S && f.fail.size() == (size_t)f.S &&
              f.letter_fail.size() == (size_t)f.S && f.key_of.size() == (size_t)f.S && f.out_ptr.size() == (size_t)f.S + 1 &&
-             f.key_len.size() == (size_t)f.n_keys && f.log1 >= 13 && f.log1 <= 20 && f.bm1.size() == ((size_t)1 << (f.log1 - 5)) &&
+             f.key_len.size() == (size_t)f.n_keys && f.log1 >= 13 && f.log1 <= 20 && ((f.filter_flags & ACB_FILTER_PAIR) ? (f.log2b >= 13 && f.log2b <= 19) : f.log2b == 0) &&
+             f.bm1.size() == ((size_t)1 << (f.log1 - 5)) + (f.log2b ? (size_t)1 << (f.log2b - 5) : 0) &&
              f.bm3.size() == (f.log3 ? ((size_t)1 << (f.log3 - 5)) : (size_t)1) && f.logA >= 10 && f.logA <= 28 &&
              f.anchors.size() == ((size_t)8 << f.logA) && !f.out_ptr.empty() && f.out_idx.size() == (size_t)f.out_ptr.back();
         if (!ok) { acb_set_error("flat-table cache is truncated or inconsistent"); return ACB_EINVAL; }

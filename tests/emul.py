@@ -103,21 +103,20 @@ def _entry_bytes(e, n):
 
 
 PAIR_M = 0x9E3779B1
-PAIR_CA = (1, 7, 13, 27)
-PAIR_CB = (3, 21, 9, 31)
-
-
-def _dp4a(G, c):
-    return sum(((G >> (8 * i)) & 0xFF) * c[i] for i in range(4))
 
 
 def pair_place(G, role, log2_bits):
-    """acb_pair_place (csrc/acb_hash.h): (word1, bit1, word2, bits2) of gram G (little-endian u32) in one role"""
+    """acb_pair_place (csrc/acb_hash.h): (word, bit) of gram G (little-endian u32) in level 1, in one role"""
+    mulp = (PAIR_M << 8) & M32
     common = G if role else (G >> 8)
-    hc = (common * ((PAIR_M << 8) & M32)) & M32
-    idx = hc >> (33 - log2_bits)
-    word2 = (1 << (log2_bits - 6)) + (hc >> (38 - log2_bits))
-    return idx >> 5, 1 << (31 - (idx & 31)), word2, (1 << (_dp4a(G, PAIR_CA) & 31)) | (1 << (_dp4a(G, PAIR_CB) & 31))
+    hc = (common * mulp) & M32
+    amount = ((G * mulp) >> 32) if role else G
+    return hc >> (37 - log2_bits), 1 << (31 - (amount & 31))
+
+
+def pair_place2(tag, log2_bits2):
+    """acb_pair_place2: (word, bits) of an anchor tag in level 2 (word counted from the start of level 2)"""
+    return tag >> (37 - log2_bits2), (1 << ((tag >> (32 - log2_bits2)) & 31)) | (1 << ((tag >> (27 - log2_bits2)) & 31))
 
 
 def _u32_at(buf, q):
@@ -134,8 +133,13 @@ def _passes_bitmap(f, buf, q):
     if flags & FILTER_PAIR:
         assert g == 4 and f["stride"] == 1 and f["letter_bytes"] == 1
         role = q & 1                                   # x even: role 0 of pair (x, x+1); x odd: role 1 of (x-1, x)
-        word1, bit1, word2, bits2 = pair_place(_u32_at(buf, q), role, l1)
-        return bool(int(f["bitmap1"][word1]) & bit1) and (int(f["bitmap1"][word2]) & bits2) == bits2
+        G = _u32_at(buf, q)
+        word1, bit1 = pair_place(G, role, l1)
+        if not int(f["bitmap1"][word1]) & bit1:
+            return False
+        tag = ((G * multipliers(4, 2)[0]) & M32) | 1
+        word2, bits2 = pair_place2(tag, f["log2_bits2"])
+        return (int(f["bitmap1"][n_words + word2]) & bits2) == bits2
     mul1 = multipliers(g, 1)
     hw = hash_bytes_wide(buf, q, g, mul1)
     h1 = hw & M32

@@ -20,7 +20,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/acb200.h but not exported"
     assert sorted(N.EXPORTED_SYMBOLS) == names
-    assert L.acb_abi_version() == N.ABI_VERSION == 4
+    assert L.acb_abi_version() == N.ABI_VERSION == 5
 
 
 def test_host_calls_work_without_a_gpu_and_scan_fails_loudly():

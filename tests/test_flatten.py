@@ -105,10 +105,11 @@ def test_filter_choice_for_baseline_configs():
     f = synth.build_automaton(w.keys).flat()
     assert (f["gram_bytes"], f["stride"], f["log2_bits1"]) == (4, 1, 20)
     assert f["filter_flags"] == emul.FILTER_PAIR          # 10 k grams of 4 bytes at stride 1: one word per two positions
+    assert f["log2_bits2"] == 17 and f["bitmap1"].size == (1 << 15) + (1 << 12)
     bits = np.unpackbits(f["bitmap1"].view(np.uint8))
-    half = bits.size // 2
-    assert 0.03 < bits[:half].mean() < 0.04     # level 1: one bit per gram and role in 2^19 bits
-    assert 0.06 < bits[half:].mean() < 0.08     # level 2: two bits per gram and role (blocked Bloom, k = 2) in 2^19 bits
+    n1 = 1 << 20
+    assert 0.015 < bits[:n1].mean() < 0.02      # level 1: one bit per gram and role in 2^20 bits
+    assert 0.12 < bits[n1:].mean() < 0.16       # level 2: two bits per gram (blocked Bloom, k = 2, keyed by the anchor tag) in 2^17 bits
     a = f["anchors"]
     used = a[a[:, 0] != 0]
     assert 9000 < len(used) <= 10000 and len(used) * 4 <= len(a)         # one anchor per distinct 4-byte prefix

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "random_batches or pathological or dense or golden" 2>&1 | tail -5 ) > gpurun_out/r2i_pytest.log
+cat gpurun_out/r2i_pytest.log
+run() { name=$1; var=$2; cfg=$3; lib=$PWD/pyahocorasick_b200/_native/libacb200${name:+_$name}.so
+  ACB_LIB=$lib timeout 200 python bench.py --config $cfg --steps 10 --warmup 3 --variant $var --no-cpu-baseline --no-e2e --no-latency 2>&1 | python tools/kline.py "lib=${name:-default} $cfg variant=$var"; }
+( run "" planted C2; run "" sparse C2; run static planted C2; run static sparse C2; run "" planted C3; run "" planted C5; run "" planted C4 ) 2>&1 | tee gpurun_out/r2i_variants.log
