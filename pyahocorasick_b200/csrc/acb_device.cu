@@ -462,6 +462,7 @@ __device__ __forceinline__ void resolve_backlog(const ScanParams &p, uint8_t *sm
 
 /* The producer warp of a streaming kernel: claims tiles from the global counter and keeps the shared-memory ring full
  * (cp.async.bulk + mbarrier); `stages` = offset of the ring in the CTA's shared memory. */
+template <int NCONS>
 __device__ __forceinline__ void stream_producer(const ScanParams &p, uint8_t *smem_raw, uint32_t sbase, uint32_t stages,
                                                 uint32_t bar_full, uint32_t bar_empty, volatile uint32_t *s_tile, int lane) {
     struct { uint32_t stages; } lay = {stages};
@@ -486,7 +487,7 @@ __device__ __forceinline__ void stream_producer(const ScanParams &p, uint8_t *sm
             if (tile >= p.n_tiles) {
                 /* out of work: sentinel fills end the consumers -- a consumer leaves at the first sentinel slice it is
                    handed, so as many fills as it takes to hand every warp one (they are never released: <= kStages) */
-                constexpr uint32_t kSentinels = (kConsumers + kTileSlices - 1) / kTileSlices;
+                constexpr uint32_t kSentinels = (NCONS + kTileSlices - 1) / kTileSlices;
                 static_assert(kSentinels <= (uint32_t)kStages, "sentinel fills must not wrap the ring");
                 for (uint32_t k2 = 0; k2 < kSentinels; k2++) {
                     const uint32_t f2 = fill + k2, st2 = f2 % kStages;
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
     const uint32_t seg_len = (uint32_t)(p.seg_end - p.seg_begin);        /* <= 2^31 */
 
     if (warp == kConsumers) {
-        stream_producer(p, smem_raw, sbase, lay.stages, bar_full, bar_empty, s_tile, lane);
+        stream_producer<kConsumers>(p, smem_raw, sbase, lay.stages, bar_full, bar_empty, s_tile, lane);
     } else {
         /* ---------------- consumer warps: slice `warp` of every fill */
         ProbeCtx c;
@@ -743,6 +744,13 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
  *             the warp take ONE atomicAdd on the record counter and are stored straight to the record buffer (no
  *             staging copy); MULTI anchors (keys sharing their first four bytes) take the general path with one
  *             atomic per record. */
+#ifndef ACB_PAIR_CONSUMERS
+#define ACB_PAIR_CONSUMERS 27
+#endif
+constexpr int kPairConsumers = ACB_PAIR_CONSUMERS;          /* consumer warps of the pair kernel: 27 + the producer = 896 threads leave 72 registers per thread,
+                                                                and the level-1 loop stops spilling (31 consumers at 64 registers: 4 % slower on C2) */
+constexpr int kPairThreads = (kPairConsumers + 1) * 32;
+static_assert((kPairConsumers + kTileSlices - 1) / kTileSlices + 2 < 2 * ACB_STAGES && kPairThreads <= 1024, "pair kernel shape");
 constexpr int kPairRing = 64;                                /* candidate ring entries per consumer warp */
 constexpr int kPairItems = 64;                               /* item list entries (uint16) per consumer warp */
 
@@ -755,8 +763,8 @@ __host__ __device__ inline PairSmem pair_smem(int log1, int log2b) {
     s.bitmap = o;    o += 1u << (log1 - 3);                       /* >= 1 KiB: level 2 follows without a gap, as in bm1 */
     s.bitmap2 = o;   o += 1u << (log2b - 3);                      o = (o + 127u) & ~127u;
     s.stages = o;    o += (uint32_t)kStages * kStageBytes;
-    s.ring = o;      o += (uint32_t)kConsumers * kPairRing * 8u;
-    s.items = o;     o += (uint32_t)kConsumers * kPairItems * 2u;
+    s.ring = o;      o += (uint32_t)kPairConsumers * kPairRing * 8u;
+    s.items = o;     o += (uint32_t)kPairConsumers * kPairItems * 2u;
     s.bars = o;      o += 2u * kStages * 8u;
     s.tiles = o;     o += (uint32_t)kStages * 4u;
     s.next = o;      o += 4u;
@@ -876,9 +884,12 @@ __device__ __forceinline__ uint32_t probe_pair_run(uint32_t acc, uint32_t sbm, u
         const uint32_t word = lds_bitmap(waddr);
 #endif
         const uint32_t ta = __funnelshift_l(0u, word, window(R, x));      /* word << (text[x] & 31): role 0's bit -> bit 31 */
-        acc = __funnelshift_l(ta, acc, 1);                                /* acc << 1 | bit 31 of ta */
-#ifndef ACB_EXP_L1_ONEROLE
         const uint32_t tb = __funnelshift_l(0u, word, hb);                /* role 1's */
+#ifdef ACB_L1_CARRY
+        asm("{ .reg .u32 t2; add.cc.u32 t2, %1, %1; addc.u32 %0, %0, %0; add.cc.u32 t2, %2, %2; addc.u32 %0, %0, %0; }"
+            : "+r"(acc) : "r"(ta), "r"(tb));
+#else
+        acc = __funnelshift_l(ta, acc, 1);                                /* acc << 1 | bit 31 of ta */
         acc = __funnelshift_l(tb, acc, 1);
 #endif
     }
@@ -886,7 +897,7 @@ __device__ __forceinline__ uint32_t probe_pair_run(uint32_t acc, uint32_t sbm, u
 }
 
 template <int L2B>
-__global__ void __launch_bounds__(kFThreads, 1) acb_pair_kernel(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(kPairThreads, 1) acb_pair_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const PairSmem lay = pair_smem(p.log1, p.log2b);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -894,29 +905,31 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_pair_kernel(const __grid_con
     const uint32_t bar_full = sbase + lay.bars, bar_empty = bar_full + 8u * kStages;
     volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem_raw + lay.tiles);
 
-    {   /* both levels of the bitmap -> shared memory with cp.async */
-        const int n16 = (1 << (p.log1 - 7)) + (1 << (p.log2b - 7));
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.bm1);
-        for (int i = tid; i < n16; i += kFThreads)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + lay.bitmap + 16u * i), "l"(src + i));
-        asm volatile("cp.async.commit_group;");
-        if (tid == 0) {
-            *reinterpret_cast<unsigned int *>(smem_raw + lay.next) = 0u;
-            for (int s = 0; s < kStages; s++) {
-                mbar_init(bar_full + 8u * s, 1);
-                mbar_init(bar_empty + 8u * s, kTileSlices);
-            }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (tid == 0) {
+        *reinterpret_cast<unsigned int *>(smem_raw + lay.next) = 0u;
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(bar_full + 8u * s, 1);
+            mbar_init(bar_empty + 8u * s, kTileSlices);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const uint32_t seg_len = (uint32_t)(p.seg_end - p.seg_begin);        /* <= 2^31 */
 
-    if (warp == kConsumers) {
-        stream_producer(p, smem_raw, sbase, lay.stages, bar_full, bar_empty, s_tile, lane);
+    if (warp == kPairConsumers) {
+        /* the producer starts at once: the first tiles are on their way while the consumers fetch the bitmap */
+        stream_producer<kPairConsumers>(p, smem_raw, sbase, lay.stages, bar_full, bar_empty, s_tile, lane);
     } else {
+        {   /* both levels of the bitmap -> shared memory with cp.async, by the consumer warps (named barrier 1) */
+            const int n16 = (1 << (p.log1 - 7)) + (1 << (p.log2b - 7));
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.bm1);
+            for (int i = tid; i < n16; i += kPairConsumers * 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbase + lay.bitmap + 16u * i), "l"(src + i));
+            asm volatile("cp.async.commit_group;");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" :: "n"(kPairConsumers * 32) : "memory");
+        }
         const uint32_t sbm = sbase + lay.bitmap, sbm2 = sbase + lay.bitmap2;
         const uint32_t n_words = 1u << (p.log1 - 5);                     /* umulhi(hc, n_words) = hc >> (37 - log1) on the FMA pipe */
         const int l2b = L2B ? L2B : p.log2b;                             /* L2B != 0: compile-time shifts */
@@ -930,19 +943,11 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_pair_kernel(const __grid_con
         const uint32_t snext = sbase + lay.next;
         const uint32_t lane5 = (uint32_t)lane << 5;
         unsigned int n_cand = 0, head = 0;                               /* warp-uniform: entries [head, head + n_cand) of the ring */
-#ifdef ACB_STATIC_SLICES
-        unsigned int g_static = (unsigned)warp;
-#endif
 
         for (;;) {
-#ifdef ACB_STATIC_SLICES
-            const unsigned int g = g_static;                             /* experiment: slice g goes to warp g % kConsumers, no hand-out */
-            g_static += (unsigned)kConsumers;
-#else
             unsigned int g = 0;
             if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(g) : "r"(snext) : "memory");
             g = __shfl_sync(kFull, g, 0);
-#endif
             const uint32_t fill = g / (uint32_t)kTileSlices, slice_off = (g % (uint32_t)kTileSlices) * (uint32_t)kSliceBytes;
             const uint32_t stage = fill % (uint32_t)kStages;
             mbar_wait(bar_full + 8u * stage, (fill / (uint32_t)kStages) & 1u);
@@ -1353,8 +1358,8 @@ static int launch_pair(const ScanParams &p, int grid, cudaStream_t s) {
         CUDA_TRY(cudaFuncSetAttribute(acb_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         opted.store(smem, std::memory_order_relaxed);
     }
-    if (p.log2b == 17) acb_pair_kernel<17><<<grid, kFThreads, smem, s>>>(p);      /* the 2^20-bit level 1 of 10 k keys and more */
-    else acb_pair_kernel<0><<<grid, kFThreads, smem, s>>>(p);
+    if (p.log2b == 17) acb_pair_kernel<17><<<grid, kPairThreads, smem, s>>>(p);      /* the 2^20-bit level 1 of 10 k keys and more */
+    else acb_pair_kernel<0><<<grid, kPairThreads, smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     return ACB_OK;

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "random_batches or pathological or dense or golden" 2>&1 | tail -5 ) > gpurun_out/r2j_pytest.log
+cat gpurun_out/r2j_pytest.log
+( ACB_LIB=$PWD/pyahocorasick_b200/_native/libacb200_ahead.so timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "random_batches or pathological or dense" 2>&1 | tail -3 )
+run() { name=$1; var=$2; cfg=$3; lib=$PWD/pyahocorasick_b200/_native/libacb200${name:+_$name}.so
+  ACB_LIB=$lib timeout 200 python bench.py --config $cfg --steps 20 --warmup 5 --variant $var --no-cpu-baseline --no-e2e --no-latency 2>&1 | python tools/kline.py "lib=${name:-default} $cfg variant=$var"; }
+( run "" planted C2; run "" sparse C2; run ahead planted C2; run ahead sparse C2 ) 2>&1 | tee gpurun_out/r2j_variants.log
