@@ -506,8 +506,11 @@ def main():
             traffic = json.load(open(tpath)).get(cfg)
         except Exception:
             traffic = None
+    kernel_name = "acb_dfa_kernel"
+    if args.algo != "dfa":      # the PAIR placement (gram 4, stride 1: C2 / C4 key sets) has its own kernel
+        kernel_name = "acb_pair_kernel" if (A.flat()["filter_flags"] & 2) else "acb_stream_kernel"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "acb_stream_kernel" if args.algo != "dfa" else "acb_dfa_kernel",
+                "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes}
 
     # ---- CPU baseline + full parity check of its match list (rank 0, N=1 only) ------------------

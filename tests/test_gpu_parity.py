@@ -139,6 +139,42 @@ def test_pathological_overlaps():
         assert _records(A.find_all_batch(hay, algo=algo)) == want
 
 
+def test_pair_kernel_boundaries_and_dense_text():
+    """the PAIR kernel (gram 4, stride 1): occurrences across every kind of boundary it has -- the 16-byte runs of a
+    lane, the two halves of a 1 KiB slice, slices, tiles -- and text dense enough to overflow its item list (more than
+    64 pending positions in a slice) and its candidate ring (more than 64 candidates in a slice), against the oracle"""
+    rng = np.random.Generator(np.random.PCG64(20260923))
+    keys = synth.draw_keys(rng, synth.ALNUM, 600, 4, 16)
+    A = synth.build_automaton(keys)
+    f = A.flat()
+    assert f["filter_flags"] & 2 and f["gram_bytes"] == 4 and f["stride"] == 1          # PAIR placement -> acb_pair_kernel
+    O = _oracle_for(keys)
+    n = 200 * 1024 + 37                                                                # ten 20 KiB tiles and a ragged tail
+    hay = rng.choice(np.frombuffer(b"#%&*+-", dtype=np.uint8), size=n).astype(np.uint8)    # no key letter: only planted keys match
+    k = 0
+    for b in range(16, n - 32, 16):                                                     # every run / half / slice / tile boundary ...
+        key = np.frombuffer(keys[k % len(keys)], dtype=np.uint8)
+        start = b - 1 - (k % min(15, len(key) - 1))                                     # ... is crossed by a key
+        if (b // 16) % 3 == 0:
+            hay[start:start + len(key)] = key
+        k += 1
+    hay[n - 4:] = np.frombuffer(keys[[len(x) for x in keys].index(4)], dtype=np.uint8)  # a key that ends with the buffer
+    off = np.array([0, n], dtype=np.int64)
+    want = _want_sorted(O, keys, hay, off)
+    assert len(want) > 3000
+    assert _records(A.find_all_batch((hay, off), algo="filter")) == want
+    roff = np.concatenate([[0], np.sort(rng.integers(0, n, size=300)), [n]]).astype(np.int64)
+    assert _records(A.find_all_batch((hay, roff), algo="filter")) == _want_sorted(O, keys, hay, roff)
+    # dense text: one short key back to back -- every position of a slice is pending, every one is a candidate
+    dense_keys = [b"abab", b"baba", b"ababab", b"abcd"]
+    D = synth.build_automaton(dense_keys)
+    assert D.flat()["filter_flags"] & 2
+    OD = _oracle_for(dense_keys)
+    dh = np.frombuffer(b"ab" * 30000 + b"abcd" * 100 + b"ab" * 5000, dtype=np.uint8).copy()
+    doff = np.array([0, 1000, 1001, 40000, dh.size], dtype=np.int64)
+    assert _records(D.find_all_batch((dh, doff), algo="filter")) == _want_sorted(OD, dense_keys, dh, doff)
+
+
 def test_unicode_and_sequence_flavours_on_gpu():
     U = ac.flavour("unicode")
     A = U.Automaton()
