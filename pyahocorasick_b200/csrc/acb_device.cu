@@ -1,21 +1,21 @@
 /*
  * acb_device.cu -- sm_100a scan kernels and the device half of the C ABI (include/acb200.h).
  *
- * ACB_ALGO_FILTER (the fast path) is ONE launch per <= 2 GiB segment of the batch:
+ * ACB_ALGO_FILTER (the fast path) is ONE launch per <= 2 GiB segment of the batch, of one of two streaming kernels
+ * (both persistent, one CTA per SM, warp specialised):
  *
- *  acb_stream_kernel<NW,STRIDE,MODE>   persistent, one CTA per SM, warp specialised.
- *      A producer warp claims 16 KiB tiles of the flat haystack buffer from an atomic counter and moves them
- *      into a 4-stage shared-memory ring with cp.async.bulk (the TMA engine) and mbarriers; sixteen consumer
- *      warps read their 1 KiB slice of a stage (32 consecutive bytes per lane), hash the gram at every probe
- *      position and test it against the gram bitmap held in shared memory (a blocked Bloom filter, two bits per
- *      gram in one word; PAIR mode: one word serves two adjacent positions).  Start-anchored search: the rare
- *      survivors get the second hash of their gram (read back from the stage, still resident) and are queued
- *      per warp; between slices a warp resolves its queue, 32 candidates at a time, through the anchor table in
- *      global memory (one 32-byte slot): a UNIQUE anchor carries the only key that can match there, which is
- *      compared with the text directly; a MULTI anchor (keys sharing that prefix) walks the trie through the
- *      column-major goto table.  No failure links are followed: an occurrence is found exactly once, from its
- *      first byte, so the result set equals what the reference produces by walking fail chains at every
- *      position (src/AutomatonSearchIter.c:157-197, src/Automaton.c:693-714).
+ *  acb_stream_kernel<NW,STRIDE,MODE>   SINGLE placements of the gram filter (any gram length and stride)
+ *  acb_pair_kernel<L2B>                PAIR placement (gram 4, stride 1, 1-byte letters: one filter word per two positions)
+ *      A producer warp claims 20 KiB tiles of the flat haystack buffer from an atomic counter and moves them
+ *      into a 3-stage shared-memory ring with cp.async.bulk (the TMA engine) and mbarriers; the consumer warps take
+ *      1 KiB slices of the stages from a shared-memory counter, hash the gram at every probe position and test it
+ *      against the gram bitmap held in shared memory.  Start-anchored search: the rare survivors get the second
+ *      hash of their gram (read back from the stage, still resident) and are collected per warp; a warp that has 32 of
+ *      them resolves them through the anchor table in global memory (one 32-byte slot): a UNIQUE anchor carries the
+ *      only key that can match there, which is compared with the text directly; a MULTI anchor (keys sharing that
+ *      prefix) walks the trie through the column-major goto table.  No failure links are followed: an occurrence is
+ *      found exactly once, from its first byte, so the result set equals what the reference produces by walking fail
+ *      chains at every position (src/AutomatonSearchIter.c:157-197, src/Automaton.c:693-714).
  *
  *  acb_dfa_kernel                      (ACB_ALGO_DFA)
  *      The textbook automaton: goto, else fail until root (src/trie.c:177-194), outputs from CSR lists.  One
@@ -26,8 +26,8 @@
  *      iter_long: the reference's longest-match walk (src/AutomatonSearchIterLong.c:89-153) replayed letter by
  *      letter on the flattened tables, one lane per haystack.
  *
- * Match records are compacted per warp in shared memory and appended to the global buffer with one atomicAdd
- * per warp flush; acb_sort_matches_device puts them into the reference's order with one radix sort.
+ * Match records are appended to the global buffer with one atomicAdd per warp flush (stream kernel: staged in shared
+ * memory) or per resolve turn (pair kernel); acb_sort_matches_device puts them into the reference's order with one radix sort.
  */
 #include "acb_internal.h"
 #include "acb_hash.h"
@@ -598,9 +598,9 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         unsigned int *s_next = reinterpret_cast<unsigned int *>(smem_raw + lay.next);
         unsigned int n_cand = 0;                                         /* warp-uniform */
 
-        /* Slices are handed out dynamically: slice g is slice g % kConsumers of fill g / kConsumers.  A warp that is busy
-           resolving candidates simply takes fewer slices.  With exactly kConsumers warps, kConsumers slices per fill and
-           one slice held per warp, a waiter can never be a whole ring turn ahead of the barrier phase it waits for. */
+        /* Slices are handed out dynamically: slice g is slice g % kTileSlices of fill g / kTileSlices.  A warp that is busy
+           resolving candidates simply takes fewer slices.  One slice held per warp and slices handed out in order: a
+           waiter can never be a whole ring turn ahead of the barrier phase it waits for (kTileSlices above). */
         for (;;) {
             unsigned int g = 0;
             if (lane == 0) g = atomicAdd(s_next, 1u);
