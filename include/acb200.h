@@ -248,6 +248,16 @@ void acb_release_records(acb_match *ptr, int64_t cap);
 int acb_sort_matches_device(acb_table *tb, acb_match *d_records, int64_t n, int64_t n_hay,
                             int64_t max_hay_letters, void *stream);
 
+/* iter_long streaming (src/AutomatonSearchIterLong.c:156-212: set() keeps iter->state): the walk state carried from one
+ * chunk to the next stays a state id, nothing of the old text is scanned again.
+ * acb_table_set_long_state: the state (BFS id, 0 = root) in which haystack 0 of the NEXT ACB_ALGO_LONG scan starts; one
+ *   shot, every other haystack and every later scan start at the root.  ACB_EINVAL for an id that is not a state.
+ * acb_table_get_long_state: the state in which haystack 0 of the LAST ACB_ALGO_LONG scan ended (its text exhausted,
+ *   a match still pending at the end reported: then the root).  After acb_scan_device the caller synchronises its
+ *   stream first. */
+int acb_table_set_long_state(acb_table *tb, int32_t state);
+int acb_table_get_long_state(acb_table *tb, int32_t *state);
+
 /* number of kernel launches issued by this library so far (bench.py's gpu_launches) */
 int64_t acb_launch_count(void);
 

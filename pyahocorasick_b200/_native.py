@@ -87,6 +87,8 @@ def lib() -> ctypes.CDLL:
         "acb_take_records": (ctypes.c_int, [vp, ctypes.POINTER(vp), pi64, pi64]),
         "acb_release_records": (None, [vp, i64]),
         "acb_sort_matches_device": (ctypes.c_int, [vp, vp, i64, i64, i64, vp]),
+        "acb_table_set_long_state": (ctypes.c_int, [vp, ctypes.c_int32]),
+        "acb_table_get_long_state": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_int32)]),
         "acb_launch_count": (i64, []),
         "acb_set_kernel_timing": (ctypes.c_int, [ctypes.c_int]),
         "acb_last_kernel_ms": (ctypes.c_float, []),
@@ -111,7 +113,7 @@ EXPORTED_SYMBOLS = [
     "acb_trie_content_hash", "acb_trie_flat_save", "acb_trie_flat_load",
     "acb_trie_export_nodes", "acb_trie_import_nodes", "acb_node_records_span",
     "acb_device_count", "acb_table_upload", "acb_table_free", "acb_table_device_bytes",
-    "acb_scan_device", "acb_scan_host", "acb_copy_records", "acb_take_records", "acb_release_records", "acb_sort_matches_device", "acb_launch_count", "acb_set_kernel_timing",
+    "acb_scan_device", "acb_scan_host", "acb_copy_records", "acb_take_records", "acb_release_records", "acb_sort_matches_device", "acb_table_set_long_state", "acb_table_get_long_state", "acb_launch_count", "acb_set_kernel_timing",
     "acb_last_kernel_ms", "acb_last_error", "acb_abi_version",
 ]
 

@@ -644,9 +644,12 @@ class Automaton:
     # ------------------------------------------------------------------ GPU scan plumbing
     @_locked
     def _scan_flat(self, flat: np.ndarray, offsets: Optional[np.ndarray], n_hay: int, stride_bytes: int,
-                   algo: str = "auto", sort: bool = True, device: Optional[int] = None, narrow: bool = False) -> np.ndarray:
+                   algo: str = "auto", sort: bool = True, device: Optional[int] = None, narrow: bool = False,
+                   long_state: Optional[int] = None) -> np.ndarray:
         """flat uint8 buffer (+ int64 byte offsets or a fixed stride) -> sorted match records.
-        narrow=True: the buffer holds 1-byte letters of a unicode-flavour automaton (latin-1 path)."""
+        narrow=True: the buffer holds 1-byte letters of a unicode-flavour automaton (latin-1 path).
+        long_state (algo "long", one haystack): the state the walk starts in; the state it ends in is left in
+        self._long_state_out (iter_long streaming, acb_table_set_long_state / acb_table_get_long_state)."""
         if narrow:
             core = self._ensure_narrow(device)
             if core is None:
@@ -658,6 +661,8 @@ class Automaton:
         cap = max(self._match_cap, 1 << 12, 2 * n_hay)        # device-side capacity; grown on overflow
         found = ctypes.c_int64(0)
         while True:
+            if long_state is not None:
+                N.check(self._lib.acb_table_set_long_state(tb, int(long_state)))      # one shot: again before a retry
             rc = self._lib.acb_scan_host(tb, N.ptr(flat) if total else None, total,
                                          N.ptr(offsets) if offsets is not None else None, n_hay, stride_bytes,
                                          None, cap, ctypes.byref(found), N.ALGOS[algo], 1 if sort else 0)
@@ -666,6 +671,10 @@ class Automaton:
                 self._match_cap = cap
                 continue
             N.check(rc)
+            if long_state is not None:
+                st = ctypes.c_int32(0)
+                N.check(self._lib.acb_table_get_long_state(tb, ctypes.byref(st)))
+                self._long_state_out = int(st.value)
             if not found.value:
                 return np.empty(0, dtype=N.MATCH_DTYPE)
             # no copy: the records stay in the pinned buffer the D2H landed in; it returns to the library's pool
@@ -719,7 +728,7 @@ class Automaton:
             rec = rec[np.lexsort((-kl[rec["key_id"]], rec["end_index"], rec["hay_id"]))]
         return rec
 
-    def _scan_one(self, letters: np.ndarray, algo: str = "auto") -> np.ndarray:
+    def _scan_one(self, letters: np.ndarray, algo: str = "auto", long_state: Optional[int] = None) -> np.ndarray:
         narrow = self._uses_narrow() and letters.dtype == np.uint8 and algo != "long"
         if self._uses_narrow() and letters.dtype == np.uint8 and not narrow:
             letters = letters.astype("<u4")                  # iter_long never runs on the latin-1 automaton
@@ -728,6 +737,8 @@ class Automaton:
             return np.empty(0, dtype=N.MATCH_DTYPE)
         if narrow:
             return self._scan_flat(flat, None, 1, int(flat.size), algo=algo, narrow=True)
+        if long_state is not None:
+            return self._scan_flat(flat, None, 1, int(flat.size), algo=algo, long_state=long_state)
         return self._scan_flat(flat, None, 1, int(flat.size), algo=algo)
 
     def _require_automaton(self):
@@ -982,31 +993,34 @@ class AutomatonSearchIterLong:
 
     * the walk restarts from the root after every match it returns (:104-112), so once a match of the current
       chunk has been returned and the chunk is not exhausted, the carried state is the root;
-    * after exhaustion the state is the node reached from the last restart point, i.e. a function of the
-      letters since that point -- `_carry` keeps exactly those letters, and the next chunk is scanned as
-      `carry + chunk` (the replay is deterministic, so it reports nothing inside the carry and reaches the same
-      state at the seam).  A stream without any match therefore keeps growing the carry; that is the price of
-      having no CPU search path.
+    * after exhaustion it is the node the walk has reached -- the kernel hands that state id back
+      (`acb_table_get_long_state`) and the next chunk starts in it (`acb_table_set_long_state`): only the new
+      chunk is uploaded and scanned, whatever the length of the stream (the first version re-scanned the letters
+      since the last restart point, which grows without bound on a stream without matches);
+    * a chunk of which nothing was consumed leaves the state it was entered with.
     """
 
     def __init__(self, A: Automaton, letters: np.ndarray, start: int, end: int):
         self._A = A
         self._version = A._version
         self._shift = 0
-        self._carry = letters[:0]
+        self._state = 0                                       # iter->state, as a state id of the flattened automaton
         self._load(letters, start, end)
 
     def _load(self, letters: np.ndarray, start: int, end: int) -> None:
         seg = letters[start:end] if end > start else letters[:0]
-        carry = self._carry
-        if len(carry) and carry.dtype != seg.dtype:           # latin-1 (narrow) next to UCS-4 letters: widen both
-            carry, seg = carry.astype("<u4"), seg.astype("<u4")
-        text = np.concatenate([carry, seg]) if len(carry) else seg
-        rec = self._A._scan_one(text, algo="long") if len(text) else np.empty(0, dtype=N.MATCH_DTYPE)
-        ends = (rec["end_index"].astype(np.int64) - len(carry) + start).tolist()
+        A = self._A
+        self._state_in = self._state if self._version == A._version else 0
+        if len(seg):
+            rec = A._scan_one(seg, algo="long", long_state=self._state_in)
+            self._state_out = A._long_state_out
+        else:
+            rec = np.empty(0, dtype=N.MATCH_DTYPE)
+            self._state_out = self._state_in
+        ends = (rec["end_index"].astype(np.int64) + start).tolist()
         self._matches = list(zip(ends, rec["key_id"].tolist()))
         self._cursor = 0
-        self._carry, self._seg = carry, seg
+        self._seg = seg
         self._start, self._end = start, end
         self._index = start - 1                               # :34
         self._exhausted = False
@@ -1037,20 +1051,16 @@ class AutomatonSearchIterLong:
         reset = bool(args[1]) if len(args) >= 2 else False
         if reset:
             self._shift = 0
-            self._carry = letters[:0]
+            self._state = 0
         else:
             if self._index >= 0:
                 self._shift += self._index                    # :195-196
             if self._exhausted:
-                if self._cursor:                              # restart point: just after the last match of this chunk
-                    self._carry = self._seg[self._matches[self._cursor - 1][0] + 1 - self._start:]
-                elif len(self._carry):
-                    self._carry = np.concatenate([self._carry, self._seg])
-                else:
-                    self._carry = self._seg
+                self._state = self._state_out                 # the whole chunk was walked: the state it ended in
             elif self._cursor:
-                self._carry = letters[:0]                     # a match was just returned: the walk is at the root
-            # else: nothing of the old chunk was consumed, state and carry are what they were
+                self._state = 0                               # a match was just returned: the walk is at the root
+            else:
+                self._state = self._state_in                  # nothing of the old chunk was consumed
         self._load(letters, 0, len(letters))
         self._index = -1                                      # :198
 

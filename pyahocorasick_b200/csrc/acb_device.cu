@@ -134,6 +134,8 @@ struct ScanParams {
     acb_match *out;
     long long cap;
     unsigned long long *count;
+    int32_t long_init;             /* ACB_ALGO_LONG: the state haystack 0 starts in (iter_long streaming) */
+    int32_t *long_final;           /* ... and where the state it ends in goes (may be null) */
     long long seg_begin, seg_end;  /* byte range of this launch */
     unsigned int n_tiles;          /* kTileBytes tiles in the segment */
     unsigned int *work_ctr;        /* [0] next tile, [1] CTAs done */
@@ -1150,7 +1152,7 @@ __global__ void __launch_bounds__(kDfaThreads) acb_long_kernel(const __grid_cons
     const long long he = p.offsets ? __ldg(p.offsets + h + 1) : hs + p.stride_bytes;
     const long long n = (he - hs) / p.L;                       /* letters */
     const uint8_t *text = p.hay + hs;
-    int32_t state = 0, last_node = -1;
+    int32_t state = (h == 0) ? p.long_init : 0, last_node = -1;     /* the walk of a stream goes on where the last chunk left it */
     long long index = -1, last_index = -1;
     for (;;) {
         if (last_node >= 0) {                                   /* return_output */
@@ -1192,6 +1194,7 @@ __global__ void __launch_bounds__(kDfaThreads) acb_long_kernel(const __grid_cons
         }
         if (!emit && last_node < 0) break;                      /* StopIteration */
     }
+    if (h == 0 && p.long_final) *p.long_final = state;
 }
 
 __global__ void acb_flag_goto_kernel(int32_t *gto, const int32_t *key_of, size_t n) {
@@ -1217,6 +1220,8 @@ struct acb_table {
     uint32_t *d_bm1 = nullptr, *d_bm3 = nullptr, *d_anchors = nullptr;
     unsigned int *d_work = nullptr;
     uint2 *d_cand = nullptr;                 /* candidate lists of the stream kernel's consumer warps (kWarpCand entries each) */
+    int32_t long_init = 0;                   /* iter_long streaming: start state of haystack 0 of the next ACB_ALGO_LONG scan */
+    int32_t *d_long_final = nullptr;         /* ... and the state it ended in */
     long long dev_bytes = 0;
     std::vector<int32_t> key_len;            /* host copy, for sorting records */
     /* workspace of acb_scan_host */
@@ -1258,7 +1263,7 @@ extern "C" void acb_table_free(acb_table *tb) {
     cudaSetDevice(tb->device);
     cudaFree(tb->d_lfail); cudaFree(tb->d_cls); cudaFree(tb->d_goto); cudaFree(tb->d_fail); cudaFree(tb->d_keyof);
     cudaFree(tb->d_outptr); cudaFree(tb->d_outidx); cudaFree(tb->d_keylen); cudaFree(tb->d_bm1); cudaFree(tb->d_bm3); cudaFree(tb->d_anchors);
-    cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
+    cudaFree(tb->d_sort); cudaFree(tb->d_work); cudaFree(tb->d_cand); cudaFree(tb->d_long_final); cudaFree(tb->w_hay); cudaFree(tb->w_off); cudaFree(tb->w_out); cudaFree(tb->w_count);
     if (tb->h_count) cudaFreeHost(tb->h_count);
     if (tb->h_out) cudaFreeHost(tb->h_out);
     if (tb->ev0) cudaEventDestroy(tb->ev0);
@@ -1480,6 +1485,10 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
         if (e != cudaSuccess) { acb_set_error("DFA kernel launch failed: %s", cudaGetErrorString(e)); return ACB_ECUDA; }
         g_launches.fetch_add(1);
     } else if (algo == ACB_ALGO_LONG) {
+        if (!tb->d_long_final) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&tb->d_long_final), sizeof(int32_t)));
+        p.long_init = tb->long_init;
+        p.long_final = tb->d_long_final;
+        tb->long_init = 0;                                      /* one shot */
         long long grid = (n_hay + kDfaThreads - 1) / kDfaThreads;
         acb_long_kernel<<<(unsigned)grid, kDfaThreads, 0, s>>>(p);
         cudaError_t e = cudaGetLastError();
@@ -1496,6 +1505,21 @@ extern "C" int acb_scan_device(acb_table *tb, const uint8_t *d_hay, int64_t tota
         CUDA_TRY(cudaEventElapsedTime(&ms, tb->ev0, tb->ev1));
         g_last_ms = ms;
     }
+    return ACB_OK;
+}
+
+extern "C" int acb_table_set_long_state(acb_table *tb, int32_t state) {
+    if (!tb || state < 0 || state >= tb->S) { acb_set_error("not a state of this automaton"); return ACB_EINVAL; }
+    tb->long_init = state;
+    return ACB_OK;
+}
+
+extern "C" int acb_table_get_long_state(acb_table *tb, int32_t *state) {
+    if (!tb || !state) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    *state = 0;
+    if (!tb->d_long_final) return ACB_OK;                    /* no ACB_ALGO_LONG scan yet */
+    CUDA_TRY(cudaSetDevice(tb->device));
+    CUDA_TRY(cudaMemcpy(state, tb->d_long_final, sizeof(int32_t), cudaMemcpyDeviceToHost));
     return ACB_OK;
 }
 

@@ -229,9 +229,10 @@ def emul_dfa(f, buf, offsets=None, stride_bytes=0, span=64):
     return _sorted(recs, key_len)
 
 
-def emul_long(f, buf, offsets=None, stride_bytes=0):
+def emul_long(f, buf, offsets=None, stride_bytes=0, init_state=0, want_state=False):
     """acb_long_kernel: the reference's iter_long state machine (src/AutomatonSearchIterLong.c:89-153) on the
-    flattened tables, one haystack at a time, letter by letter."""
+    flattened tables, one haystack at a time, letter by letter.  init_state: the state haystack 0 starts in
+    (acb_table_set_long_state); want_state: also return the state it ended in (acb_table_get_long_state)."""
     L = f["letter_bytes"]
     total = len(buf)
     n_hay = (len(offsets) - 1) if offsets is not None else total // stride_bytes
@@ -250,7 +251,7 @@ def emul_long(f, buf, offsets=None, stride_bytes=0):
                     return -1
             return st
 
-        state, index, last_node, last_index = 0, -1, -1, -1
+        state, index, last_node, last_index = (init_state if h == 0 else 0), -1, -1, -1
         while True:
             if last_node >= 0:
                 recs.append((h, last_index, int(key_of[last_node])))
@@ -283,6 +284,10 @@ def emul_long(f, buf, offsets=None, stride_bytes=0):
                             break
             if not emit and last_node < 0:
                 break
+        if h == 0:
+            final_state = state
+    if want_state:
+        return _sorted(recs, f["key_len"]), (final_state if n_hay else init_state)
     return _sorted(recs, f["key_len"])
 
 
@@ -293,14 +298,17 @@ def install(monkeypatch_or_none, algo="filter"):
 
     default_algo = algo
 
-    def fake_scan_flat(self, flat, offsets, n_hay, stride_bytes, algo="auto", sort=True, device=None, narrow=False):
+    def fake_scan_flat(self, flat, offsets, n_hay, stride_bytes, algo="auto", sort=True, device=None, narrow=False, long_state=None):
         f = self.flat(narrow=narrow)
         if f is None:
             return np.empty(0, dtype=N.MATCH_DTYPE)
         if algo == "auto":
             algo = default_algo
         fn = {"dfa": emul_dfa, "long": emul_long}.get(algo, emul_filter)
-        recs = fn(f, np.asarray(flat, dtype=np.uint8), offsets, stride_bytes)
+        if long_state is not None:
+            recs, self._long_state_out = emul_long(f, np.asarray(flat, dtype=np.uint8), offsets, stride_bytes, init_state=long_state, want_state=True)
+        else:
+            recs = fn(f, np.asarray(flat, dtype=np.uint8), offsets, stride_bytes)
         out = np.empty(len(recs), dtype=N.MATCH_DTYPE)
         for i, r in enumerate(recs):
             out[i] = r

@@ -28,8 +28,8 @@ SC = all_scenarios()
 def test_golden_on_gpu(sc, algo, monkeypatch):
     real = am.Automaton._scan_flat
 
-    def forced(self, flat, offsets, n_hay, stride_bytes, algo="auto", sort=True, device=None, narrow=False, _a=algo):
-        return real(self, flat, offsets, n_hay, stride_bytes, algo=_a if algo == "auto" else algo, sort=sort, device=device, narrow=narrow)
+    def forced(self, flat, offsets, n_hay, stride_bytes, algo="auto", sort=True, device=None, narrow=False, _a=algo, **kw):
+        return real(self, flat, offsets, n_hay, stride_bytes, algo=_a if algo == "auto" else algo, sort=sort, device=device, narrow=narrow, **kw)
     monkeypatch.setattr(am.Automaton, "_scan_flat", forced)
     bad = run_ops(ac.flavour(sc["flavour"]), sc, record=False)
     assert not bad, bad[:3]

@@ -85,3 +85,58 @@ def test_iter_long_set_documented_example_and_errors(monkeypatch):
     A.add_word(b"zzz", 9)
     with pytest.raises(ValueError, match="has changed"):
         next(it)
+
+
+def _stream_case(mod):
+    A = mod.Automaton()
+    for i, k in enumerate([b"abcd", b"bcdx", b"q", b"abcdefghij"]):
+        A.add_word(k, i)
+    A.make_automaton()
+    return A
+
+
+def test_iter_long_stream_uploads_only_the_new_chunk(monkeypatch):
+    """a stream without matches: every set() scans its own chunk and nothing else (the walk's state travels as a
+    state id, acb_table_set_long_state / acb_table_get_long_state); keys spread over many chunks are still found"""
+    fake = emul.install(monkeypatch, "filter")
+    sizes = []
+
+    def counting(self, flat, *a, **kw):
+        sizes.append(int(np.asarray(flat).size))
+        return fake(self, flat, *a, **kw)
+    from pyahocorasick_b200 import automaton as am
+    monkeypatch.setattr(am.Automaton, "_scan_flat", counting)
+    mod = pkg.flavour("bytes")
+    A = _stream_case(mod)
+    it = A.iter_long(b"z" * 100)
+    assert list(it) == []
+    for _ in range(50):
+        it.set(b"zab" * 33 + b"z")                        # ends inside nothing; "ab" prefixes never complete
+        assert list(it) == []
+    assert sizes == [100] * 51
+    pos = 100 * 51
+    for ch in (b"a", b"b", b"c", b"d", b"e"):              # "abcd" over four chunks, reported when the walk fails on "e"... or at the end
+        it.set(ch)
+        got = list(it)
+        pos += 1
+        if ch == b"d":
+            assert got == [(pos - 1, 0)]                   # end of the chunk with a pending match: reported at once
+        else:
+            assert got == []
+    assert sizes[-5:] == [1] * 5
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_iter_long_long_stream_on_gpu():
+    """the same stream through the real ACB_ALGO_LONG kernel, against the reference extension"""
+    ref, mod = oracle.ref_module("bytes"), pkg.flavour("bytes")
+    A, R = _stream_case(mod), _stream_case(ref)
+    rng = np.random.default_rng(5)
+    ia, ir = A.iter_long(b"z" * 100), R.iter_long(b"z" * 100)
+    assert list(ia) == list(ir)
+    for _ in range(200):
+        n = int(rng.integers(0, 40))
+        chunk = bytes(rng.choice(np.frombuffer(b"abcdxzq", dtype=np.uint8), size=n).tolist())
+        ia.set(chunk), ir.set(chunk)
+        assert list(ia) == list(ir)
