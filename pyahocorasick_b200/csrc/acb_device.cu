@@ -67,9 +67,6 @@ namespace {
 #ifndef ACB_LANE_BYTES
 #define ACB_LANE_BYTES 32
 #endif
-#ifndef ACB_PHASE_FILLS
-#define ACB_PHASE_FILLS 16
-#endif
 constexpr int kConsumers    = ACB_CONSUMERS;          /* consumer warps of the stream kernel           */
 constexpr int kFThreads     = (kConsumers + 1) * 32;  /* + the producer warp                           */
 constexpr int kLaneBytes    = ACB_LANE_BYTES;         /* text bytes per lane and iteration             */
@@ -435,7 +432,7 @@ __host__ __device__ inline StreamSmem stream_smem(int log1) {
 /* A consumer warp's collected candidates {position in the segment, tag}, entries [0, n) of its list, through the anchor
  * table: one entry per lane and turn, the text at the position and the anchor slot its tag hashes to loaded together
  * (one round trip; a second entry per lane makes ptxas spill inside the probe loop).  Text and anchors come from L2:
- * the bytes were streamed at most kPhaseFills tiles ago.  Records are flushed when the staging area is a quarter full. */
+ * the bytes were streamed microseconds ago.  Records are flushed when the staging area is a quarter full. */
 __device__ __forceinline__ void resolve_backlog(const ScanParams &p, uint8_t *smem_raw, unsigned int n) {
     /* everything but n is rebuilt here rather than kept alive across the probe loop */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -535,15 +532,14 @@ __device__ __forceinline__ void stream_producer(const ScanParams &p, uint8_t *sm
 /* acb_stream_kernel: persistent, one CTA per SM, warp specialised:
  *   producer  (1 warp)          claims tiles from a global counter and keeps the shared-memory ring full
  *                               (cp.async.bulk + mbarrier)
- *   consumers (kConsumers)      slice `warp` of every tile: the lane's bytes go to registers, the stage is released at
- *                               once, every probe position is tested against the gram bitmap in shared memory; a lane
- *                               whose bytes hold a survivor appends {position of its bytes, hit mask} to the warp's own
- *                               candidate list in global memory (the cursor is a register: no atomic, a plain store
- *                               nobody waits for).  Every kPhaseFills slices the warp takes its list through the anchor
- *                               table (resolve_backlog): the consumers of a CTA move in step, so they all do this at
- *                               about the same fill while the producer refills the ring, and the text they compare with
- *                               is still in L2.  A list has room for every lane of every slice of a phase: it cannot
- *                               overflow. */
+ *   consumers (kConsumers)      take 1 KiB slices from a shared-memory counter: the lane's 32 bytes go to registers, every
+ *                               probe position is tested against the gram bitmap in shared memory; the pending bits of all
+ *                               lanes become work items spread evenly over the warp, every item reads its text back from
+ *                               the stage (still held), probes the tag bitmap (dense key sets) and appends {position,
+ *                               anchor tag} to the warp's own candidate list in global memory (the cursor is a register:
+ *                               no atomic, a plain store nobody waits for; a list holds a slice's worst case, it cannot
+ *                               overflow).  The stage is released, and a warp that has 32 candidates takes them through
+ *                               the anchor table (resolve_backlog) while the other warps stream on. */
 template <int NW, int STRIDE, int MODE>
 __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -588,7 +584,6 @@ __global__ void __launch_bounds__(kFThreads, 1) acb_stream_kernel(const __grid_c
         uint32_t mul[NW];
 #pragma unroll
         for (int k = 0; k < NW; k++) mul[k] = p.mul1[k];
-        const uint32_t slice_off = (uint32_t)warp * kSliceBytes;
         uint2 *list = p.cand + ((size_t)blockIdx.x * kConsumers + warp) * kWarpCand;
         uint32_t mul2[NW];
 #pragma unroll
