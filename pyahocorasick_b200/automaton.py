@@ -862,7 +862,7 @@ class Automaton:
         # different: which match it keeps depends on the whole trie (a non-latin-1 key whose prefix is latin-1 adds
         # nodes the walk passes through, src/AutomatonSearchIterLong.c:118-126), so it always runs on the full one
         if not self._UNICODE and self._key_type == KEY_STRING and isinstance(haystacks, (list, tuple)) and haystacks \
-                and all(type(h) is bytes for h in haystacks):
+                and set(map(type, haystacks)) == {bytes}:       # C-level pass, 3 x faster than a generator with all()
             # the common drop-in input, a list of bytes objects: one join instead of an array per haystack
             n = len(haystacks)
             offs = np.zeros(n + 1, dtype=np.int64)

@@ -1025,7 +1025,11 @@ __global__ void __launch_bounds__(kPairThreads, 1) acb_pair_kernel(const __grid_
                 }
                 __syncwarp();
                 for (unsigned int base = 0; base < n_items;) {
-                    if (n_cand == (unsigned)kPairRing) { pair_resolve(p, sring, head, 32u); head += 32u; n_cand -= 32u; continue; }   /* one slice alone filled the ring */
+                    if (n_cand == (unsigned)kPairRing) {                /* one slice alone filled the ring */
+                        __syncwarp();                                    /* the entries were written by other lanes */
+                        pair_resolve(p, sring, head, 32u); head += 32u; n_cand -= 32u;
+                        continue;
+                    }
                     unsigned int take = n_items - base;
                     if (take > 32u) take = 32u;
                     if (take > (unsigned)kPairRing - n_cand) take = (unsigned)kPairRing - n_cand;
