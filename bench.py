@@ -508,7 +508,7 @@ def main():
             traffic = None
     kernel_name = "acb_dfa_kernel"
     if args.algo != "dfa":      # the PAIR placement (gram 4, stride 1: C2 / C4 key sets) has its own kernel
-        kernel_name = "acb_pair_kernel" if (A.flat()["filter_flags"] & 2) else "acb_stream_kernel"
+        kernel_name = "acb_pair_kernel" if (A.filter_shape()["filter_flags"] & 2) else "acb_stream_kernel"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes}

@@ -130,6 +130,7 @@ class Automaton:
     """Drop-in for ``ahocorasick.Automaton`` (src/Automaton.c:96-181 constructor)."""
 
     _UNICODE = True           # flavour; the bytes flavour subclass overrides it
+    _long_state_out = 0       # state the last iter_long chunk ended in (acb_table_get_long_state), see AutomatonSearchIterLong
 
     # ------------------------------------------------------------------ construction
     def __init__(self, *args):
@@ -609,6 +610,15 @@ class Automaton:
         self._table = tb
         self._table_device = device
         return tb
+
+    @_locked
+    def filter_shape(self) -> dict:
+        """The prefilter the host chose for this key set (no table copies): gram length, probe stride, bitmap sizes
+        and the placement flags -- ACB_FILTER_PAIR (2) means the scan runs on acb_pair_kernel, else acb_stream_kernel."""
+        fv = N.FlatView()
+        N.check(self._lib.acb_trie_flat_view(self._trie, ctypes.byref(fv)))
+        return dict(gram_bytes=fv.gram_bytes, stride=fv.stride, log2_bits1=fv.log2_bits1, log2_bits2=fv.log2_bits2,
+                    log2_bits3=fv.log2_bits3, log2_anchor_slots=fv.log2_anchor_slots, filter_flags=fv.filter_flags)
 
     @_locked
     def flat(self, narrow: bool = False) -> dict:
