@@ -116,6 +116,22 @@ def test_filter_choice_for_baseline_configs():
     assert (used[:, 1].astype(np.int32) >= 0).mean() > 0.95               # almost all UNIQUE
 
 
+def test_filter_choice_for_the_dense_key_sets():
+    """BASELINE configs 5 and 3 keep the SINGLE placement (acb_stream_kernel): 100 k four-byte grams would fill a
+    pair filter's level 1 to 19 % per role; the C4 key set is C2's (PAIR, acb_pair_kernel)"""
+    rng = np.random.Generator(np.random.PCG64(1005))
+    keys = synth.draw_keys(rng, synth.ALNUM, 100_000, 4, 16)                 # config 5's key set
+    s5 = synth.build_automaton(keys).filter_shape()
+    assert (s5["gram_bytes"], s5["stride"], s5["log2_bits1"]) == (4, 1, 20)
+    assert s5["filter_flags"] == emul.FILTER_WIDE and s5["log2_bits2"] == 0 and s5["log2_bits3"] >= 20      # tag bitmap in L2
+    rng = np.random.Generator(np.random.PCG64(3))
+    dna = synth.draw_keys(rng, synth.DNA, 100_000, 20, 20)                   # config 3's shape
+    s3 = synth.build_automaton(dna).filter_shape()
+    assert s3["stride"] == 8 and s3["gram_bytes"] == 13 and not (s3["filter_flags"] & emul.FILTER_PAIR)
+    s4 = synth.build_automaton(synth.make("C4", scale=0.001).keys).filter_shape()
+    assert s4["filter_flags"] == emul.FILTER_PAIR and s4["log2_bits2"] == 17
+
+
 def test_state_machine_and_removal():
     A = B.Automaton()
     assert A.kind == ac.EMPTY and A.make_automaton() is False
