@@ -1339,11 +1339,16 @@ extern "C" float acb_last_kernel_ms(void) { return g_last_ms; }
 
 /* ------------------------------------------------------------- launching */
 
+constexpr int kMaxDevices = 64;                              /* opt-in caches below are per device */
+
 template <int NW, int STRIDE, int MODE>
 static int launch_stream_m(const ScanParams &p, int grid, cudaStream_t s) {
     auto kern = acb_stream_kernel<NW, STRIDE, MODE>;
     const size_t smem = stream_smem(p.log1).total;
-    static std::atomic<size_t> opted{0};                     /* per instantiation: the largest size opted into so far */
+    static std::atomic<size_t> opted_dev[kMaxDevices];       /* per instantiation and device: the largest size opted into so far */
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));                           /* the attribute belongs to the current device's context */
+    std::atomic<size_t> &opted = opted_dev[dev % kMaxDevices];
     if (opted.load(std::memory_order_relaxed) < smem) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         opted.store(smem, std::memory_order_relaxed);
@@ -1356,7 +1361,10 @@ static int launch_stream_m(const ScanParams &p, int grid, cudaStream_t s) {
 
 static int launch_pair(const ScanParams &p, int grid, cudaStream_t s) {
     const size_t smem = pair_smem(p.log1, p.log2b).total;
-    static std::atomic<size_t> opted{0};
+    static std::atomic<size_t> opted_dev[kMaxDevices];
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::atomic<size_t> &opted = opted_dev[dev % kMaxDevices];
     if (opted.load(std::memory_order_relaxed) < smem) {
         CUDA_TRY(cudaFuncSetAttribute(acb_pair_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(acb_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
