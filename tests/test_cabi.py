@@ -47,6 +47,9 @@ def test_host_calls_work_without_a_gpu_and_scan_fails_loudly():
         assert rc == N.ACB_ECUDA and N.last_error()                            # no silent CPU fallback
         with pytest.raises(N.NativeError):
             N.check(rc)
+    st = ctypes.c_int32(7)
+    assert L.acb_table_set_long_state(None, 0) == N.ACB_EINVAL                 # iter_long streaming state: no table, no state
+    assert L.acb_table_get_long_state(None, ctypes.byref(st)) == N.ACB_EINVAL
     L.acb_trie_free(t)
     assert L.acb_trie_new(3) is None and "letter_bytes" in N.last_error()
 
