@@ -97,6 +97,11 @@ int64_t acb_trie_nodes(const acb_trie *t);         /* live nodes  (get_stats nod
 int64_t acb_trie_links(const acb_trie *t);         /* live edges  (get_stats links_count)    */
 int64_t acb_trie_host_bytes(const acb_trie *t);    /* bytes of the node arena + edge table (get_stats total_size) */
 
+/* The ids of the live keys in the order in which the reference's keys() / values() / items() yield them: a pre-order
+ * walk that takes a node's most recently linked child first (its iterator pushes the children in array order and pops
+ * the last, src/AutomatonItemsIter.c:125-288).  *n = number of live keys; ACB_EOVERFLOW when cap is smaller. */
+int acb_trie_key_order(const acb_trie *t, int32_t *out, int64_t cap, int64_t *n);
+
 /* Read-only view of the flattened automaton (valid until the trie changes).
  * State ids are BFS order, root = 0.  Used for upload and for white-box tests. */
 typedef struct acb_flat_view {

@@ -69,6 +69,7 @@ def lib() -> ctypes.CDLL:
         "acb_trie_nodes": (i64, [vp]),
         "acb_trie_links": (i64, [vp]),
         "acb_trie_host_bytes": (i64, [vp]),
+        "acb_trie_key_order": (ctypes.c_int, [vp, vp, i64, pi64]),
         "acb_trie_content_hash": (ctypes.c_uint64, [vp]),
         "acb_trie_flat_save": (ctypes.c_int, [vp, vp, i64, ctypes.POINTER(i64)]),
         "acb_trie_flat_load": (ctypes.c_int, [vp, vp, i64]),
@@ -109,7 +110,7 @@ def lib() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "acb_trie_new", "acb_trie_free", "acb_trie_clear", "acb_trie_add_word", "acb_trie_remove_word",
     "acb_trie_find", "acb_trie_longest_prefix", "acb_trie_make_automaton", "acb_trie_kind",
-    "acb_trie_count", "acb_trie_longest_word", "acb_trie_nodes", "acb_trie_links", "acb_trie_host_bytes", "acb_trie_flat_view",
+    "acb_trie_count", "acb_trie_longest_word", "acb_trie_nodes", "acb_trie_links", "acb_trie_host_bytes", "acb_trie_key_order", "acb_trie_flat_view",
     "acb_trie_content_hash", "acb_trie_flat_save", "acb_trie_flat_load",
     "acb_trie_export_nodes", "acb_trie_import_nodes", "acb_node_records_span",
     "acb_device_count", "acb_table_upload", "acb_table_free", "acb_table_device_bytes",

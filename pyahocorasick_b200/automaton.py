@@ -404,7 +404,14 @@ class Automaton:
                 raise ValueError("The optional how third argument must be one of: "
                                  "MATCH_EXACT_LENGTH, MATCH_AT_LEAST_PREFIX or MATCH_AT_LEAST_PREFIX")
         version = self._version
-        live = [(k, self._values[i]) for i, k in enumerate(self._key_objs) if k is not None]
+        # the reference's order: a pre-order walk of the trie that takes a node's youngest child first
+        # (src/AutomatonItemsIter.c:125-288); the host trie knows it (acb_trie_key_order)
+        n_live = len(self)
+        order = np.empty(max(n_live, 1), dtype=np.int32)
+        got = ctypes.c_int64(0)
+        N.check(self._lib.acb_trie_key_order(self._trie, N.ptr(order), n_live, ctypes.byref(got)))
+        ko, vals = self._key_objs, self._values
+        live = [(ko[i], vals[i]) for i in order[:got.value].tolist()]
         if prefix is None:
             sel = live
         else:
@@ -453,7 +460,7 @@ class Automaton:
         """src/Automaton.c:1044-1097.  nodes / links / words / longest_word describe the trie of LETTERS exactly as
         the reference counts them (one node per letter, also for 2- and 4-byte letters; longest_word is the depth
         of the live trie, so unlike the attribute behind `save` it shrinks when the longest key is removed);
-        sizeof_node / total_size are this implementation's own host memory: 28-byte arena nodes, one per BYTE of
+        sizeof_node / total_size are this implementation's own host memory: 32-byte arena nodes, one per BYTE of
         a letter, plus the edge table that indexes wide fan-outs (acb_trie_host_bytes)."""
         byte_nodes = int(self._lib.acb_trie_nodes(self._trie))
         nodes, links = byte_nodes, int(self._lib.acb_trie_links(self._trie))
@@ -463,7 +470,7 @@ class Automaton:
                                                     ctypes.byref(need), ctypes.byref(n), None, None, 0))
             nodes, links = n.value, max(n.value - 1, 0)
         longest = max((len(k) for k in self._key_objs if k is not None), default=0)
-        node_bytes = 28                                   # arena Node in csrc/acb_host.cpp
+        node_bytes = 32                                   # arena Node in csrc/acb_host.cpp
         return dict(nodes_count=nodes, words_count=len(self), longest_word=longest, links_count=links,
                     sizeof_node=node_bytes, total_size=int(self._lib.acb_trie_host_bytes(self._trie)))
 

@@ -94,6 +94,9 @@ struct Node {
     int32_t next_sibling;
     int32_t key_id;        /* -1 = not the end of a key ("eow" false) */
     int32_t live_below;    /* live keys ending at or below this node; 0 = pruned */
+    uint32_t birth;        /* stamp of the moment the link to this node was (last) made: the reference appends a child to
+                              its parent's array then (src/trienode.c:125-147) and deletes it again when no key is left below
+                              (src/trie.c:66-136), so this orders siblings the way its traversals see them */
     uint8_t byte;
     uint8_t n_children;    /* saturates at 255; children beyond the kListed-th are also in the edge table */
 };
@@ -116,6 +119,7 @@ struct acb_trie {
     int64_t count = 0;          /* live keys */
     int64_t longest = 0;        /* letters; like the reference it never shrinks on removal */
     int64_t live_nodes = 0;     /* nodes with live_below > 0, root included once it exists */
+    uint32_t birth_ctr = 0;     /* Node::birth stamps */
     std::vector<Node> nodes;
     EdgeMap edges;
     Flat flat;
@@ -128,6 +132,7 @@ static int32_t new_node(acb_trie *t, int32_t parent, uint8_t byte) {
     n.first_child = n.last_child = n.next_sibling = -1;
     n.key_id = -1;
     n.live_below = 0;
+    n.birth = ++t->birth_ctr;
     n.byte = byte;
     n.n_children = 0;
     t->nodes.push_back(n);
@@ -200,7 +205,10 @@ extern "C" int acb_trie_add_word(acb_trie *t, const uint8_t *key, int64_t nbytes
         if (prev < 0) {                                      /* a new key: src/trie.c:52-56 */
             t->count += 1;
             for (int32_t x = nd; x >= 0; x = t->nodes[x].parent) {
-                if (x != 0 && t->nodes[x].live_below == 0) t->live_nodes += 1;   /* the root is always live */
+                if (x != 0 && t->nodes[x].live_below == 0) {                     /* the root is always live */
+                    t->live_nodes += 1;
+                    t->nodes[x].birth = ++t->birth_ctr;                          /* (re)linked now: last among its siblings */
+                }
                 t->nodes[x].live_below += 1;
             }
             int64_t letters = nbytes / t->letter_bytes;      /* src/Automaton.c:285-286 */
@@ -924,7 +932,8 @@ static inline uint32_t get_u32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4);
 
 struct LetterEdge { uint32_t letter; int32_t node; };
 
-/* live letter-children of arena node a: every live node L bytes below it, in sibling (insertion) order */
+/* live letter-children of arena node a: every live node L bytes below it, in the order in which the reference holds
+ * them in the node's child array -- the order in which the links were made (Node::birth of the letter's last byte) */
 static void letter_children(const acb_trie *t, int32_t a, std::vector<LetterEdge> &out, std::vector<LetterEdge> &tmp) {
     const int L = t->letter_bytes;
     out.clear();
@@ -936,9 +945,42 @@ static void letter_children(const acb_trie *t, int32_t a, std::vector<LetterEdge
                 if (t->nodes[c].live_below > 0) tmp.push_back({e.letter | ((uint32_t)t->nodes[c].byte << (8 * d)), c});
         out.swap(tmp);
     }
+    if (out.size() > 1)
+        std::sort(out.begin(), out.end(), [t](const LetterEdge &x, const LetterEdge &y) { return t->nodes[x.node].birth < t->nodes[y.node].birth; });
 }
 
 } // namespace
+
+/* Key ids in the order in which the reference's keys() / values() / items() yield them: its iterator keeps a stack, pushes
+ * a node's children in array order and pops the last one first (src/AutomatonItemsIter.c:125-288) -- a pre-order walk
+ * that takes the youngest child first. */
+extern "C" int acb_trie_key_order(const acb_trie *t, int32_t *out, int64_t cap, int64_t *n) {
+    if (!t || !n || cap < 0 || (cap && !out)) { acb_set_error("bad argument"); return ACB_EINVAL; }
+    *n = 0;
+    if (t->nodes.empty() || t->count == 0) return ACB_OK;
+    try {
+        std::vector<int32_t> stack;
+        std::vector<LetterEdge> kids, tmp;
+        stack.push_back(0);
+        int64_t k = 0;
+        while (!stack.empty()) {
+            const int32_t a = stack.back();
+            stack.pop_back();
+            if (t->nodes[a].key_id >= 0) {
+                if (k < cap) out[k] = t->nodes[a].key_id;
+                k++;
+            }
+            letter_children(t, a, kids, tmp);
+            for (const LetterEdge &e : kids) stack.push_back(e.node);          /* the youngest ends up on top */
+        }
+        *n = k;
+        if (k > cap) { acb_set_error("key order: room for %lld ids, %lld keys", (long long)cap, (long long)k); return ACB_EOVERFLOW; }
+        return ACB_OK;
+    } catch (const std::exception &) {
+        acb_set_error("out of memory");
+        return ACB_ENOMEM;
+    }
+}
 
 extern "C" int acb_trie_export_nodes(const acb_trie *t, int letter_width, const int64_t *value_of_key, int64_t n_values,
                                      uint8_t *out, int64_t cap, int64_t *need_bytes, int64_t *n_nodes,

@@ -18,7 +18,7 @@ def _call(obj, name, *args):
     try:
         r = getattr(obj, name)(*args)
         if name in ("keys", "values", "items"):
-            r = sorted(r, key=repr)
+            r = list(r)            # NOT sorted: the order is the reference's trie walk (acb_trie_key_order)
         return ("ok", r)
     except Exception as e:  # noqa: BLE001
         return ("exc", type(e).__name__)
@@ -144,3 +144,55 @@ def test_get_stats_counts_the_letter_trie_like_the_reference(fl):
         assert sorted(a) == sorted(r)
         for k in ("nodes_count", "words_count", "longest_word", "links_count"):
             assert a[k] == r[k], (k, ws)
+
+
+def _mask_padding(chunks, letter_width):
+    """node records of a pickle (src/Automaton_pickle.c:128-188) with the three padding bytes of every node header
+    zeroed: the reference dumps its structs raw, uninitialised padding included"""
+    out = []
+    for ch in chunks:
+        b = bytearray(ch)
+        pos = 8                                       # a chunk starts with its node count
+        while pos + 24 <= len(b):
+            n = int.from_bytes(b[pos + 16:pos + 20], "little")
+            b[pos + 21:pos + 24] = b"\0\0\0"
+            pos += 24 + n * (letter_width + 8)
+        out.append(bytes(b))
+    return out
+
+
+@pytest.mark.parametrize("fl", ["bytes", "unicode"])
+def test_enumeration_order_and_pickle_records_after_removals(fl):
+    """keys() / values() / items() in the reference's order (a pre-order walk that takes the most recently linked child
+    first, src/AutomatonItemsIter.c:125-288) and __reduce__ records identical to the reference's (pre-order, children in
+    link order, src/trie.c:197-213) -- also after remove_word and re-adding, when a re-made link goes to the END of its
+    parent's child array in the reference (src/trie.c:66-136, src/trienode.c:125-147)"""
+    from pyahocorasick_b200 import serialize
+    ref, mod = oracle.ref_module(fl), ac.flavour(fl)
+    rng = np.random.default_rng(2026)
+    al = "ab\u0142\U0001f600" if fl == "unicode" else "abcd"
+    for trial in range(150):
+        R, A = ref.Automaton(), mod.Automaton()
+        live = []
+        for _ in range(int(rng.integers(1, 30))):
+            if live and rng.integers(0, 3) == 0:
+                k = live.pop(int(rng.integers(0, len(live))))
+                assert R.remove_word(k) == A.remove_word(k)
+            else:
+                w = "".join(al[int(j)] for j in rng.integers(0, len(al), size=int(rng.integers(1, 6))))
+                k = w.encode() if fl == "bytes" else w
+                v = int(rng.integers(0, 1000))
+                R.add_word(k, v), A.add_word(k, v)
+                if k not in live:
+                    live.append(k)
+        if trial % 2:
+            R.make_automaton(), A.make_automaton()
+        assert list(R.values()) == list(A.values())
+        if fl == "unicode":                               # the bytes build of the reference mangles the keys it returns
+            assert list(R.keys()) == list(A.keys()) and list(R.items()) == list(A.items())
+        if not live:
+            continue
+        pr, pa = R.__reduce__()[1], serialize.reduce_args(A)
+        lw = 4 if fl == "unicode" else 2
+        assert _mask_padding(pr[0], lw) == _mask_padding(pa[0], lw)
+        assert tuple(pr[1:]) == tuple(pa[1:])
